@@ -1,0 +1,173 @@
+"""Role-named weight sets for the NUNet-TLS path and the packed blob the C-ABI consumes.
+
+A *weight set* is `{"<layer>/<var>": float32 ndarray}` in the reference's own (Keras) tensor
+layouts, where `<layer>` is the layer's *role* in `models/proposed.py:284-625`
+(`msfe6_en_conv1`, `msfe4_de2_spconv3`, `lstm`, `out_conv`, ...) and `<var>` one of
+`kernel, bias, gamma, beta, alpha` (conv units), `kernel0, bias0, kernel1, bias1` (the two 1x1
+layers of a CTFA time/frequency attention MLP), `kernel, recurrent_kernel, bias` (LSTM).
+
+The `.h5` groups weights by the *training model's* layer names, and six decoder Dense layers are
+mis-named there (`proposed.py:47-63`); Keras loads them topologically (`converter_proposed.py:13`),
+so the role -> group remap below is part of the format.
+"""
+from __future__ import annotations
+
+import re
+import struct
+from typing import Dict
+
+import numpy as np
+
+from .h5_reader import read_h5
+
+MAGIC = b"NUNETW01"
+VARIANT_LSTM = 0
+VARIANT_DDB = 1
+_ENTRY = struct.Struct("<64sI4IQ8x")  # name, ndim, dims[4], offset (floats), pad -> 96 bytes
+
+# role (Dense that follows <role>_lstm) -> h5 group that actually holds it (proposed.py:47-63)
+DENSE_ROLE_TO_H5 = {
+    "msfe3_de_dense": "msfe6_de_dense",
+    "msfe4_de_dense": "msfe5_de_dense",
+    "msfe4_de2_dense": "msfe4_de_dense",
+    "msfe4_de3_dense": "msfe4_de2_dense",
+    "msfe5_de_dense": "msfe4_de3_dense",
+    "msfe6_de_dense": "msfe3_de_dense",
+}
+_H5_TO_DENSE_ROLE = {v: k for k, v in DENSE_ROLE_TO_H5.items()}
+
+# (block prefix, F0, depth n) in network order; encoder side then decoder side (proposed.py:297-613)
+ENC_BLOCKS = [("msfe6_en", 256, 6), ("msfe5_en", 128, 5), ("msfe4_en", 64, 4),
+              ("msfe4_en2", 32, 4), ("msfe4_en3", 16, 4), ("msfe3_en", 8, 3)]
+DEC_BLOCKS = [("msfe3_de", 8, 3), ("msfe4_de", 16, 4), ("msfe4_de2", 32, 4),
+              ("msfe4_de3", 64, 4), ("msfe5_de", 128, 5), ("msfe6_de", 256, 6)]
+DOWN_NAMES = ["msfe6_down_sampling", "msfe5_down_sampling", "msfe4_down_sampling",
+              "msfe4_down_sampling2", "msfe4_down_sampling3", "msfe3_down_sampling"]
+UP_NAMES = ["msfe3_upsampling", "msfe4_upsampling", "msfe4_upsampling2",
+            "msfe4_upsampling3", "msfe5_upsampling", "msfe6_upsampling"]
+
+
+def _suffix(name: str) -> int:
+    m = re.search(r"_(\d+)$", name)
+    return int(m.group(1)) if m else 0
+
+
+def lstm_weights_from_h5(path: str) -> Dict[str, np.ndarray]:
+    """Role-named float32 weight set of NUNet-TLS-LSTM from the reference `.h5`."""
+    raw = read_h5(path)
+    groups: Dict[str, Dict[str, Dict[str, np.ndarray]]] = {}
+    for key, arr in raw.items():
+        parts = key.strip("/").split("/")
+        group, sub, var = parts[0], parts[-2], parts[-1].split(":")[0]
+        groups.setdefault(group, {}).setdefault(sub, {})[var] = arr.astype(np.float32)
+
+    out: Dict[str, np.ndarray] = {}
+    for group, subs in groups.items():
+        role = _H5_TO_DENSE_ROLE.get(group, group)
+        if group == "conv2d":
+            role = "out_conv"
+        mlp = 0
+        for sub in sorted(subs, key=lambda s: (_suffix(s), s)):
+            v = subs[sub]
+            if sub.startswith("layer_normalization"):
+                out[f"{role}/gamma"], out[f"{role}/beta"] = v["gamma"], v["beta"]
+            elif sub.startswith("p_re_lu"):
+                out[f"{role}/alpha"] = v["alpha"].reshape(1)
+            elif sub.startswith("lstm_cell"):
+                out[f"{role}/kernel"] = v["kernel"]
+                out[f"{role}/recurrent_kernel"] = v["recurrent_kernel"]
+                out[f"{role}/bias"] = v["bias"]
+            elif role.endswith("_ta") or role.endswith("_fa"):
+                out[f"{role}/kernel{mlp}"] = v["kernel"].reshape(v["kernel"].shape[-2:])
+                out[f"{role}/bias{mlp}"] = v["bias"]
+                mlp += 1
+            else:  # Conv2D / Conv2DTranspose / Dense
+                out[f"{role}/kernel"], out[f"{role}/bias"] = v["kernel"], v["bias"]
+    return out
+
+
+def expected_lstm_shapes() -> Dict[str, tuple]:
+    """Shape table of the LSTM variant, derived from the topology, used to validate a set."""
+    s: Dict[str, tuple] = {}
+
+    def unit(name, kshape, ln):
+        s[f"{name}/kernel"] = kshape
+        s[f"{name}/bias"] = (kshape[-1],)
+        if ln:
+            s[f"{name}/gamma"] = s[f"{name}/beta"] = (ln,)
+            s[f"{name}/alpha"] = (1,)
+
+    unit("input_layer", (1, 1, 1, 64), 64)
+    for side, blocks in (("en", ENC_BLOCKS), ("de", DEC_BLOCKS)):
+        for name, f0, n in blocks:
+            unit(f"{name}_in", (1, 1, 64 if side == "en" else 128, 64), 64)
+            for k in range(1, n + 1):
+                if side == "en":
+                    cin = 64 if k == 1 else 32
+                else:
+                    cin = 128 if k == 1 else 64
+                unit(f"{name}_conv{k}", (2, 3, cin, 32), 32)
+            d = (f0 >> n) * 32
+            s[f"{name}_lstm/kernel"] = (d, 84)
+            s[f"{name}_lstm/recurrent_kernel"] = (21, 84)
+            s[f"{name}_lstm/bias"] = (84,)
+            s[f"{name}_dense/kernel"] = (21, d)
+            s[f"{name}_dense/bias"] = (d,)
+            for k in range(1, n + 1):
+                co = 64 if k == n else 32
+                unit(f"{name}_spconv{k}", (2, 3, 64, 2 * co), co)
+            for att in ("ta", "fa"):
+                s[f"{name}_{att}/kernel0"] = (64, 16)
+                s[f"{name}_{att}/bias0"] = (16,)
+                s[f"{name}_{att}/kernel1"] = (16, 64)
+                s[f"{name}_{att}/bias1"] = (64,)
+    for dn in DOWN_NAMES:
+        unit(dn, (1, 3, 64, 64), 0)
+    for un in UP_NAMES:
+        s[f"{un}/kernel"] = (1, 3, 128, 128)
+        s[f"{un}/bias"] = (128,)
+    s["lstm/kernel"], s["lstm/recurrent_kernel"], s["lstm/bias"] = (256, 84), (21, 84), (84,)
+    s["dense/kernel"], s["dense/bias"] = (21, 256), (256,)
+    unit("out_conv", (1, 1, 64, 1), 0)
+    return s
+
+
+def validate(weights: Dict[str, np.ndarray], shapes: Dict[str, tuple]) -> None:
+    missing = sorted(set(shapes) - set(weights))
+    extra = sorted(set(weights) - set(shapes))
+    if missing or extra:
+        raise ValueError(f"weight set mismatch: missing {missing[:5]} extra {extra[:5]}")
+    for k, shp in shapes.items():
+        if tuple(weights[k].shape) != tuple(shp):
+            raise ValueError(f"{k}: shape {weights[k].shape} != expected {shp}")
+
+
+def pack_blob(weights: Dict[str, np.ndarray], variant: int = VARIANT_LSTM) -> bytes:
+    """Serialise a weight set into the blob `nunet_create` takes (include/nunet_b200.h)."""
+    names = sorted(weights)
+    head = bytearray(MAGIC + struct.pack("<II", len(names), variant))
+    data = []
+    off = 0
+    for n in names:
+        a = np.ascontiguousarray(weights[n], dtype="<f4")
+        if a.ndim > 4 or len(n.encode()) > 63:
+            raise ValueError(f"cannot pack {n} {a.shape}")
+        dims = list(a.shape) + [0] * (4 - a.ndim)
+        head += _ENTRY.pack(n.encode(), a.ndim, *dims, off)
+        data.append(a.tobytes())
+        off += a.size
+    return bytes(head) + b"".join(data)
+
+
+def unpack_blob(blob: bytes):
+    if blob[:8] != MAGIC:
+        raise ValueError("bad blob magic")
+    n, variant = struct.unpack_from("<II", blob, 8)
+    base = 16 + n * _ENTRY.size
+    out = {}
+    for i in range(n):
+        name, ndim, d0, d1, d2, d3, off = _ENTRY.unpack_from(blob, 16 + i * _ENTRY.size)
+        shape = (d0, d1, d2, d3)[:ndim]
+        cnt = int(np.prod(shape)) if shape else 1
+        out[name.rstrip(b"\0").decode()] = np.frombuffer(blob, "<f4", cnt, base + 4 * off).reshape(shape).copy()
+    return out, variant
