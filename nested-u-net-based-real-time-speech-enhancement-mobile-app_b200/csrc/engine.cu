@@ -1,0 +1,1031 @@
+// Host engine + C ABI (include/nunet_b200.h) of the B200-native NUNet-TLS-LSTM inference path.
+//
+// The engine turns the reference topology (models/proposed.py:284-625 offline; the one-frame stateful
+// form converter_proposed.py:188-867) into a static list of kernel launches ("plan") over a pre-sized
+// HBM arena.  Two plans are built from the same topology code:
+//   offline  : tensors are [max_frames][F][C]; the previous-frame tap of a conv is the same tensor one
+//              frame earlier (zero at t = 0); scratch tensors of one nested sub-U-Net are recycled by the next.
+//   streaming: tensors are [max_streams][F][C] x 2 (ping-pong by step parity); the previous-frame tap is the
+//              other parity's buffer, so the reference's 104 conv-history tensors are simply last step's
+//              activations and never copied.  LSTM h/c are [max_streams][21], updated in place.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/nunet_b200.h"
+#include "conv_simt.cuh"
+#include "framing.cuh"
+#include "misc_kernels.cuh"
+
+namespace nunet {
+
+// ------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+[[noreturn]] static void fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    throw Error(code, buf);
+}
+
+#define CUDA_OK(expr)                                                                           \
+    do {                                                                                        \
+        cudaError_t e_ = (expr);                                                                \
+        if (e_ != cudaSuccess) fail(NUNET_ECUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------ weight blob
+struct Arr {
+    std::vector<int> dims;
+    const float* data = nullptr;
+    size_t n = 0;
+};
+
+struct Blob {
+    std::map<std::string, Arr> m;
+    int variant = 0;
+    void parse(const void* blob, size_t bytes) {
+        const uint8_t* p = static_cast<const uint8_t*>(blob);
+        if (bytes < 16 || memcmp(p, "NUNETW01", 8) != 0) fail(NUNET_EINVAL, "weight blob: bad magic");
+        uint32_t cnt, var;
+        memcpy(&cnt, p + 8, 4);
+        memcpy(&var, p + 12, 4);
+        variant = (int)var;
+        const size_t ENTRY = 96;
+        const size_t base = 16 + (size_t)cnt * ENTRY;
+        if (bytes < base) fail(NUNET_EINVAL, "weight blob: truncated table");
+        for (uint32_t i = 0; i < cnt; ++i) {
+            const uint8_t* e = p + 16 + i * ENTRY;
+            char name[65];
+            memcpy(name, e, 64);
+            name[64] = 0;
+            uint32_t ndim, d[4];
+            uint64_t off;
+            memcpy(&ndim, e + 64, 4);
+            memcpy(d, e + 68, 16);
+            memcpy(&off, e + 84, 8);
+            if (ndim > 4) fail(NUNET_EINVAL, "weight blob: %s has rank %u", name, ndim);
+            Arr a;
+            a.n = 1;
+            for (uint32_t k = 0; k < ndim; ++k) {
+                a.dims.push_back((int)d[k]);
+                a.n *= d[k];
+            }
+            if (base + (off + a.n) * 4 > bytes) fail(NUNET_EINVAL, "weight blob: %s out of range", name);
+            a.data = reinterpret_cast<const float*>(p + base + off * 4);
+            m[name] = a;
+        }
+    }
+    const Arr& get(const std::string& name, std::initializer_list<int> dims = {}) const {
+        auto it = m.find(name);
+        if (it == m.end()) fail(NUNET_EINVAL, "weight blob: missing tensor %s", name.c_str());
+        if (dims.size()) {
+            std::vector<int> want(dims);
+            if (want != it->second.dims) fail(NUNET_EINVAL, "weight blob: %s has an unexpected shape", name.c_str());
+        }
+        return it->second;
+    }
+};
+
+// All packed parameters live in one device allocation; layers hold float offsets into it.
+struct ParamPool {
+    std::vector<float> host;
+    float* dev = nullptr;
+    size_t add(const float* p, size_t n) {
+        size_t off = (host.size() + 63) & ~size_t(63);
+        host.resize(off + n);
+        memcpy(host.data() + off, p, n * sizeof(float));
+        return off;
+    }
+    size_t add(const std::vector<float>& v) { return add(v.data(), v.size()); }
+    void upload() {
+        CUDA_OK(cudaMalloc(&dev, host.size() * sizeof(float) + 256));
+        CUDA_OK(cudaMemcpy(dev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    const float* at(size_t off) const { return dev + off; }
+    ~ParamPool() {
+        if (dev) cudaFree(dev);
+    }
+};
+
+struct ConvLayer {
+    size_t w = 0, bias = 0, gamma = 0, beta = 0, alpha = 0;
+    int CA = 0, CB = 0, COUT = 0, KT = 1, KF = 1, padl = 0, stride = 1, epi = EPI_LN;
+};
+struct MlpLayer {
+    size_t k0, b0, k1, b1;
+};
+struct LstmLayer {
+    size_t wk, wr, wb, dk, db;
+    int D;
+};
+struct VecLayer {   // input_layer / out_conv
+    size_t w, b, gamma, beta, alpha;
+};
+
+static int conv_cn(int COUT) { return COUT == 32 ? 4 : 8; }
+
+// kernel: logical [taps][Cin][COUT] -> column-permuted copy for conv_unit_kernel
+static std::vector<float> permute_cols(const std::vector<float>& k, int rows, int COUT) {
+    std::vector<float> out(k.size());
+    const int CN = conv_cn(COUT);
+    for (int r = 0; r < rows; ++r)
+        for (int q = 0; q < COUT; ++q) out[(size_t)r * COUT + q] = k[(size_t)r * COUT + conv_col_to_channel(q, COUT, CN)];
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------ tensors / plans
+struct Ten {
+    int F = 0, C = 0;
+    size_t off[2] = {0, 0};   // float offset per unit (frame / stream) inside the arena; [1] only when ping-ponged
+    bool scratch = false;     // offline: lives on the recyclable stack (offset fixed up by Plan::finalize)
+    bool pingpong = false;    // streaming: two copies selected by step parity
+    std::string name;
+    size_t numel() const { return (size_t)F * C; }
+};
+
+struct Run {   // arguments of one forward / step call
+    int B = 0, T = 0;
+    int parity = 0;
+    cudaStream_t st = nullptr;
+    const float* mag_in = nullptr;   // [B*T][256]
+    float* est_out = nullptr;        // [B*T][est_stride], written at +est_off
+    int est_stride = 256, est_off = 0;
+    int ring_pos = 0;
+};
+
+struct Engine;
+using Op = std::function<void(Engine&, const Run&)>;
+
+// A plan = tensors laid out in one arena + the launch list.  Every tensor is a dense [cap][F*C] block at
+// arena + off*cap.  Offline plans keep two bump stacks: `persistent` (second-level skips, block outputs) and
+// `scratch` (recycled by each nested sub-U-Net); streaming plans keep everything and ping-pong activations.
+struct Plan {
+    bool streaming = false;
+    int cap = 0;                 // frames or streams
+    float* arena = nullptr;
+    size_t unit_floats = 0;      // floats per frame / stream
+    size_t ptop = 0, stop = 0, shigh = 0;
+    std::vector<std::unique_ptr<Ten>> tens;
+    std::map<std::string, Ten*> named;
+    std::vector<Op> ops;
+    // streaming state: reference name (without _prev/_cur) -> up to two tensors concatenated on channels
+    struct StateRef {
+        std::string name;
+        Ten* a = nullptr;
+        Ten* b = nullptr;
+        bool is_lstm = false;    // a = the [21] h or c vector
+    };
+    std::vector<StateRef> states;
+    std::vector<Ten*> rings;
+
+    Ten* make(const std::string& name, int F, int C, bool persistent, bool pingpong = true) {
+        auto t = std::make_unique<Ten>();
+        t->F = F;
+        t->C = C;
+        t->name = name;
+        const size_t n = ((size_t)F * C + 63) & ~size_t(63);
+        if (streaming) {
+            t->pingpong = pingpong;
+            t->off[0] = ptop;
+            ptop += n;
+            if (pingpong) {
+                t->off[1] = ptop;
+                ptop += n;
+            } else {
+                t->off[1] = t->off[0];
+            }
+        } else if (persistent) {
+            t->off[0] = t->off[1] = ptop;
+            ptop += n;
+        } else {
+            t->scratch = true;
+            t->off[0] = t->off[1] = stop;
+            stop += n;
+            if (stop > shigh) shigh = stop;
+        }
+        Ten* raw = t.get();
+        tens.push_back(std::move(t));
+        if (!name.empty()) named[name] = raw;
+        return raw;
+    }
+    size_t mark() const { return stop; }
+    void release(size_t m) { stop = m; }
+    void finalize() {
+        for (auto& t : tens)
+            if (t->scratch) {
+                t->off[0] += ptop;
+                t->off[1] += ptop;
+            }
+        unit_floats = ptop + shigh;
+    }
+    float* ptr(size_t off) const { return arena + off * (size_t)cap; }
+    float* cur(const Ten* t, int parity) const { return ptr(t->off[parity & 1]); }
+    float* prev(const Ten* t, int parity) const { return streaming ? ptr(t->off[(parity ^ 1) & 1]) : nullptr; }
+    ~Plan() {
+        if (arena) cudaFree(arena);
+    }
+};
+
+static const char* ENC_NAMES[6] = {"msfe6_en", "msfe5_en", "msfe4_en", "msfe4_en2", "msfe4_en3", "msfe3_en"};
+static const int ENC_F0[6] = {256, 128, 64, 32, 16, 8};
+static const int ENC_N[6] = {6, 5, 4, 4, 4, 3};
+static const char* DEC_NAMES[6] = {"msfe3_de", "msfe4_de", "msfe4_de2", "msfe4_de3", "msfe5_de", "msfe6_de"};
+static const int DEC_F0[6] = {8, 16, 32, 64, 128, 256};
+static const int DEC_N[6] = {3, 4, 4, 4, 5, 6};
+static const char* DOWN_NAMES[6] = {"msfe6_down_sampling", "msfe5_down_sampling", "msfe4_down_sampling",
+                                    "msfe4_down_sampling2", "msfe4_down_sampling3", "msfe3_down_sampling"};
+static const char* UP_NAMES[6] = {"msfe3_upsampling", "msfe4_upsampling", "msfe4_upsampling2",
+                                  "msfe4_upsampling3", "msfe5_upsampling", "msfe6_upsampling"};
+
+// converter_proposed.py:26-187 naming: block 'msfe4_en2' -> conv history 'msfe4_ee2', spconv history 'msfe4_ed2'
+static void state_prefixes(const std::string& block, std::string& pc, std::string& ps) {
+    const size_t us = block.find('_');
+    const std::string head = block.substr(0, us), tail = block.substr(us + 1);
+    const std::string side = tail.substr(0, 2), idx = tail.substr(2);
+    const char a = side == "en" ? 'e' : 'd';
+    pc = head + "_" + a + "e" + idx;
+    ps = head + "_" + a + "d" + idx;
+}
+
+struct Engine {
+    nunet_config cfg{};
+    Blob blob;
+    ParamPool pool;
+    std::map<std::string, ConvLayer> convs;
+    std::map<std::string, MlpLayer> mlps;
+    std::map<std::string, LstmLayer> lstms;
+    VecLayer in_layer{}, out_layer{};
+    size_t tw_off = 0, win_off = 0, win_stream_off = 0, inv_win_off = 0;
+
+    Plan offline, stream;
+    // offline extras (per frame offsets)
+    Ten *o_mag = nullptr, *o_ph = nullptr, *o_est = nullptr, *o_frames = nullptr;
+    // streaming extras (per stream offsets)
+    Ten *s_mag = nullptr, *s_ph = nullptr, *s_est = nullptr, *s_inbuf = nullptr, *s_outbuf = nullptr;
+    int stream_parity = 0;   // parity of the most recent step (its buffers hold the history)
+    int stream_steps = 0;
+
+    cudaStream_t own_stream = nullptr;
+    float *h_in = nullptr, *h_out = nullptr;   // device staging for the *_host calls
+    size_t h_in_cap = 0, h_out_cap = 0;
+    int launches = 0;
+    int last_B = 0, last_T = 0;
+
+    ~Engine() {
+        if (h_in) cudaFree(h_in);
+        if (h_out) cudaFree(h_out);
+        if (own_stream) cudaStreamDestroy(own_stream);
+    }
+
+    // -------------------------------------------------------------------------------- parameter packing
+    size_t add_arr(const std::string& name, std::initializer_list<int> dims = {}) {
+        const Arr& a = blob.get(name, dims);
+        return pool.add(a.data, a.n);
+    }
+
+    void add_conv(const std::string& role, int CA, int CB, int COUT, int KT, int KF, int padl, int stride, int epi) {
+        const Arr& k = blob.get(role + "/kernel", {KT, KF, CA + CB, COUT});
+        ConvLayer L;
+        L.CA = CA; L.CB = CB; L.COUT = COUT; L.KT = KT; L.KF = KF; L.padl = padl; L.stride = stride; L.epi = epi;
+        std::vector<float> kv(k.data, k.data + k.n);
+        L.w = pool.add(permute_cols(kv, KT * KF * (CA + CB), COUT));
+        L.bias = add_arr(role + "/bias", {COUT});
+        if (epi != EPI_BIAS) {
+            const int cln = (epi == EPI_LN) ? COUT : COUT / 2;
+            L.gamma = add_arr(role + "/gamma", {cln});
+            L.beta = add_arr(role + "/beta", {cln});
+            L.alpha = add_arr(role + "/alpha", {1});
+        }
+        convs[role] = L;
+    }
+
+    // up_sampling (Conv2DTranspose (1,3) stride (1,2) 'same', models/proposed.py:260) followed by the decoder
+    // block's inconv (1x1 + LN + PReLU, :218) with nothing in between: composed into ONE conv unit with two
+    // frequency taps (x[i-1], x[i]) and 2 x 64 output channels that the SHUF64 epilogue scatters to bins 2i, 2i+1.
+    //   u[2i]   = x[i] W0 + x[i-1] W2 + b_up,  u[2i+1] = x[i] W1 + b_up,  z = u Win + b_in
+    void add_up_in(const std::string& up, const std::string& in_role) {
+        const Arr& ku = blob.get(up + "/kernel", {1, 3, 128, 128});      // (kh, kw, Cout, Cin)
+        const Arr& bu = blob.get(up + "/bias", {128});
+        const Arr& ki = blob.get(in_role + "/kernel", {1, 1, 128, 64});  // (1,1,Cin,Cout)
+        const Arr& bi = blob.get(in_role + "/bias", {64});
+        // M[k][ci][m] = sum_co Wup[0,k,co,ci] * Win[co,m]
+        std::vector<double> M(3 * 128 * 64, 0.0);
+        for (int k = 0; k < 3; ++k)
+            for (int co = 0; co < 128; ++co)
+                for (int ci = 0; ci < 128; ++ci) {
+                    const double wu = ku.data[((size_t)k * 128 + co) * 128 + ci];
+                    const float* wi = ki.data + (size_t)co * 64;
+                    double* dst = &M[((size_t)k * 128 + ci) * 64];
+                    for (int m = 0; m < 64; ++m) dst[m] += wu * (double)wi[m];
+                }
+        std::vector<double> bz(64, 0.0);
+        for (int m = 0; m < 64; ++m) {
+            double s = bi.data[m];
+            for (int co = 0; co < 128; ++co) s += (double)bu.data[co] * (double)ki.data[(size_t)co * 64 + m];
+            bz[m] = s;
+        }
+        // conv channel c = 64h + 2i' + j  <->  output bin 2i+h, output channel m = 32j + i'
+        std::vector<float> W(2 * 128 * 128, 0.0f), B(128, 0.0f);
+        for (int c = 0; c < 128; ++c) {
+            const int h = c / 64, ip = (c % 64) / 2, j = c & 1, m = 32 * j + ip;
+            B[c] = (float)bz[m];
+            for (int ci = 0; ci < 128; ++ci) {
+                // tap kf = 0 reads x[i-1]: contributes W2 to the even bin only; tap kf = 1 reads x[i]: W0 (even), W1 (odd)
+                W[((size_t)0 * 128 + ci) * 128 + c] = (h == 0) ? (float)M[((size_t)2 * 128 + ci) * 64 + m] : 0.0f;
+                W[((size_t)1 * 128 + ci) * 128 + c] = (float)M[((size_t)(h == 0 ? 0 : 1) * 128 + ci) * 64 + m];
+            }
+        }
+        ConvLayer L;
+        L.CA = 64; L.CB = 64; L.COUT = 128; L.KT = 1; L.KF = 2; L.padl = 1; L.stride = 1; L.epi = EPI_SHUF64;
+        L.w = pool.add(permute_cols(W, 2 * 128, 128));
+        L.bias = pool.add(B);
+        L.gamma = add_arr(in_role + "/gamma", {64});
+        L.beta = add_arr(in_role + "/beta", {64});
+        L.alpha = add_arr(in_role + "/alpha", {1});
+        convs[in_role] = L;
+    }
+
+    void add_mlp(const std::string& role) {
+        MlpLayer m;
+        m.k0 = add_arr(role + "/kernel0", {64, 16});
+        m.b0 = add_arr(role + "/bias0", {16});
+        m.k1 = add_arr(role + "/kernel1", {16, 64});
+        m.b1 = add_arr(role + "/bias1", {64});
+        mlps[role] = m;
+    }
+    void add_lstm(const std::string& lstm, const std::string& dense, int D) {
+        LstmLayer l;
+        l.D = D;
+        l.wk = add_arr(lstm + "/kernel", {D, LSTM_GATES});
+        l.wr = add_arr(lstm + "/recurrent_kernel", {LSTM_UNITS, LSTM_GATES});
+        l.wb = add_arr(lstm + "/bias", {LSTM_GATES});
+        l.dk = add_arr(dense + "/kernel", {LSTM_UNITS, D});
+        l.db = add_arr(dense + "/bias", {D});
+        lstms[lstm] = l;
+    }
+
+    void pack_params() {
+        if (blob.variant != NUNET_VARIANT_LSTM || cfg.variant != NUNET_VARIANT_LSTM)
+            fail(NUNET_EINVAL, "this build implements the NUNet-TLS-LSTM variant only (blob variant %d, cfg %d)",
+                 blob.variant, cfg.variant);
+        in_layer.w = add_arr("input_layer/kernel", {1, 1, 1, 64});
+        in_layer.b = add_arr("input_layer/bias", {64});
+        in_layer.gamma = add_arr("input_layer/gamma", {64});
+        in_layer.beta = add_arr("input_layer/beta", {64});
+        in_layer.alpha = add_arr("input_layer/alpha", {1});
+        out_layer.w = add_arr("out_conv/kernel", {1, 1, 64, 1});
+        out_layer.b = add_arr("out_conv/bias", {1});
+        for (int side = 0; side < 2; ++side)
+            for (int i = 0; i < 6; ++i) {
+                const std::string blk = side ? DEC_NAMES[i] : ENC_NAMES[i];
+                const int n = side ? DEC_N[i] : ENC_N[i];
+                const int F0 = side ? DEC_F0[i] : ENC_F0[i];
+                if (side == 0) add_conv(blk + "_in", 64, 0, 64, 1, 1, 0, 1, EPI_LN);
+                else add_up_in(UP_NAMES[i], blk + "_in");
+                for (int k = 1; k <= n; ++k) {
+                    int CA, CB;
+                    if (side == 0) { CA = (k == 1) ? 64 : 32; CB = 0; }
+                    else { CA = (k == 1) ? 64 : 32; CB = CA; }
+                    add_conv(blk + "_conv" + std::to_string(k), CA, CB, 32, 2, 3, 1, 2, EPI_LN);
+                }
+                add_lstm(blk + "_lstm", blk + "_dense", (F0 >> n) * 32);
+                for (int k = 1; k <= n; ++k) {
+                    const bool last = (k == n);
+                    add_conv(blk + "_spconv" + std::to_string(k), 32, 32, last ? 128 : 64, 2, 3, 1, 1,
+                             last ? EPI_SHUF64 : EPI_SHUF32);
+                }
+                add_mlp(blk + "_ta");
+                add_mlp(blk + "_fa");
+                if (side == 0) add_conv(DOWN_NAMES[i], 64, 0, 64, 1, 3, 0, 2, EPI_BIAS);
+            }
+        add_lstm("lstm", "dense", 256);
+
+        // framing tables (tf.signal.hann_window periodic; inverse_stft_window_fn(256); interpreter_proposed.py:21-26)
+        std::vector<float> tw(512), win(512), wins(512), inv(512);
+        const double PI = 3.14159265358979323846;
+        for (int k = 0; k < 256; ++k) {
+            tw[2 * k] = (float)cos(2.0 * PI * k / 512.0);
+            tw[2 * k + 1] = (float)(-sin(2.0 * PI * k / 512.0));
+        }
+        for (int i = 0; i < 512; ++i) win[i] = (float)(0.5 - 0.5 * cos(2.0 * PI * i / 512.0));
+        wins = win;
+        wins[0] = 1e-7f;
+        wins[511] = 1e-7f;
+        for (int i = 0; i < 512; ++i) {
+            const float a = win[i], b = win[(i + 256) % 512];
+            inv[i] = a / (a * a + b * b);
+        }
+        tw_off = pool.add(tw);
+        win_off = pool.add(win);
+        win_stream_off = pool.add(wins);
+        inv_win_off = pool.add(inv);
+        pool.upload();
+    }
+
+    FramingTables tables(bool streaming) const {
+        FramingTables t;
+        t.tw = reinterpret_cast<const float2*>(pool.at(tw_off));
+        t.win = pool.at(streaming ? win_stream_off : win_off);
+        t.inv_win = pool.at(inv_win_off);
+        return t;
+    }
+
+    // -------------------------------------------------------------------------------- launches
+    void check_launch(const char* what) {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) fail(NUNET_ECUDA, "launch %s: %s", what, cudaGetErrorString(e));
+        ++launches;
+    }
+
+    template <int COUT, int CN, int PM, int NT, int EPI>
+    void launch_conv_t(const ConvParams& p, int grid, size_t smem, cudaStream_t st) {
+        static bool attr_set = false;
+        auto kfn = conv_unit_kernel<COUT, CN, PM, NT, EPI>;
+        if (!attr_set) {
+            CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            attr_set = true;
+        }
+        kfn<<<grid, NT, smem, st>>>(p);
+        check_launch("conv_unit");
+    }
+
+    void launch_conv(const ConvLayer& L, const float* a_cur, const float* a_prev, const float* b_cur,
+                     const float* b_prev, float* out, int B, int T, bool has_prev, int F_in, cudaStream_t st) {
+        ConvParams p;
+        p.a_cur = a_cur; p.a_prev = a_prev; p.b_cur = b_cur; p.b_prev = b_prev;
+        p.w = pool.at(L.w); p.bias = pool.at(L.bias);
+        p.gamma = pool.at(L.gamma); p.beta = pool.at(L.beta); p.alpha = pool.at(L.alpha);
+        p.out = out;
+        p.CA = L.CA; p.CB = L.CB; p.B = B; p.T = T; p.has_prev = has_prev ? 1 : 0;
+        p.F_in = F_in;
+        p.F_out = (L.stride == 2) ? F_in / 2 : F_in;
+        p.KT = L.KT; p.KF = L.KF; p.padl = L.padl; p.stride = L.stride;
+        // tile geometry: 128 pixels = G clips x TT frames x FT bins
+        int lFT = 0;
+        while ((1 << (lFT + 1)) <= p.F_out && (1 << (lFT + 1)) <= 32) ++lFT;
+        const int FT = 1 << lFT;
+        int rem = CONV_P / FT;
+        int tcap = (FT == 32) ? 4 : 8;
+        int lTT = 0;
+        while ((1 << (lTT + 1)) <= rem && (1 << (lTT + 1)) <= tcap && (1 << lTT) < T) ++lTT;
+        int lG = 0;
+        while ((1 << (lG + 1)) <= rem >> lTT) ++lG;
+        const int Cmax = L.CA > L.CB ? L.CA : L.CB;
+        const size_t wbytes = 2 * CONV_KC * L.COUT * sizeof(float);
+        const size_t budget = 200 * 1024;
+        while (lG > 0 && wbytes + sizeof(float) * conv_tile_floats(1 << lG, 1 << lTT, FT, L.KT, L.KF, L.stride, Cmax) > budget) --lG;
+        // no point in more clip slots than clips
+        while (lG > 0 && (1 << (lG - 1)) >= B) --lG;
+        p.lFT = lFT; p.lTT = lTT; p.lG = lG;
+        const size_t smem = wbytes + sizeof(float) * conv_tile_floats(1 << lG, 1 << lTT, FT, L.KT, L.KF, L.stride, Cmax);
+        if (smem > 220 * 1024) fail(NUNET_EINVAL, "conv tile does not fit shared memory (%zu bytes)", smem);
+        const int nfb = p.F_out >> lFT, ntb = (T + (1 << lTT) - 1) >> lTT, nbg = (B + (1 << lG) - 1) >> lG;
+        const long long grid = (long long)nfb * ntb * nbg;
+        if (grid <= 0 || grid > 0x7fffffffLL) fail(NUNET_EINVAL, "conv grid out of range");
+        if (L.COUT == 32 && L.epi == EPI_LN) launch_conv_t<32, 4, 8, 128, EPI_LN>(p, (int)grid, smem, st);
+        else if (L.COUT == 64 && L.epi == EPI_LN) launch_conv_t<64, 8, 4, 256, EPI_LN>(p, (int)grid, smem, st);
+        else if (L.COUT == 64 && L.epi == EPI_BIAS) launch_conv_t<64, 8, 4, 256, EPI_BIAS>(p, (int)grid, smem, st);
+        else if (L.COUT == 64 && L.epi == EPI_SHUF32) launch_conv_t<64, 8, 4, 256, EPI_SHUF32>(p, (int)grid, smem, st);
+        else if (L.COUT == 128 && L.epi == EPI_SHUF64) launch_conv_t<128, 8, 8, 256, EPI_SHUF64>(p, (int)grid, smem, st);
+        else fail(NUNET_EINVAL, "no conv kernel for COUT=%d epi=%d", L.COUT, L.epi);
+    }
+
+    MlpW mlpw(const MlpLayer& m) const { return MlpW{pool.at(m.k0), pool.at(m.b0), pool.at(m.k1), pool.at(m.b1)}; }
+
+    // -------------------------------------------------------------------------------- topology -> plan
+    // conv unit reading one or two tensors
+    Ten* op_conv(Plan& P, const std::string& role, Ten* a, Ten* b, const std::string& out_name, bool persistent) {
+        const ConvLayer& L = convs.at(role);
+        if (a->C != L.CA || (b ? b->C : 0) != L.CB || (b && b->F != a->F)) fail(NUNET_EINVAL, "plan: %s wiring", role.c_str());
+        const int F_in = a->F;
+        const int F_conv = (L.stride == 2) ? F_in / 2 : F_in;
+        const bool shuf = (L.epi == EPI_SHUF32 || L.epi == EPI_SHUF64);
+        Ten* o = P.make(out_name, shuf ? 2 * F_conv : F_conv, shuf ? L.COUT / 2 : L.COUT, persistent);
+        Plan* pp = &P;
+        P.ops.push_back([=](Engine& E, const Run& r) {
+            E.launch_conv(L, pp->cur(a, r.parity), pp->prev(a, r.parity), b ? pp->cur(b, r.parity) : nullptr,
+                          b ? pp->prev(b, r.parity) : nullptr, pp->cur(o, r.parity), r.B, r.T, pp->streaming, F_in, r.st);
+        });
+        return o;
+    }
+
+    // Reshape [T, F*C] -> LSTM(21) -> Dense(F*C) -> Reshape (models/proposed.py:305-309)
+    Ten* op_lstm(Plan& P, const std::string& lstm, Ten* x, const std::string& out_name, const std::string& state_name,
+                 bool persistent) {
+        const LstmLayer& L = lstms.at(lstm);
+        const int D = x->F * x->C;
+        if (D != L.D) fail(NUNET_EINVAL, "plan: %s width", lstm.c_str());
+        Ten* xw = P.make("", 1, LSTM_GATES, false, false);
+        Ten* hs = P.make("", 1, LSTM_UNITS, false, false);
+        Ten *hst = nullptr, *cst = nullptr;
+        if (P.streaming) {
+            hst = P.make("", 1, LSTM_UNITS, true, false);
+            cst = P.make("", 1, LSTM_UNITS, true, false);
+            Plan::StateRef sh, sc;
+            sh.name = state_name + "_h"; sh.is_lstm = true; sh.a = hst;
+            sc.name = state_name + "_c"; sc.is_lstm = true; sc.a = cst;
+            P.states.push_back(sh);
+            P.states.push_back(sc);
+        }
+        Ten* o = P.make(out_name, x->F, x->C, persistent);
+        Plan* pp = &P;
+        P.ops.push_back([=](Engine& E, const Run& r) {
+            const long long rows = (long long)r.B * r.T;
+            const int blocks = (int)((rows + DENSE_RB - 1) / DENSE_RB);
+            float* xwp = pp->cur(xw, 0);
+            float* hsp = pp->cur(hs, 0);
+            dense_rows_kernel<<<blocks, 128, DENSE_RB * D * sizeof(float), r.st>>>(pp->cur(x, r.parity), E.pool.at(L.wk),
+                                                                                 E.pool.at(L.wb), xwp, rows, D, LSTM_GATES);
+            E.check_launch("lstm_in_proj");
+            lstm_recur_kernel<<<r.B, 96, 0, r.st>>>(xwp, E.pool.at(L.wr), hst ? pp->cur(hst, 0) : nullptr,
+                                                   cst ? pp->cur(cst, 0) : nullptr, hsp, r.T);
+            E.check_launch("lstm_recur");
+            dense_rows_kernel<<<blocks, 128, DENSE_RB * LSTM_UNITS * sizeof(float), r.st>>>(
+                hsp, E.pool.at(L.dk), E.pool.at(L.db), pp->cur(o, r.parity), rows, LSTM_UNITS, D);
+            E.check_launch("lstm_dense");
+        });
+        return o;
+    }
+
+    // One nested sub-U-Net (MSFE): returns ctfa(de_1) + en_in; fills des_out[k-1] = de_k (k = 1..n, F0 >> (k-1) bins)
+    Ten* op_msfe(Plan& P, const std::string& blk, int n, Ten* en_in, Ten* const* skips, Ten** des_out,
+                 bool des_persistent, bool out_persistent) {
+        std::string pc, ps;
+        state_prefixes(blk, pc, ps);
+        std::vector<Ten*> ens;
+        Ten* cur = en_in;
+        for (int k = 1; k <= n; ++k) {
+            Ten* sk = skips ? skips[k - 1] : nullptr;
+            if (P.streaming) {
+                Plan::StateRef s;
+                s.name = pc + "_" + std::to_string(k);
+                s.a = cur;
+                s.b = sk;
+                P.states.push_back(s);
+            }
+            cur = op_conv(P, blk + "_conv" + std::to_string(k), cur, sk, blk + "_conv" + std::to_string(k), false);
+            ens.push_back(cur);
+        }
+        Ten* bb = op_lstm(P, blk + "_lstm", cur, blk + "_bb", blk, false);
+        cur = bb;
+        std::vector<Ten*> des;
+        for (int k = 1; k <= n; ++k) {
+            Ten* sk = ens[n - k];
+            if (P.streaming) {
+                Plan::StateRef s;
+                s.name = ps + "_" + std::to_string(k);
+                s.a = cur;
+                s.b = sk;
+                P.states.push_back(s);
+            }
+            cur = op_conv(P, blk + "_spconv" + std::to_string(k), cur, sk, blk + "_spconv" + std::to_string(k), des_persistent);
+            des.push_back(cur);
+        }
+        if (des_out)
+            for (int k = 1; k <= n; ++k) des_out[k - 1] = des[n - k];
+        // CTFA + residual
+        Ten* x = cur;
+        const int F0 = x->F;
+        Ten* ta = P.make(blk + "_ta", 1, 64, false, false);
+        Ten* gate = P.make(blk + "_gate", 1, 64, false, false);
+        Ten* ring = nullptr;
+        if (P.streaming && cfg.stream_ctfa_history) {
+            ring = P.make("", CTFA_WINDOW, 64, true, false);
+            P.rings.push_back(ring);
+        }
+        Ten* out = P.make(blk + "_out", F0, 64, out_persistent);
+        const MlpLayer mta = mlps.at(blk + "_ta"), mfa = mlps.at(blk + "_fa");
+        Plan* pp = &P;
+        const int off_mode = cfg.ctfa_mode;
+        P.ops.push_back([=](Engine& E, const Run& r) {
+            const int frames = r.B * r.T;
+            ctfa_ta_kernel<<<frames, 256, 0, r.st>>>(pp->cur(x, r.parity), E.mlpw(mta), pp->cur(ta, 0), F0);
+            E.check_launch("ctfa_ta");
+            const int div32 = pp->streaming ? 1 : (off_mode == NUNET_CTFA_FRAME_DIV32);
+            ctfa_gate_kernel<<<frames, 64, 0, r.st>>>(pp->cur(ta, 0), E.mlpw(mfa), pp->cur(gate, 0), r.T, div32,
+                                                     ring ? pp->cur(ring, 0) : nullptr, r.ring_pos);
+            E.check_launch("ctfa_gate");
+            const long long n4 = (long long)frames * F0 * 16;
+            const int blocks = (int)std::min<long long>((n4 + 255) / 256, 148LL * 16);
+            gate_residual_kernel<<<blocks, 256, 0, r.st>>>(reinterpret_cast<const float4*>(pp->cur(x, r.parity)),
+                                                          reinterpret_cast<const float4*>(pp->cur(en_in, r.parity)),
+                                                          reinterpret_cast<const float4*>(pp->cur(gate, 0)),
+                                                          reinterpret_cast<float4*>(pp->cur(out, r.parity)), n4, F0);
+            E.check_launch("gate_residual");
+        });
+        return out;
+    }
+
+    void build_plan(Plan& P) {
+        Plan* pp = &P;
+        const bool recycle = !P.streaming && !getenv("NUNET_NO_RECYCLE");
+        Ten* x0 = P.make("input_layer", 256, 64, false);
+        P.ops.push_back([=](Engine& E, const Run& r) {
+            const long long npix = (long long)r.B * r.T * 256;
+            const int blocks = (int)((npix * 8 + 255) / 256);
+            const VecLayer& v = E.in_layer;
+            input_layer_kernel<<<blocks, 256, 0, r.st>>>(r.mag_in, E.pool.at(v.w), E.pool.at(v.b), E.pool.at(v.gamma),
+                                                        E.pool.at(v.beta), E.pool.at(v.alpha), pp->cur(x0, r.parity), npix);
+            E.check_launch("input_layer");
+        });
+        Ten* x = x0;
+        Ten* enc_des[6][6] = {};
+        Ten* enc_out[6] = {};
+        for (int i = 0; i < 6; ++i) {
+            const std::string blk = ENC_NAMES[i];
+            const size_t m = P.mark();
+            Ten* en_in = op_conv(P, blk + "_in", x, nullptr, blk + "_in", false);
+            Ten* out = op_msfe(P, blk, ENC_N[i], en_in, nullptr, enc_des[i], true, false);
+            x = op_conv(P, DOWN_NAMES[i], out, nullptr, DOWN_NAMES[i], true);
+            enc_out[i] = x;
+            if (recycle) P.release(m);
+        }
+        Ten* y = op_lstm(P, "lstm", x, "bb_main", "state", true);
+        for (int i = 0; i < 6; ++i) {
+            const std::string blk = DEC_NAMES[i];
+            const int j = 5 - i;
+            const size_t m = P.mark();
+            Ten* en_in = op_conv(P, blk + "_in", y, enc_out[j], blk + "_in", false);
+            y = op_msfe(P, blk, DEC_N[i], en_in, enc_des[j], nullptr, false, true);
+            if (recycle) P.release(m);
+        }
+        P.ops.push_back([=](Engine& E, const Run& r) {
+            const long long npix = (long long)r.B * r.T * 256;
+            const int blocks = (int)((npix * 16 + 255) / 256);
+            out_conv_kernel<<<blocks, 256, 0, r.st>>>(pp->cur(y, r.parity), E.pool.at(E.out_layer.w), E.pool.at(E.out_layer.b),
+                                                     r.est_out, npix, 256, r.est_stride, r.est_off);
+            E.check_launch("out_conv");
+        });
+    }
+
+    void alloc_plan(Plan& P, int cap, bool streaming) {
+        P.streaming = streaming;
+        P.cap = cap;
+        build_plan(P);
+        if (streaming) {
+            s_mag = P.make("", 1, 256, true, false);
+            s_ph = P.make("", 1, 2 * NBINS, true, false);
+            s_est = P.make("", 1, 256, true, false);
+            s_inbuf = P.make("", 1, NFFT, true, false);
+            s_outbuf = P.make("", 1, NFFT, true, false);
+        } else {
+            o_mag = P.make("mag", 1, 256, true);
+            o_ph = P.make("", 1, 2 * NBINS, true);
+            o_est = P.make("est", 1, NBINS, true);
+            o_frames = P.make("", 1, NFFT, true);
+        }
+        P.finalize();
+        const size_t bytes = P.unit_floats * (size_t)cap * sizeof(float);
+        cudaError_t e = cudaMalloc(&P.arena, bytes);
+        if (e != cudaSuccess) fail(NUNET_ENOMEM, "cudaMalloc of the %s arena (%.2f GB) failed: %s",
+                                   streaming ? "streaming" : "offline", bytes / 1e9, cudaGetErrorString(e));
+        CUDA_OK(cudaMemset(P.arena, 0, bytes));
+    }
+
+    // -------------------------------------------------------------------------------- public operations
+    void run_plan(Plan& P, const Run& r) {
+        for (auto& op : P.ops) op(*this, r);
+    }
+
+    void forward_mag(const float* mag, int B, int T, float* out, int out_stride, int out_off, cudaStream_t st) {
+        if (!offline.arena) fail(NUNET_EINVAL, "offline path disabled (max_frames = 0)");
+        if (B <= 0 || T <= 0) fail(NUNET_EINVAL, "bad shape B=%d T=%d", B, T);
+        if ((long long)B * T > offline.cap) fail(NUNET_ENOMEM, "B*T = %lld exceeds max_frames = %d", (long long)B * T, offline.cap);
+        Run r;
+        r.B = B; r.T = T; r.st = st; r.mag_in = mag; r.est_out = out; r.est_stride = out_stride; r.est_off = out_off;
+        last_B = B; last_T = T;
+        run_plan(offline, r);
+    }
+
+    void forward_wav(const float* wav, int B, int n, float* out_wav, float* out_mag, cudaStream_t st) {
+        const int T = nunet_num_frames(n);
+        if (T <= 0) fail(NUNET_EINVAL, "clip shorter than one 512-sample frame");
+        if (!offline.arena) fail(NUNET_EINVAL, "offline path disabled (max_frames = 0)");
+        if ((long long)B * T > offline.cap) fail(NUNET_ENOMEM, "B*T = %lld exceeds max_frames = %d", (long long)B * T, offline.cap);
+        launches = 0;
+        const long long frames = (long long)B * T;
+        float* mag = offline.cur(o_mag, 0);
+        float2* ph = reinterpret_cast<float2*>(offline.cur(o_ph, 0));
+        float* est = offline.cur(o_est, 0);   // [frames][257]
+        float* fr = offline.cur(o_frames, 0);
+        const int fblocks = (int)((frames + FRAMES_PER_CTA - 1) / FRAMES_PER_CTA);
+        stft_kernel<<<fblocks, 32 * FRAMES_PER_CTA, 0, st>>>(wav, tables(false), mag, ph, B, T, n);
+        check_launch("stft");
+        forward_mag(mag, B, T, est, NBINS, 1, st);
+        if (out_mag) CUDA_OK(cudaMemcpyAsync(out_mag, est, frames * NBINS * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        if (out_wav) {
+            istft_frames_kernel<<<fblocks, 32 * FRAMES_PER_CTA, 0, st>>>(est, ph, tables(false), fr, frames);
+            check_launch("istft_frames");
+            const long long n_out = (long long)(T - 1) * HOP + NFFT;
+            const int blocks = (int)std::min<long long>((B * n_out + 255) / 256, 148LL * 16);
+            overlap_add_kernel<<<blocks, 256, 0, st>>>(fr, out_wav, B, T, n_out);
+            check_launch("overlap_add");
+        }
+    }
+
+    void check_streams(int S) {
+        if (!stream.arena) fail(NUNET_EINVAL, "streaming path disabled (max_streams = 0)");
+        if (S != stream.cap) fail(NUNET_EINVAL, "a step must cover all max_streams = %d streams (got S = %d)", stream.cap, S);
+    }
+
+    void stream_step_mag(const float* mag, int S, float* out, cudaStream_t st) {
+        check_streams(S);
+        Run r;
+        r.B = S; r.T = 1; r.st = st; r.mag_in = mag; r.est_out = out; r.est_stride = 256; r.est_off = 0;
+        r.parity = stream_parity ^ 1;
+        r.ring_pos = stream_steps & (CTFA_WINDOW - 1);
+        run_plan(stream, r);
+        stream_parity ^= 1;
+        ++stream_steps;
+    }
+
+    void stream_step_wav(const float* hop, int S, float* out_hop, float* out_mag, cudaStream_t st) {
+        check_streams(S);
+        launches = 0;
+        float* mag = stream.cur(s_mag, 0);
+        float2* ph = reinterpret_cast<float2*>(stream.cur(s_ph, 0));
+        float* est = stream.cur(s_est, 0);
+        const int fblocks = (S + FRAMES_PER_CTA - 1) / FRAMES_PER_CTA;
+        stream_analysis_kernel<<<fblocks, 32 * FRAMES_PER_CTA, 0, st>>>(hop, stream.cur(s_inbuf, 0), tables(true), mag, ph, S);
+        check_launch("stream_analysis");
+        stream_step_mag(mag, S, est, st);
+        if (out_mag) CUDA_OK(cudaMemcpyAsync(out_mag, est, (size_t)S * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        stream_synthesis_kernel<<<fblocks, 32 * FRAMES_PER_CTA, 0, st>>>(est, ph, tables(true), stream.cur(s_outbuf, 0), out_hop, S,
+                                                                       cfg.dc_mode == NUNET_DC_EDGE);
+        check_launch("stream_synthesis");
+    }
+
+    void stream_reset(int first, int count, cudaStream_t st) {
+        if (!stream.arena) fail(NUNET_EINVAL, "streaming path disabled (max_streams = 0)");
+        if (first < 0 || count < 0 || first + count > stream.cap) fail(NUNET_EINVAL, "stream range out of bounds");
+        if (first == 0 && count == stream.cap) {
+            CUDA_OK(cudaMemsetAsync(stream.arena, 0, stream.unit_floats * (size_t)stream.cap * sizeof(float), st));
+            return;
+        }
+        // every per-stream region is [cap][n] at offset off*cap: zero rows [first, first+count) of each
+        for (auto& t : stream.tens) {
+            const size_t n = t->numel();
+            CUDA_OK(cudaMemsetAsync(stream.ptr(t->off[0]) + (size_t)first * n, 0, (size_t)count * n * sizeof(float), st));
+            if (t->pingpong)
+                CUDA_OK(cudaMemsetAsync(stream.ptr(t->off[1]) + (size_t)first * n, 0, (size_t)count * n * sizeof(float), st));
+        }
+    }
+
+    const Plan::StateRef* find_state(const std::string& name) const {
+        for (auto& s : stream.states)
+            if (s.name == name) return &s;
+        return nullptr;
+    }
+    int state_numel(const Plan::StateRef& s) const {
+        if (s.is_lstm) return LSTM_UNITS;
+        return s.a->F * (s.a->C + (s.b ? s.b->C : 0));
+    }
+    void state_xfer(int sid, const std::string& name, float* buf, bool to_host) {
+        if (!stream.arena) fail(NUNET_EINVAL, "streaming path disabled (max_streams = 0)");
+        if (sid < 0 || sid >= stream.cap) fail(NUNET_EINVAL, "stream id out of range");
+        const Plan::StateRef* s = find_state(name);
+        if (!s) fail(NUNET_ESTATE, "unknown state tensor '%s'", name.c_str());
+        CUDA_OK(cudaDeviceSynchronize());
+        auto xfer = [&](float* dev, float* host, size_t width, size_t hpitch, size_t rows) {
+            if (to_host) CUDA_OK(cudaMemcpy2D(host, hpitch * 4, dev, width * 4, width * 4, rows, cudaMemcpyDeviceToHost));
+            else CUDA_OK(cudaMemcpy2D(dev, width * 4, host, hpitch * 4, width * 4, rows, cudaMemcpyHostToDevice));
+        };
+        if (s->is_lstm) {
+            xfer(stream.cur(s->a, 0) + (size_t)sid * LSTM_UNITS, buf, LSTM_UNITS, LSTM_UNITS, 1);
+            return;
+        }
+        const int CA = s->a->C, CB = s->b ? s->b->C : 0, F = s->a->F;
+        xfer(stream.cur(s->a, stream_parity) + (size_t)sid * s->a->numel(), buf, CA, CA + CB, F);
+        if (s->b) xfer(stream.cur(s->b, stream_parity) + (size_t)sid * s->b->numel(), buf + CA, CB, CA + CB, F);
+    }
+};
+
+}  // namespace nunet
+
+using namespace nunet;
+
+struct nunet_engine {
+    Engine e;
+};
+
+template <typename Fn>
+static int guarded(Fn&& fn) {
+    try {
+        fn();
+        g_err.clear();
+        return NUNET_OK;
+    } catch (const Error& e) {
+        g_err = e.what();
+        return e.code;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return NUNET_EINVAL;
+    }
+}
+
+extern "C" {
+
+const char* nunet_last_error(void) { return g_err.c_str(); }
+int nunet_abi_version(void) { return NUNET_ABI_VERSION; }
+
+int nunet_num_frames(int n_samples) { return n_samples < NFFT ? 0 : 1 + (n_samples - NFFT) / HOP; }
+
+int nunet_create(const nunet_config* cfg, const void* blob, size_t blob_bytes, nunet_engine** out) {
+    if (out) *out = nullptr;
+    std::unique_ptr<nunet_engine> h;
+    int rc = guarded([&] {
+        if (!cfg || !blob || !out) fail(NUNET_EINVAL, "nunet_create: null argument");
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) fail(NUNET_ENODEV, "no CUDA device");
+        if (cfg->device < 0 || cfg->device >= ndev) fail(NUNET_ENODEV, "device %d not present (%d devices)", cfg->device, ndev);
+        CUDA_OK(cudaSetDevice(cfg->device));
+        cudaDeviceProp prop;
+        CUDA_OK(cudaGetDeviceProperties(&prop, cfg->device));
+        if (prop.major != 10) fail(NUNET_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
+        if (cfg->max_frames < 0 || cfg->max_streams < 0 || (cfg->max_frames == 0 && cfg->max_streams == 0))
+            fail(NUNET_EINVAL, "max_frames / max_streams");
+        h.reset(new nunet_engine());
+        Engine& E = h->e;
+        E.cfg = *cfg;
+        E.blob.parse(blob, blob_bytes);
+        E.pack_params();
+        E.blob.m.clear();   // the host blob is not referenced after packing
+        if (cfg->max_frames > 0) E.alloc_plan(E.offline, cfg->max_frames, false);
+        if (cfg->max_streams > 0) E.alloc_plan(E.stream, cfg->max_streams, true);
+        CUDA_OK(cudaStreamCreateWithFlags(&E.own_stream, cudaStreamNonBlocking));
+        // staging for the host entry points
+        size_t in_f = 0, out_f = 0;
+        if (cfg->max_frames > 0) {
+            in_f = (size_t)cfg->max_frames * 2 * HOP + NFFT;
+            out_f = in_f;
+        }
+        if (cfg->max_streams > 0) {
+            in_f = std::max(in_f, (size_t)cfg->max_streams * HOP);
+            out_f = std::max(out_f, (size_t)cfg->max_streams * HOP);
+        }
+        CUDA_OK(cudaMalloc(&E.h_in, in_f * sizeof(float)));
+        CUDA_OK(cudaMalloc(&E.h_out, out_f * sizeof(float)));
+        E.h_in_cap = in_f;
+        E.h_out_cap = out_f;
+        CUDA_OK(cudaDeviceSynchronize());
+    });
+    if (rc == NUNET_OK) *out = h.release();
+    return rc;
+}
+
+void nunet_destroy(nunet_engine* h) {
+    if (!h) return;
+    cudaSetDevice(h->e.cfg.device);
+    cudaDeviceSynchronize();
+    delete h;
+}
+
+int nunet_forward_wav_dev(nunet_engine* h, const float* wav, int B, int n_samples, float* out_wav, float* out_mag,
+                          void* stream) {
+    return guarded([&] {
+        if (!h || !wav) fail(NUNET_EINVAL, "null argument");
+        h->e.forward_wav(wav, B, n_samples, out_wav, out_mag, static_cast<cudaStream_t>(stream));
+    });
+}
+
+int nunet_forward_wav_host(nunet_engine* h, const float* wav, int B, int n_samples, float* out_wav, float* out_mag) {
+    return guarded([&] {
+        if (!h || !wav) fail(NUNET_EINVAL, "null argument");
+        Engine& E = h->e;
+        const int T = nunet_num_frames(n_samples);
+        if (T <= 0) fail(NUNET_EINVAL, "clip shorter than one 512-sample frame");
+        const size_t n_in = (size_t)B * n_samples, n_out = (size_t)B * ((size_t)(T - 1) * HOP + NFFT);
+        if (n_in > E.h_in_cap || n_out > E.h_out_cap) fail(NUNET_ENOMEM, "host-call staging capacity exceeded");
+        cudaStream_t st = E.own_stream;
+        CUDA_OK(cudaMemcpyAsync(E.h_in, wav, n_in * sizeof(float), cudaMemcpyHostToDevice, st));
+        float* est = nullptr;
+        E.forward_wav(E.h_in, B, n_samples, out_wav ? E.h_out : nullptr, nullptr, st);
+        if (out_wav) CUDA_OK(cudaMemcpyAsync(out_wav, E.h_out, n_out * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (out_mag) {
+            est = E.offline.cur(E.o_est, 0);
+            CUDA_OK(cudaMemcpyAsync(out_mag, est, (size_t)B * T * NBINS * sizeof(float), cudaMemcpyDeviceToHost, st));
+        }
+        CUDA_OK(cudaStreamSynchronize(st));
+    });
+}
+
+int nunet_forward_mag_dev(nunet_engine* h, const float* mag, int B, int T, float* out_mag, void* stream) {
+    return guarded([&] {
+        if (!h || !mag || !out_mag) fail(NUNET_EINVAL, "null argument");
+        h->e.launches = 0;
+        h->e.forward_mag(mag, B, T, out_mag, 256, 0, static_cast<cudaStream_t>(stream));
+    });
+}
+
+int nunet_stream_reset(nunet_engine* h, int first, int count, void* stream) {
+    return guarded([&] {
+        if (!h) fail(NUNET_EINVAL, "null argument");
+        h->e.stream_reset(first, count, static_cast<cudaStream_t>(stream));
+    });
+}
+
+int nunet_stream_step_mag_dev(nunet_engine* h, const float* mag, int S, float* out_mag, void* stream) {
+    return guarded([&] {
+        if (!h || !mag || !out_mag) fail(NUNET_EINVAL, "null argument");
+        h->e.launches = 0;
+        h->e.stream_step_mag(mag, S, out_mag, static_cast<cudaStream_t>(stream));
+    });
+}
+
+int nunet_stream_step_wav_dev(nunet_engine* h, const float* hop, int S, float* out_hop, float* out_mag, void* stream) {
+    return guarded([&] {
+        if (!h || !hop || !out_hop) fail(NUNET_EINVAL, "null argument");
+        h->e.stream_step_wav(hop, S, out_hop, out_mag, static_cast<cudaStream_t>(stream));
+    });
+}
+
+int nunet_stream_step_wav_host(nunet_engine* h, const float* hop, int S, float* out_hop) {
+    return guarded([&] {
+        if (!h || !hop || !out_hop) fail(NUNET_EINVAL, "null argument");
+        Engine& E = h->e;
+        E.check_streams(S);
+        cudaStream_t st = E.own_stream;
+        const size_t n = (size_t)S * HOP;
+        CUDA_OK(cudaMemcpyAsync(E.h_in, hop, n * sizeof(float), cudaMemcpyHostToDevice, st));
+        E.stream_step_wav(E.h_in, S, E.h_out, nullptr, st);
+        CUDA_OK(cudaMemcpyAsync(out_hop, E.h_out, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+    });
+}
+
+int nunet_state_count(nunet_engine* h) { return h ? (int)h->e.stream.states.size() : NUNET_EINVAL; }
+
+int nunet_state_name(nunet_engine* h, int index, char* name_out, int cap) {
+    return guarded([&] {
+        if (!h || !name_out || cap <= 0) fail(NUNET_EINVAL, "null argument");
+        if (index < 0 || index >= (int)h->e.stream.states.size()) fail(NUNET_EINVAL, "state index out of range");
+        snprintf(name_out, (size_t)cap, "%s", h->e.stream.states[index].name.c_str());
+    });
+}
+
+int nunet_state_numel(nunet_engine* h, const char* name) {
+    int n = 0;
+    int rc = guarded([&] {
+        if (!h || !name) fail(NUNET_EINVAL, "null argument");
+        const Plan::StateRef* s = h->e.find_state(name);
+        if (!s) fail(NUNET_ESTATE, "unknown state tensor '%s'", name);
+        n = h->e.state_numel(*s);
+    });
+    return rc == NUNET_OK ? n : rc;
+}
+
+int nunet_state_export(nunet_engine* h, int stream_id, const char* name, float* buf) {
+    return guarded([&] {
+        if (!h || !name || !buf) fail(NUNET_EINVAL, "null argument");
+        h->e.state_xfer(stream_id, name, buf, true);
+    });
+}
+
+int nunet_state_import(nunet_engine* h, int stream_id, const char* name, const float* buf) {
+    return guarded([&] {
+        if (!h || !name || !buf) fail(NUNET_EINVAL, "null argument");
+        h->e.state_xfer(stream_id, name, const_cast<float*>(buf), false);
+    });
+}
+
+int nunet_last_launch_count(nunet_engine* h) { return h ? h->e.launches : NUNET_EINVAL; }
+
+long long nunet_debug_read(nunet_engine* h, const char* tensor_name, float* buf, long long cap) {
+    long long n = 0;
+    int rc = guarded([&] {
+        if (!h || !tensor_name) fail(NUNET_EINVAL, "null argument");
+        Engine& E = h->e;
+        auto it = E.offline.named.find(tensor_name);
+        if (it == E.offline.named.end()) fail(NUNET_ESTATE, "unknown tensor '%s'", tensor_name);
+        const Ten* t = it->second;
+        n = (long long)E.last_B * E.last_T * (long long)t->numel();
+        if (buf) {
+            if (cap < n) fail(NUNET_EINVAL, "buffer too small");
+            CUDA_OK(cudaDeviceSynchronize());
+            CUDA_OK(cudaMemcpy(buf, E.offline.cur(t, 0), (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+        }
+    });
+    return rc == NUNET_OK ? n : rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,177 @@
+"""Python handle on the CUDA engine (csrc/engine.cu through the C ABI).  torch is used only for
+device memory and streams; all arithmetic happens in the hand-written sm_100a kernels."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (NUNET_CTFA_CAUSAL_AVG32, NUNET_CTFA_FRAME_DIV32, NUNET_DC_EDGE, NUNET_DC_ZERO,
+                   NUNET_VARIANT_LSTM, NunetConfig, check)
+
+CTFA_MODES = {"causal_avg32": NUNET_CTFA_CAUSAL_AVG32, "frame_div32": NUNET_CTFA_FRAME_DIV32}
+DC_MODES = {"zero": NUNET_DC_ZERO, "edge": NUNET_DC_EDGE}
+
+
+def num_frames(n_samples: int) -> int:
+    """tf.signal.stft(frame_length=512, frame_step=256, pad_end=False) frame count (models/proposed.py:285)."""
+    return 0 if n_samples < 512 else 1 + (n_samples - 512) // 256
+
+
+def _host_ptr(a) -> Tuple[int, object]:
+    """Pointer of a C-contiguous float32 host buffer (numpy array or CPU torch tensor)."""
+    if isinstance(a, torch.Tensor):
+        if a.is_cuda or a.dtype != torch.float32 or not a.is_contiguous():
+            raise ValueError("host buffer must be a contiguous float32 CPU tensor")
+        return a.data_ptr(), a
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a.ctypes.data, a
+
+
+class NunetEngine:
+    """One engine = one GPU, one packed weight set, fixed capacity (no allocation after construction)."""
+
+    def __init__(self, blob: bytes, max_frames: int = 0, max_streams: int = 0, device: int = 0,
+                 ctfa_mode: str = "causal_avg32", dc_mode: str = "edge", stream_ctfa_history: bool = False,
+                 variant: int = NUNET_VARIANT_LSTM):
+        self._L = _lib.lib()
+        self._h = C.c_void_p()
+        self.device = torch.device("cuda", device)
+        cfg = NunetConfig(variant, device, int(max_frames), int(max_streams), CTFA_MODES[ctfa_mode],
+                          DC_MODES[dc_mode], int(bool(stream_ctfa_history)), 0)
+        self.max_frames, self.max_streams = int(max_frames), int(max_streams)
+        self.ctfa_mode, self.dc_mode = ctfa_mode, dc_mode
+        buf = (C.c_char * len(blob)).from_buffer_copy(blob)
+        check(self._L.nunet_create(C.byref(cfg), buf, len(blob), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.nunet_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _dev(self, t: torch.Tensor) -> torch.Tensor:
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.device == self.device):
+            raise ValueError(f"expected a contiguous float32 tensor on {self.device}")
+        return t
+
+    @property
+    def last_launch_count(self) -> int:
+        return self._L.nunet_last_launch_count(self._h)
+
+    # ------------------------------------------------------------------ offline
+    def forward_wav(self, wav: torch.Tensor, want_wav: bool = True, want_mag: bool = True):
+        """wav [B,N] (cuda) -> (enhanced wav [B,(T-1)*256+512] | None, est magnitudes [B,T,257] | None)."""
+        wav = self._dev(wav)
+        B, N = wav.shape
+        T = num_frames(N)
+        out_wav = torch.empty((B, (T - 1) * 256 + 512), device=self.device, dtype=torch.float32) if want_wav else None
+        out_mag = torch.empty((B, T, 257), device=self.device, dtype=torch.float32) if want_mag else None
+        check(self._L.nunet_forward_wav_dev(self._h, wav.data_ptr(), B, N,
+                                            out_wav.data_ptr() if want_wav else None,
+                                            out_mag.data_ptr() if want_mag else None, self._stream()))
+        return out_wav, out_mag
+
+    def forward_wav_into(self, wav: torch.Tensor, out_wav: Optional[torch.Tensor], out_mag: Optional[torch.Tensor] = None):
+        """Allocation-free variant for benchmarks."""
+        B, N = wav.shape
+        check(self._L.nunet_forward_wav_dev(self._h, wav.data_ptr(), B, N,
+                                            out_wav.data_ptr() if out_wav is not None else None,
+                                            out_mag.data_ptr() if out_mag is not None else None, self._stream()))
+
+    def forward_mag(self, mag: torch.Tensor) -> torch.Tensor:
+        """mag [B,T,256] (DC dropped) -> estimated magnitudes [B,T,256]."""
+        mag = self._dev(mag)
+        B, T, F = mag.shape
+        if F != 256:
+            raise ValueError("magnitudes must have 256 bins (DC dropped)")
+        out = torch.empty_like(mag)
+        check(self._L.nunet_forward_mag_dev(self._h, mag.data_ptr(), B, T, out.data_ptr(), self._stream()))
+        return out
+
+    def forward_wav_host(self, wav, out_wav=None, out_mag=None):
+        """End-to-end host call: host wav [B,N] -> host buffers (H2D + kernels + D2H inside the call)."""
+        p_in, keep = _host_ptr(wav)
+        B, N = keep.shape
+        T = num_frames(N)
+        if out_wav is None:
+            out_wav = np.empty((B, (T - 1) * 256 + 512), np.float32)
+        p_out, _k2 = _host_ptr(out_wav)
+        p_mag = None
+        if out_mag is not None:
+            p_mag, _k3 = _host_ptr(out_mag)
+        check(self._L.nunet_forward_wav_host(self._h, p_in, B, N, p_out, p_mag))
+        return out_wav, out_mag
+
+    def debug_read(self, name: str) -> np.ndarray:
+        n = check(self._L.nunet_debug_read(self._h, name.encode(), None, 0))
+        buf = np.empty(n, np.float32)
+        check(self._L.nunet_debug_read(self._h, name.encode(), buf.ctypes.data, n))
+        return buf
+
+    # ------------------------------------------------------------------ streaming
+    def stream_reset(self, first: int = 0, count: Optional[int] = None):
+        check(self._L.nunet_stream_reset(self._h, first, self.max_streams - first if count is None else count,
+                                         self._stream()))
+
+    def stream_step_mag(self, mag: torch.Tensor) -> torch.Tensor:
+        mag = self._dev(mag)
+        out = torch.empty_like(mag)
+        check(self._L.nunet_stream_step_mag_dev(self._h, mag.data_ptr(), mag.shape[0], out.data_ptr(), self._stream()))
+        return out
+
+    def stream_step_wav(self, hop: torch.Tensor, out_hop: Optional[torch.Tensor] = None,
+                        out_mag: Optional[torch.Tensor] = None) -> torch.Tensor:
+        hop = self._dev(hop)
+        if out_hop is None:
+            out_hop = torch.empty_like(hop)
+        check(self._L.nunet_stream_step_wav_dev(self._h, hop.data_ptr(), hop.shape[0], out_hop.data_ptr(),
+                                                out_mag.data_ptr() if out_mag is not None else None, self._stream()))
+        return out_hop
+
+    def stream_step_wav_host(self, hop, out_hop=None):
+        p_in, keep = _host_ptr(hop)
+        if out_hop is None:
+            out_hop = np.empty(keep.shape, np.float32)
+        p_out, _k = _host_ptr(out_hop)
+        check(self._L.nunet_stream_step_wav_host(self._h, p_in, keep.shape[0], p_out))
+        return out_hop
+
+    # ------------------------------------------------------------------ history wire format
+    def state_names(self) -> List[str]:
+        n = check(self._L.nunet_state_count(self._h))
+        out = []
+        buf = C.create_string_buffer(96)
+        for i in range(n):
+            check(self._L.nunet_state_name(self._h, i, buf, 96))
+            out.append(buf.value.decode())
+        return out
+
+    def state_numel(self, name: str) -> int:
+        return check(self._L.nunet_state_numel(self._h, name.encode()))
+
+    def state_export(self, stream_id: int, name: str) -> np.ndarray:
+        buf = np.empty(self.state_numel(name), np.float32)
+        check(self._L.nunet_state_export(self._h, stream_id, name.encode(), buf.ctypes.data))
+        return buf
+
+    def state_import(self, stream_id: int, name: str, value) -> None:
+        a = np.ascontiguousarray(value, dtype=np.float32).reshape(-1)
+        if a.size != self.state_numel(name):
+            raise ValueError(f"{name}: expected {self.state_numel(name)} values, got {a.size}")
+        check(self._L.nunet_state_import(self._h, stream_id, name.encode(), a.ctypes.data))
+
+    def state_dict(self, stream_id: int = 0) -> Dict[str, np.ndarray]:
+        return {n: self.state_export(stream_id, n) for n in self.state_names()}

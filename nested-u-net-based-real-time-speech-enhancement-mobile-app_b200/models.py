@@ -1,0 +1,108 @@
+"""Surface 1 of the reference, backed by the CUDA engine:
+
+    m = models.NUTLS_LSTM(opt); model = m.build_model(); model.load_weights(path); y = model(x, training=False)
+
+mirrors `dnn_model/models/proposed.py:13-22` (ctor), `:627-637` (build_model), `test_interface.py:45,58`
+(load_weights / call) and `:639` (tflite_model: the one-frame model with zero history).  The returned objects
+are plain callables, not Keras models; the arithmetic runs in csrc/*.cu (no CPU path).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from .engine import NunetEngine, num_frames
+from .weights import expected_lstm_shapes, lstm_weights_from_h5, pack_blob, validate
+
+
+class _Model:
+    """What `build_model()` returns: waveform [B, N] -> enhanced waveform [B, (T-1)*256+512]."""
+
+    def __init__(self, opt, ctfa_mode: str = "causal_avg32"):
+        self.opt = opt
+        self.ctfa_mode = ctfa_mode
+        self._weights: Optional[Dict[str, np.ndarray]] = None
+        self._blob: Optional[bytes] = None
+        self._engine: Optional[NunetEngine] = None
+        self.device = int(getattr(opt, "device", 0))
+
+    # Keras API subset ---------------------------------------------------------------------------
+    def load_weights(self, path_or_set):
+        """`.h5` path written by Keras save_weights (train_interface.py:99-100) or a role-named weight set."""
+        w = lstm_weights_from_h5(path_or_set) if isinstance(path_or_set, str) else dict(path_or_set)
+        validate(w, expected_lstm_shapes())
+        self._weights, self._blob, self._engine = w, pack_blob(w), None
+        return self
+
+    def _get_engine(self, frames: int) -> NunetEngine:
+        if self._blob is None:
+            raise RuntimeError("load_weights() first (the engine has no random initialiser)")
+        if self._engine is None or self._engine.max_frames < frames:
+            if self._engine is not None:
+                self._engine.close()
+            self._engine = NunetEngine(self._blob, max_frames=frames, device=self.device, ctfa_mode=self.ctfa_mode)
+        return self._engine
+
+    def __call__(self, x, training: bool = False):
+        if training:
+            raise NotImplementedError("inference path only (training is out of scope, SURVEY 8)")
+        as_numpy = not isinstance(x, torch.Tensor)
+        xt = torch.as_tensor(np.asarray(x, dtype=np.float32)) if as_numpy else x.to(torch.float32)
+        if xt.dim() != 2:
+            raise ValueError("expected [batch, samples]")
+        dev = torch.device("cuda", self.device)
+        xt = xt.to(dev).contiguous()
+        eng = self._get_engine(xt.shape[0] * num_frames(xt.shape[1]))
+        y, _ = eng.forward_wav(xt, want_wav=True, want_mag=False)
+        return y.cpu().numpy() if as_numpy else y
+
+    predict = __call__
+
+    def enhance_mag(self, x):
+        """Estimated magnitude spectrogram [B, T, 257] (DC zero), the quantity the parity bar is stated on."""
+        xt = torch.as_tensor(np.asarray(x, dtype=np.float32)).to(torch.device("cuda", self.device)).contiguous()
+        eng = self._get_engine(xt.shape[0] * num_frames(xt.shape[1]))
+        _, mag = eng.forward_wav(xt, want_wav=False, want_mag=True)
+        return mag.cpu().numpy()
+
+
+class _FrameModel:
+    """What `tflite_model()` returns: [1,1,256,1] -> [1,1,256,1] with zero history (proposed.py:639-1151)."""
+
+    def __init__(self, opt):
+        self.opt = opt
+        self._blob = None
+        self.device = int(getattr(opt, "device", 0))
+
+    def load_weights(self, path_or_set):
+        w = lstm_weights_from_h5(path_or_set) if isinstance(path_or_set, str) else dict(path_or_set)
+        validate(w, expected_lstm_shapes())
+        self._blob = pack_blob(w)
+        self._engine = NunetEngine(self._blob, max_streams=1, device=self.device)
+        return self
+
+    def __call__(self, x, training: bool = False):
+        x = np.asarray(x, dtype=np.float32).reshape(1, 256)
+        self._engine.stream_reset()
+        out = self._engine.stream_step_mag(torch.from_numpy(x).to(self._engine.device))
+        return out.cpu().numpy().reshape(1, 1, 256, 1)
+
+
+class NUTLS_LSTM:
+    def __init__(self, opt):
+        self.in_ch, self.mid_ch, self.out_ch = 1, 32, 64
+        self.win_len, self.fft_len, self.hop_len = opt.win_len, opt.fft_len, opt.hop_len
+        if (self.win_len, self.fft_len, self.hop_len) != (512, 512, 256):
+            raise ValueError("the kernels are specialised for win_len = fft_len = 512, hop_len = 256")
+        self.unit = 21
+        self.opt = opt
+        self.model = None
+
+    def build_model(self) -> _Model:
+        self.model = _Model(self.opt)
+        return self.model
+
+    def tflite_model(self) -> _FrameModel:
+        return _FrameModel(self.opt)

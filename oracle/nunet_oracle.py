@@ -156,7 +156,7 @@ class Oracle:
         return y.reshape(b, t, f, c), (h, cst)
 
     # ------------------------------------------------------------------ the network
-    def _msfe(self, block: str, depth: int, en_in, skips2, st_in, st_out, ctfa_hist):
+    def _msfe(self, block: str, depth: int, en_in, skips2, st_in, st_out, ctfa_hist, taps=None):
         """One nested sub-U-Net.  `skips2` = the paired encoder block's spconv outputs
         [de_1 .. de_n] (None on the encoder side).  Returns (ctfa_out + en_in, [de_1..de_n])."""
         pc, ps, pl = state_prefixes(block)
@@ -175,10 +175,14 @@ class Oracle:
             keep(pc, k, xin)
             cur = self.conv(xin, f"{block}_conv{k}", prev(pc, k))
             ens.append(cur)
+            if taps is not None:
+                taps[f"{block}_conv{k}"] = cur
         lstm_state = None if st_in is None else (st_in[f"{pl}_h"], st_in[f"{pl}_c"])
         bb, (h, c) = self.lstm_dense(cur, f"{block}_lstm", f"{block}_dense", lstm_state)
         if st_out is not None:
             st_out[f"{pl}_h"], st_out[f"{pl}_c"] = h, c
+        if taps is not None:
+            taps[f"{block}_bb"] = bb
         des = []
         cur = bb
         for k in range(1, depth + 1):
@@ -186,9 +190,14 @@ class Oracle:
             keep(ps, k, xin)
             cur = self.spconv(xin, f"{block}_spconv{k}", prev(ps, k))
             des.append(cur)
+            if taps is not None:
+                taps[f"{block}_spconv{k}"] = cur
         gated, new_hist = self.ctfa(cur, block, None if ctfa_hist is None else ctfa_hist.get(block))
         if ctfa_hist is not None:
             ctfa_hist[block] = new_hist
+        if taps is not None:
+            taps[f"{block}_in"] = en_in
+            taps[f"{block}_out"] = gated + en_in
         return gated + en_in, des[::-1]
 
     def net(self, mag, st_in=None, st_out=None, ctfa_hist=None, taps: Optional[dict] = None):
@@ -197,11 +206,13 @@ class Oracle:
         st_in/st_out: reference-named history dicts (converter_proposed.py signature) or None for
         the zero-history offline graph."""
         x = self.inconv(mag, "input_layer")
+        if taps is not None:
+            taps["input_layer"] = x
         enc_de: List[List[torch.Tensor]] = []
         enc_out: List[torch.Tensor] = []
         for (block, depth), dn in zip(ENC_BLOCKS, DOWN_NAMES):
             en_in = self.inconv(x, f"{block}_in")
-            out, des = self._msfe(block, depth, en_in, None, st_in, st_out, ctfa_hist)
+            out, des = self._msfe(block, depth, en_in, None, st_in, st_out, ctfa_hist, taps)
             x = self.down_sampling(out, dn)
             enc_de.append(des)
             enc_out.append(x)
@@ -211,13 +222,13 @@ class Oracle:
         y, (h, c) = self.lstm_dense(x, "lstm", "dense", main_state)
         if st_out is not None:
             st_out["state_h"], st_out["state_c"] = h, c
+        if taps is not None:
+            taps["bb_main"] = y
         for i, ((block, depth), un) in enumerate(zip(DEC_BLOCKS, UP_NAMES)):
             j = 5 - i
             u = self.up_sampling(torch.cat([y, enc_out[j]], dim=3), un)
             en_in = self.inconv(u, f"{block}_in")
-            y, _ = self._msfe(block, depth, en_in, enc_de[j], st_in, st_out, ctfa_hist)
-            if taps is not None:
-                taps[block] = y
+            y, _ = self._msfe(block, depth, en_in, enc_de[j], st_in, st_out, ctfa_hist, taps)
         return self._conv2d(y, "out_conv")
 
     # ------------------------------------------------------------------ offline surface (proposed.py:284-625)

@@ -1,0 +1,28 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run by the driver with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def weights():
+    from nunet_b200.weights import load_default_weights
+    try:
+        return load_default_weights()
+    except FileNotFoundError as e:
+        pytest.skip(str(e))
+
+
+@pytest.fixture(scope="session")
+def golden_io():
+    return dict(np.load(os.path.join(GOLDEN, "oracle_io_lstm.npz")))

@@ -1,0 +1,81 @@
+"""Regenerates the committed fixtures in tests/golden/ from the reference checkout (/root/reference).
+
+Run in the build container only (the GPU box has no /root/reference):  python tests/golden/make_golden.py
+Fixtures:
+  java_windows.json        literal analysis / synthesis window tables of RTSE_NUTLS_LSTM.java:62-63
+  state_shapes_lstm.json   history-tensor table of interpreter_proposed.py:36-198
+  input_specs_lstm.json    TensorSpec names/shapes of converter_proposed.py:26-187
+  wav_excerpt.npz          first 1.5 s (int16) of data/40hc020i_0.wav (noisy) and data/40hc020i.wav (clean)
+  oracle_io_lstm.npz       oracle outputs with the reference .h5 weights on seeded inputs (regression pin +
+                           expected values for the GPU parity tests)
+"""
+import ast
+import glob
+import json
+import os
+import re
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+
+
+def java_windows():
+    path = glob.glob(f"{REF}/mobile_app/app/src/main/java/**/RTSE_NUTLS_LSTM.java", recursive=True)[0]
+    src = open(path).read()
+    out = {}
+    for name in ("window", "inverse_window"):
+        m = re.search(r"this\.%s = new double\[\]\{([^}]*)\}" % name, src)
+        out[name] = [float(v) for v in m.group(1).split(",")]
+        assert len(out[name]) == 512
+    json.dump(out, open(f"{HERE}/java_windows.json", "w"))
+
+
+def state_tables():
+    src = open(f"{REF}/dnn_model/interpreter_proposed.py").read()
+    shapes = {}
+    for name, shp in re.findall(r"['\"](\w+)['\"]\s*:\s*np\.zeros\(\(([\d, ]+)\)", src):
+        shapes[name] = [int(v) for v in shp.split(",")]
+    json.dump(shapes, open(f"{HERE}/state_shapes_lstm.json", "w"), indent=0)
+    src = open(f"{REF}/dnn_model/converter_proposed.py").read()
+    specs = re.findall(r"tf\.TensorSpec\(shape=\[([\w, ]+)\], dtype=tf\.float32, name='(\w+)'\)", src)
+    json.dump([[n, [None if v.strip() == "None" else int(v) for v in s.split(",")]] for s, n in specs],
+              open(f"{HERE}/input_specs_lstm.json", "w"), indent=0)
+
+
+def wav_excerpt():
+    from oracle.wavio import read_wav
+    noisy, fs = read_wav(f"{REF}/dnn_model/data/40hc020i_0.wav")
+    clean, _ = read_wav(f"{REF}/dnn_model/data/40hc020i.wav")
+    n = 24000
+    np.savez_compressed(f"{HERE}/wav_excerpt.npz", noisy=np.round(noisy[:n] * 32768).astype(np.int16),
+                        clean=np.round(clean[:n] * 32768).astype(np.int16), fs=fs)
+
+
+def oracle_io():
+    from nunet_b200.synth import synth_clips
+    from nunet_b200.weights import lstm_weights_from_h5
+    from oracle.nunet_oracle import Oracle
+    w = lstm_weights_from_h5(f"{REF}/dnn_model/log/saved_model/nutls_lstm.h5")
+    wav = synth_clips(2, 512 + 256 * 39, first_clip=0)           # 2 clips x 40 frames
+    out = {"wav": wav}
+    with torch.no_grad():
+        for mode in ("causal_avg32", "frame_div32"):
+            o = Oracle(w, ctfa_mode=mode)
+            y, est = o.forward_wav(wav)
+            out[f"est_{mode}"] = est.numpy()
+            out[f"wav_{mode}"] = y.numpy()
+    np.savez_compressed(f"{HERE}/oracle_io_lstm.npz", **out)
+
+
+if __name__ == "__main__":
+    java_windows()
+    state_tables()
+    wav_excerpt()
+    oracle_io()
+    print("fixtures written to", HERE)

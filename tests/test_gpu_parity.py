@@ -1,0 +1,255 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical inputs, weights and
+mode flags.  Bar (BASELINE.json north_star): max-abs <= 1e-3 on the enhanced magnitude spectrogram, inputs
+peak-normalised so magnitudes reach ~48.  Wav outputs are held to the same absolute bar."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL_MAG = 1e-3
+TOL_WAV = 1e-3
+
+
+@pytest.fixture(scope="module")
+def blob(weights):
+    from nunet_b200.weights import pack_blob
+    return pack_blob(weights)
+
+
+@pytest.fixture(scope="module")
+def oracles(weights):
+    from oracle.nunet_oracle import Oracle
+    return {m: Oracle(weights, ctfa_mode=m) for m in ("causal_avg32", "frame_div32")}
+
+
+def _engine(blob, **kw):
+    from nunet_b200.engine import NunetEngine
+    return NunetEngine(blob, **kw)
+
+
+def test_library_is_the_cuda_one():
+    from nunet_b200 import _lib
+    L = _lib.lib()
+    assert L.nunet_abi_version() == 1
+    assert torch.cuda.get_device_capability(0)[0] == 10
+
+
+@pytest.mark.parametrize("mode", ["causal_avg32", "frame_div32"])
+def test_offline_matches_golden_and_oracle(blob, oracles, golden_io, mode):
+    wav = golden_io["wav"]
+    eng = _engine(blob, max_frames=2 * 40, ctfa_mode=mode)
+    y, est = eng.forward_wav(torch.from_numpy(wav).cuda())
+    est, y = est.cpu().numpy(), y.cpu().numpy()
+    assert eng.last_launch_count > 100
+    ref = golden_io[f"est_{mode}"]
+    assert ref.max() > 20.0
+    assert np.abs(est - ref).max() <= TOL_MAG
+    assert np.abs(y - golden_io[f"wav_{mode}"]).max() <= TOL_WAV
+    with torch.no_grad():
+        y2, est2 = oracles[mode].forward_wav(wav)
+    assert np.abs(est - est2.numpy()).max() <= TOL_MAG
+    assert (est[:, :, 0] == 0).all()                      # DC bin zero-padded (proposed.py:617)
+
+
+@pytest.mark.parametrize("B,T", [(1, 1), (1, 2), (3, 33), (5, 9), (2, 70)])
+def test_forward_mag_ragged_shapes(blob, oracles, B, T):
+    """Frame counts that do not fill the time tiles, odd batch sizes, T = 1 (no history at all)."""
+    from nunet_b200.synth import synth_clips
+    o = oracles["causal_avg32"]
+    wav = synth_clips(B, 512 + 256 * (T - 1), first_clip=7)
+    mags, _ = o.stft(torch.from_numpy(wav))
+    mag = mags[:, :, 1:].contiguous()
+    with torch.no_grad():
+        ref = o.net(mag[..., None]).squeeze(-1)
+    eng = _engine(blob, max_frames=B * T + 5, ctfa_mode="causal_avg32")
+    out = eng.forward_mag(mag.cuda()).cpu()
+    assert float((out - ref).abs().max()) <= TOL_MAG
+
+
+def test_wav_length_not_multiple_of_hop(blob, oracles):
+    from nunet_b200.synth import synth_clips
+    wav = synth_clips(2, 512 + 256 * 6 + 131, first_clip=3)   # trailing 131 samples are ignored by the STFT
+    eng = _engine(blob, max_frames=2 * 7)
+    y, est = eng.forward_wav(torch.from_numpy(wav).cuda())
+    with torch.no_grad():
+        y2, est2 = oracles["causal_avg32"].forward_wav(wav)
+    assert y.shape == y2.shape and est.shape == est2.shape
+    assert float((est.cpu() - est2).abs().max()) <= TOL_MAG
+    assert float((y.cpu() - y2).abs().max()) <= TOL_WAV
+
+
+def test_host_call_equals_device_call(blob):
+    from nunet_b200.synth import synth_clips
+    wav = synth_clips(3, 512 + 256 * 15, first_clip=11)
+    eng = _engine(blob, max_frames=3 * 16)
+    y, est = eng.forward_wav(torch.from_numpy(wav).cuda())
+    out_wav = torch.empty(y.shape, dtype=torch.float32).pin_memory()
+    out_mag = torch.empty(est.shape, dtype=torch.float32).pin_memory()
+    eng.forward_wav_host(torch.from_numpy(wav).pin_memory(), out_wav, out_mag)
+    assert torch.equal(out_wav, y.cpu()) and torch.equal(out_mag, est.cpu())
+
+
+def test_batch_independence_and_causality(blob):
+    """Size-independent properties: a clip's output does not depend on its batch neighbours, and frame t does
+    not depend on samples after frame t (the whole model is causal)."""
+    from nunet_b200.synth import synth_clips
+    T = 48
+    wav = synth_clips(6, 512 + 256 * (T - 1), first_clip=20)
+    eng = _engine(blob, max_frames=6 * T)
+    _, est = eng.forward_wav(torch.from_numpy(wav).cuda(), want_wav=False)
+    _, est1 = eng.forward_wav(torch.from_numpy(wav[4:5]).cuda(), want_wav=False)
+    assert torch.equal(est[4:5], est1)
+    wav2 = wav.copy()
+    wav2[:, 512 + 256 * 30:] = 0.0                     # destroy everything after frame 30's window
+    _, est2 = eng.forward_wav(torch.from_numpy(wav2).cuda(), want_wav=False)
+    assert torch.equal(est[:, :31], est2[:, :31])
+    assert not torch.equal(est[:, 32:], est2[:, 32:])
+
+
+def test_capacity_and_argument_errors(blob):
+    from nunet_b200._lib import NunetError
+    eng = _engine(blob, max_frames=8)
+    with pytest.raises(NunetError) as ei:
+        eng.forward_mag(torch.zeros(3, 3, 256, device="cuda"))
+    assert ei.value.code == -2 and "max_frames" in str(ei.value)
+    with pytest.raises(NunetError):
+        eng.stream_step_mag(torch.zeros(1, 256, device="cuda"))     # streaming disabled
+    with pytest.raises(NunetError) as ei:
+        _engine(b"garbage" * 10, max_frames=8)
+    assert "magic" in str(ei.value)
+    with pytest.raises(NunetError):
+        eng.forward_wav(torch.zeros(1, 300, device="cuda"))         # shorter than one frame
+
+
+# --------------------------------------------------------------------------------------------- streaming
+def test_streaming_step_mag_matches_frame_graph(blob, oracles):
+    """S streams x 12 steps of the one-frame stateful graph (converter_proposed.py:188-867) vs the oracle's
+    frame_step with carried history; also checks every exported history tensor after the last step."""
+    from nunet_b200.synth import synth_clips
+    o = oracles["frame_div32"]
+    S, steps = 3, 12
+    wav = synth_clips(S, 512 + 256 * (steps - 1), first_clip=40)
+    mags, _ = o.stft(torch.from_numpy(wav))
+    mag = mags[:, :, 1:].contiguous()                   # [S, steps, 256]
+    eng = _engine(blob, max_streams=S)
+    eng.stream_reset()
+    state = o.zero_state(S)
+    worst = 0.0
+    for t in range(steps):
+        feed = {"input": mag[:, t].reshape(S, 1, 256, 1)}
+        feed.update({k.replace("_cur", "_prev"): v for k, v in state.items()})
+        with torch.no_grad():
+            res = o.frame_step(feed)
+        ref = res.pop("model_out").reshape(S, 256)
+        state = res
+        out = eng.stream_step_mag(mag[:, t].contiguous().cuda()).cpu()
+        worst = max(worst, float((out - ref).abs().max()))
+    assert worst <= TOL_MAG
+    from nunet_b200.interpreter import _engine_to_ref
+    names = eng.state_names()
+    assert len(names) == 130
+    for n in names:
+        ref = state[_engine_to_ref(n, "cur")]
+        for s in (0, S - 1):
+            got = eng.state_export(s, n)
+            assert np.abs(got - ref[s].reshape(-1).numpy()).max() <= TOL_MAG, n
+
+
+def test_streaming_with_ctfa_history_equals_offline(blob):
+    """Extension flag: with 31 frames of TA carried per stream the streaming engine computes the offline graph."""
+    from nunet_b200.synth import synth_clips
+    S, T = 2, 45
+    wav = synth_clips(S, 512 + 256 * (T - 1), first_clip=50)
+    off = _engine(blob, max_frames=S * T, ctfa_mode="causal_avg32")
+    _, est = off.forward_wav(torch.from_numpy(wav).cuda(), want_wav=False)
+    # magnitudes exactly as the offline engine saw them
+    mag = torch.from_numpy(off.debug_read("mag").reshape(S, T, 256)).cuda()
+    eng = _engine(blob, max_streams=S, stream_ctfa_history=True)
+    eng.stream_reset()
+    outs = [eng.stream_step_mag(mag[:, t].contiguous()) for t in range(T)]
+    out = torch.stack(outs, dim=1)
+    assert float((out - est[:, :, 1:]).abs().max()) <= 2e-4
+
+
+def test_streaming_wav_loop_matches_interpreter_loop(blob, oracles, weights):
+    """real_time_speech_enhancer (interpreter_proposed.py:15-370): hop in, hop out, DC 'edge' padding."""
+    from nunet_b200.interpreter import Interpreter, real_time_speech_enhancer
+    from nunet_b200.synth import synth_clips
+    noisy = synth_clips(1, 256 * 14, first_clip=60)[0]
+    mags = []
+    with torch.no_grad():
+        ref, _ = oracles["frame_div32"].real_time_speech_enhancer(noisy, dc_pad="edge", collect_mag=mags)
+    it = Interpreter(weights=weights)
+    out, times = real_time_speech_enhancer(noisy, it)
+    assert out.shape == ref.shape and len(times) == 13
+    assert np.abs(out - ref).max() <= TOL_WAV
+
+
+def test_signature_runner_contract(weights, oracles):
+    """131 tensors in, 131 out, reference names; foreign history arrays are honoured (import path)."""
+    from nunet_b200.interpreter import Interpreter
+    from nunet_b200.state_table import STATE_SHAPES
+    o = oracles["frame_div32"]
+    it = Interpreter(weights=weights)
+    it.allocate_tensors()
+    sig = it.get_signature_list()
+    assert list(sig) == ["nutls_lstm_sm"] and len(sig["nutls_lstm_sm"]["inputs"]) == 131
+    run = it.get_signature_runner("nutls_lstm_sm")
+    rng = np.random.default_rng(5)
+    state = {k: np.zeros(s, np.float32) for k, s in STATE_SHAPES.items()}
+    ostate = o.zero_state(1)
+    for step in range(4):
+        x = rng.uniform(0, 30, (1, 1, 256, 1)).astype(np.float32)
+        feed = {k.replace("_cur", "_prev"): v for k, v in state.items()}
+        if step == 2:   # hand back copies: forces the import path
+            feed = {k: v.copy() for k, v in feed.items()}
+        out = run(input=x, **feed)
+        assert len(out) == 131 and out["model_out"].shape == (1, 1, 256, 1)
+        ofeed = {"input": torch.from_numpy(x)}
+        ofeed.update({k.replace("_cur", "_prev"): v for k, v in ostate.items()})
+        with torch.no_grad():
+            ores = o.frame_step(ofeed)
+        assert np.abs(out["model_out"] - ores["model_out"].numpy()).max() <= TOL_MAG
+        ostate = {k: v for k, v in ores.items() if k != "model_out"}
+        state = {k: v for k, v in out.items() if k != "model_out"}
+        for k in ("msfe6_ee_cur1", "msfe4_dd2_cur3", "msfe6_de_cur1", "state_h", "msfe3_de_c"):
+            assert out[k].shape == tuple(STATE_SHAPES[k])
+            assert np.abs(out[k] - ostate[k].numpy()).max() <= TOL_MAG, k
+    with pytest.raises(ValueError):
+        run(input=x)                                   # missing history tensors
+    with pytest.raises(ValueError):
+        it.get_signature_runner("nope")
+
+
+def test_models_surface(weights, golden_io):
+    """models.NUTLS_LSTM(opt).build_model() -> model(x, training=False) (test_interface.py:45,58)."""
+    from nunet_b200 import models
+    from nunet_b200.options import default_options
+    m = models.NUTLS_LSTM(default_options())
+    model = m.build_model()
+    model.load_weights(weights)
+    y = model(golden_io["wav"], training=False)
+    assert isinstance(y, np.ndarray)
+    assert np.abs(y - golden_io["wav_causal_avg32"]).max() <= TOL_WAV
+    with pytest.raises(NotImplementedError):
+        model(golden_io["wav"], training=True)
+    fm = m.tflite_model().load_weights(weights)
+    out = fm(np.full((1, 1, 256, 1), 3.0, np.float32))
+    assert out.shape == (1, 1, 256, 1) and np.isfinite(out).all()
+
+
+def test_enhancement_quality_on_reference_excerpt(blob):
+    """Functional pin: on the reference's own noisy/clean pair the enhanced output must be much closer to clean
+    than the noisy input is."""
+    import os
+    from oracle.nunet_oracle import min_max_norm, si_sdr
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "wav_excerpt.npz"))
+    noisy = g["noisy"].astype(np.float64) / 32768.0
+    clean = g["clean"].astype(np.float64) / 32768.0
+    x = min_max_norm(noisy).astype(np.float32)[None]
+    eng = _engine(blob, max_frames=128)
+    y, _ = eng.forward_wav(torch.from_numpy(x).cuda())
+    y = y.cpu().numpy()[0]
+    before, after = si_sdr(clean[:len(y)], x[0, :len(y)]), si_sdr(clean[:len(y)], y)
+    assert after > before + 8.0, (before, after)
