@@ -75,6 +75,10 @@ typedef struct nunet_config {
 const char* nunet_last_error(void);
 int nunet_abi_version(void);
 
+/* Host-only check of a weight blob (no GPU needed): parses it, verifies every tensor the variant needs is present
+ * with the reference shape and packs the parameters.  Returns the packed float count or a negative error. */
+long long nunet_blob_validate(const void* blob, size_t blob_bytes, int variant);
+
 /* Replaces: NUTLS_LSTM(opt) + model.load_weights(path) (test_interface.py:45, converter_proposed.py:13) and
  * tf.lite.Interpreter(model_path) + allocate_tensors() (interpreter_proposed.py:374-375).
  * `blob` is the packed role-named weight set produced by nunet_b200.weights.pack_blob (HOST memory). */
@@ -125,6 +129,13 @@ int nunet_state_import(nunet_engine* h, int stream_id, const char* name, const f
 
 /* Introspection used by bench.py / tests: kernels launched by the most recent forward/step call. */
 int nunet_last_launch_count(nunet_engine* h);
+/* Per-launch profile of the NEXT forward/step calls (bench.py roofline leg): when enabled, a CUDA event is
+ * recorded on the launching stream after every kernel.  Entry i = (kernel name, device milliseconds since the
+ * previous event, algorithmic bytes = what that launch must read + write once). */
+int nunet_profile_enable(nunet_engine* h, int on);
+int nunet_profile_count(nunet_engine* h);
+int nunet_profile_entry(nunet_engine* h, int index, char* name_out, int cap, float* ms_out, double* alg_bytes_out);
+
 /* Debug tap: copy an intermediate tensor of the most recent OFFLINE forward to host (tests only).
  * Returns the element count (per call) or a negative error; buf may be NULL to query the size. */
 long long nunet_debug_read(nunet_engine* h, const char* tensor_name, float* buf, long long cap);

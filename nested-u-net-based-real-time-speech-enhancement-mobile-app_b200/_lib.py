@@ -17,11 +17,12 @@ NUNET_DC_ZERO, NUNET_DC_EDGE = 0, 1
 
 # every symbol include/nunet_b200.h declares (tests check the .so exports exactly these)
 EXPORTS = [
-    "nunet_last_error", "nunet_abi_version", "nunet_create", "nunet_destroy", "nunet_num_frames",
+    "nunet_last_error", "nunet_abi_version", "nunet_blob_validate", "nunet_create", "nunet_destroy", "nunet_num_frames",
     "nunet_forward_wav_dev", "nunet_forward_wav_host", "nunet_forward_mag_dev",
     "nunet_stream_reset", "nunet_stream_step_mag_dev", "nunet_stream_step_wav_dev", "nunet_stream_step_wav_host",
     "nunet_state_count", "nunet_state_name", "nunet_state_numel", "nunet_state_export", "nunet_state_import",
     "nunet_last_launch_count", "nunet_debug_read",
+    "nunet_profile_enable", "nunet_profile_count", "nunet_profile_entry",
 ]
 
 
@@ -52,6 +53,8 @@ def lib() -> C.CDLL:
     L.nunet_last_error.restype = C.c_char_p
     L.nunet_last_error.argtypes = []
     L.nunet_abi_version.restype = i
+    L.nunet_blob_validate.restype = ll
+    L.nunet_blob_validate.argtypes = [vp, C.c_size_t, i]
     L.nunet_create.restype = i
     L.nunet_create.argtypes = [C.POINTER(NunetConfig), vp, C.c_size_t, C.POINTER(vp)]
     L.nunet_destroy.restype = None
@@ -84,6 +87,12 @@ def lib() -> C.CDLL:
     L.nunet_state_import.argtypes = [vp, i, C.c_char_p, vp]
     L.nunet_last_launch_count.restype = i
     L.nunet_last_launch_count.argtypes = [vp]
+    L.nunet_profile_enable.restype = i
+    L.nunet_profile_enable.argtypes = [vp, i]
+    L.nunet_profile_count.restype = i
+    L.nunet_profile_count.argtypes = [vp]
+    L.nunet_profile_entry.restype = i
+    L.nunet_profile_entry.argtypes = [vp, i, C.c_char_p, i, C.POINTER(C.c_float), C.POINTER(C.c_double)]
     L.nunet_debug_read.restype = ll
     L.nunet_debug_read.argtypes = [vp, C.c_char_p, vp, ll]
     _ = fp

@@ -290,6 +290,17 @@ struct Engine {
     size_t h_in_cap = 0, h_out_cap = 0;
     int launches = 0;
     int last_B = 0, last_T = 0;
+    // per-launch profiling (bench.py roofline leg): one CUDA event after every launch on the launching stream
+    bool prof_on = false;
+    cudaStream_t prof_stream = nullptr;
+    std::string cur_op;
+    struct ProfEntry {
+        std::string name;
+        double alg_bytes;
+        cudaEvent_t ev;
+    };
+    std::vector<ProfEntry> prof;
+    cudaEvent_t prof_start = nullptr;
 
     ~Engine() {
         if (h_in) cudaFree(h_in);
@@ -439,7 +450,6 @@ struct Engine {
         win_off = pool.add(win);
         win_stream_off = pool.add(wins);
         inv_win_off = pool.add(inv);
-        pool.upload();
     }
 
     FramingTables tables(bool streaming) const {
@@ -451,10 +461,26 @@ struct Engine {
     }
 
     // -------------------------------------------------------------------------------- launches
-    void check_launch(const char* what) {
+    void check_launch(const char* what, double alg_bytes = 0.0) {
         cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) fail(NUNET_ECUDA, "launch %s: %s", what, cudaGetErrorString(e));
+        if (e != cudaSuccess) fail(NUNET_ECUDA, "launch %s (%s): %s", what, cur_op.c_str(), cudaGetErrorString(e));
         ++launches;
+        if (prof_on) {
+            ProfEntry pe;
+            pe.name = cur_op.empty() ? std::string(what) : cur_op + ":" + what;
+            pe.alg_bytes = alg_bytes;
+            CUDA_OK(cudaEventCreate(&pe.ev));
+            CUDA_OK(cudaEventRecord(pe.ev, prof_stream));
+            prof.push_back(pe);
+        }
+    }
+    void prof_begin(cudaStream_t st) {
+        prof_stream = st;
+        if (!prof_on) return;
+        for (auto& pe : prof) cudaEventDestroy(pe.ev);
+        prof.clear();
+        if (!prof_start) CUDA_OK(cudaEventCreate(&prof_start));
+        CUDA_OK(cudaEventRecord(prof_start, st));
     }
 
     template <int COUT, int CN, int PM, int NT, int EPI>
@@ -466,7 +492,8 @@ struct Engine {
             attr_set = true;
         }
         kfn<<<grid, NT, smem, st>>>(p);
-        check_launch("conv_unit");
+        const double frames = (double)p.B * p.T;
+        check_launch("conv_unit", frames * 4.0 * ((double)p.F_in * (p.CA + p.CB) + (double)p.F_out * COUT));
     }
 
     void launch_conv(const ConvLayer& L, const float* a_cur, const float* a_prev, const float* b_cur,
@@ -523,6 +550,7 @@ struct Engine {
         Ten* o = P.make(out_name, shuf ? 2 * F_conv : F_conv, shuf ? L.COUT / 2 : L.COUT, persistent);
         Plan* pp = &P;
         P.ops.push_back([=](Engine& E, const Run& r) {
+            E.cur_op = out_name;
             E.launch_conv(L, pp->cur(a, r.parity), pp->prev(a, r.parity), b ? pp->cur(b, r.parity) : nullptr,
                           b ? pp->prev(b, r.parity) : nullptr, pp->cur(o, r.parity), r.B, r.T, pp->streaming, F_in, r.st);
         });
@@ -550,19 +578,20 @@ struct Engine {
         Ten* o = P.make(out_name, x->F, x->C, persistent);
         Plan* pp = &P;
         P.ops.push_back([=](Engine& E, const Run& r) {
+            E.cur_op = out_name;
             const long long rows = (long long)r.B * r.T;
             const int blocks = (int)((rows + DENSE_RB - 1) / DENSE_RB);
             float* xwp = pp->cur(xw, 0);
             float* hsp = pp->cur(hs, 0);
             dense_rows_kernel<<<blocks, 128, DENSE_RB * D * sizeof(float), r.st>>>(pp->cur(x, r.parity), E.pool.at(L.wk),
                                                                                  E.pool.at(L.wb), xwp, rows, D, LSTM_GATES);
-            E.check_launch("lstm_in_proj");
+            E.check_launch("lstm_in_proj", rows * 4.0 * (D + LSTM_GATES));
             lstm_recur_kernel<<<r.B, 96, 0, r.st>>>(xwp, E.pool.at(L.wr), hst ? pp->cur(hst, 0) : nullptr,
                                                    cst ? pp->cur(cst, 0) : nullptr, hsp, r.T);
-            E.check_launch("lstm_recur");
+            E.check_launch("lstm_recur", rows * 4.0 * (LSTM_GATES + LSTM_UNITS));
             dense_rows_kernel<<<blocks, 128, DENSE_RB * LSTM_UNITS * sizeof(float), r.st>>>(
                 hsp, E.pool.at(L.dk), E.pool.at(L.db), pp->cur(o, r.parity), rows, LSTM_UNITS, D);
-            E.check_launch("lstm_dense");
+            E.check_launch("lstm_dense", rows * 4.0 * (D + LSTM_UNITS));
         });
         return o;
     }
@@ -618,20 +647,21 @@ struct Engine {
         Plan* pp = &P;
         const int off_mode = cfg.ctfa_mode;
         P.ops.push_back([=](Engine& E, const Run& r) {
+            E.cur_op = blk;
             const int frames = r.B * r.T;
             ctfa_ta_kernel<<<frames, 256, 0, r.st>>>(pp->cur(x, r.parity), E.mlpw(mta), pp->cur(ta, 0), F0);
-            E.check_launch("ctfa_ta");
+            E.check_launch("ctfa_ta", frames * 4.0 * (F0 * 64 + 64));
             const int div32 = pp->streaming ? 1 : (off_mode == NUNET_CTFA_FRAME_DIV32);
             ctfa_gate_kernel<<<frames, 64, 0, r.st>>>(pp->cur(ta, 0), E.mlpw(mfa), pp->cur(gate, 0), r.T, div32,
                                                      ring ? pp->cur(ring, 0) : nullptr, r.ring_pos);
-            E.check_launch("ctfa_gate");
+            E.check_launch("ctfa_gate", frames * 4.0 * (64 + 64));
             const long long n4 = (long long)frames * F0 * 16;
             const int blocks = (int)std::min<long long>((n4 + 255) / 256, 148LL * 16);
             gate_residual_kernel<<<blocks, 256, 0, r.st>>>(reinterpret_cast<const float4*>(pp->cur(x, r.parity)),
                                                           reinterpret_cast<const float4*>(pp->cur(en_in, r.parity)),
                                                           reinterpret_cast<const float4*>(pp->cur(gate, 0)),
                                                           reinterpret_cast<float4*>(pp->cur(out, r.parity)), n4, F0);
-            E.check_launch("gate_residual");
+            E.check_launch("gate_residual", frames * 4.0 * (3.0 * F0 * 64 + 64));
         });
         return out;
     }
@@ -641,12 +671,13 @@ struct Engine {
         const bool recycle = !P.streaming && !getenv("NUNET_NO_RECYCLE");
         Ten* x0 = P.make("input_layer", 256, 64, false);
         P.ops.push_back([=](Engine& E, const Run& r) {
+            E.cur_op = "input_layer";
             const long long npix = (long long)r.B * r.T * 256;
             const int blocks = (int)((npix * 8 + 255) / 256);
             const VecLayer& v = E.in_layer;
             input_layer_kernel<<<blocks, 256, 0, r.st>>>(r.mag_in, E.pool.at(v.w), E.pool.at(v.b), E.pool.at(v.gamma),
                                                         E.pool.at(v.beta), E.pool.at(v.alpha), pp->cur(x0, r.parity), npix);
-            E.check_launch("input_layer");
+            E.check_launch("input_layer", npix * 4.0 * 65);
         });
         Ten* x = x0;
         Ten* enc_des[6][6] = {};
@@ -670,11 +701,12 @@ struct Engine {
             if (recycle) P.release(m);
         }
         P.ops.push_back([=](Engine& E, const Run& r) {
+            E.cur_op = "out_conv";
             const long long npix = (long long)r.B * r.T * 256;
             const int blocks = (int)((npix * 16 + 255) / 256);
             out_conv_kernel<<<blocks, 256, 0, r.st>>>(pp->cur(y, r.parity), E.pool.at(E.out_layer.w), E.pool.at(E.out_layer.b),
                                                      r.est_out, npix, 256, r.est_stride, r.est_off);
-            E.check_launch("out_conv");
+            E.check_launch("out_conv", npix * 4.0 * 65);
         });
     }
 
@@ -723,6 +755,8 @@ struct Engine {
         if (!offline.arena) fail(NUNET_EINVAL, "offline path disabled (max_frames = 0)");
         if ((long long)B * T > offline.cap) fail(NUNET_ENOMEM, "B*T = %lld exceeds max_frames = %d", (long long)B * T, offline.cap);
         launches = 0;
+        cur_op = "framing";
+        prof_begin(st);
         const long long frames = (long long)B * T;
         float* mag = offline.cur(o_mag, 0);
         float2* ph = reinterpret_cast<float2*>(offline.cur(o_ph, 0));
@@ -730,16 +764,17 @@ struct Engine {
         float* fr = offline.cur(o_frames, 0);
         const int fblocks = (int)((frames + FRAMES_PER_CTA - 1) / FRAMES_PER_CTA);
         stft_kernel<<<fblocks, 32 * FRAMES_PER_CTA, 0, st>>>(wav, tables(false), mag, ph, B, T, n);
-        check_launch("stft");
+        check_launch("stft", frames * 4.0 * (256 + 256 + 514));
         forward_mag(mag, B, T, est, NBINS, 1, st);
         if (out_mag) CUDA_OK(cudaMemcpyAsync(out_mag, est, frames * NBINS * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        cur_op = "framing";
         if (out_wav) {
             istft_frames_kernel<<<fblocks, 32 * FRAMES_PER_CTA, 0, st>>>(est, ph, tables(false), fr, frames);
-            check_launch("istft_frames");
+            check_launch("istft_frames", frames * 4.0 * (257 + 514 + 512));
             const long long n_out = (long long)(T - 1) * HOP + NFFT;
             const int blocks = (int)std::min<long long>((B * n_out + 255) / 256, 148LL * 16);
             overlap_add_kernel<<<blocks, 256, 0, st>>>(fr, out_wav, B, T, n_out);
-            check_launch("overlap_add");
+            check_launch("overlap_add", frames * 4.0 * (512 + 256));
         }
     }
 
@@ -762,17 +797,20 @@ struct Engine {
     void stream_step_wav(const float* hop, int S, float* out_hop, float* out_mag, cudaStream_t st) {
         check_streams(S);
         launches = 0;
+        cur_op = "framing";
+        prof_begin(st);
         float* mag = stream.cur(s_mag, 0);
         float2* ph = reinterpret_cast<float2*>(stream.cur(s_ph, 0));
         float* est = stream.cur(s_est, 0);
         const int fblocks = (S + FRAMES_PER_CTA - 1) / FRAMES_PER_CTA;
         stream_analysis_kernel<<<fblocks, 32 * FRAMES_PER_CTA, 0, st>>>(hop, stream.cur(s_inbuf, 0), tables(true), mag, ph, S);
-        check_launch("stream_analysis");
+        check_launch("stream_analysis", S * 4.0 * (256 + 512 + 512 + 256 + 514));
         stream_step_mag(mag, S, est, st);
         if (out_mag) CUDA_OK(cudaMemcpyAsync(out_mag, est, (size_t)S * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        cur_op = "framing";
         stream_synthesis_kernel<<<fblocks, 32 * FRAMES_PER_CTA, 0, st>>>(est, ph, tables(true), stream.cur(s_outbuf, 0), out_hop, S,
                                                                        cfg.dc_mode == NUNET_DC_EDGE);
-        check_launch("stream_synthesis");
+        check_launch("stream_synthesis", S * 4.0 * (256 + 514 + 512 + 512 + 256));
     }
 
     void stream_reset(int first, int count, cudaStream_t st) {
@@ -850,6 +888,19 @@ int nunet_abi_version(void) { return NUNET_ABI_VERSION; }
 
 int nunet_num_frames(int n_samples) { return n_samples < NFFT ? 0 : 1 + (n_samples - NFFT) / HOP; }
 
+long long nunet_blob_validate(const void* blob, size_t blob_bytes, int variant) {
+    long long n = 0;
+    int rc = guarded([&] {
+        if (!blob) fail(NUNET_EINVAL, "null argument");
+        Engine E;
+        E.cfg.variant = variant;
+        E.blob.parse(blob, blob_bytes);
+        E.pack_params();
+        n = (long long)E.pool.host.size();
+    });
+    return rc == NUNET_OK ? n : rc;
+}
+
 int nunet_create(const nunet_config* cfg, const void* blob, size_t blob_bytes, nunet_engine** out) {
     if (out) *out = nullptr;
     std::unique_ptr<nunet_engine> h;
@@ -869,6 +920,7 @@ int nunet_create(const nunet_config* cfg, const void* blob, size_t blob_bytes, n
         E.cfg = *cfg;
         E.blob.parse(blob, blob_bytes);
         E.pack_params();
+        E.pool.upload();
         E.blob.m.clear();   // the host blob is not referenced after packing
         if (cfg->max_frames > 0) E.alloc_plan(E.offline, cfg->max_frames, false);
         if (cfg->max_streams > 0) E.alloc_plan(E.stream, cfg->max_streams, true);
@@ -933,6 +985,7 @@ int nunet_forward_mag_dev(nunet_engine* h, const float* mag, int B, int T, float
     return guarded([&] {
         if (!h || !mag || !out_mag) fail(NUNET_EINVAL, "null argument");
         h->e.launches = 0;
+        h->e.prof_begin(static_cast<cudaStream_t>(stream));
         h->e.forward_mag(mag, B, T, out_mag, 256, 0, static_cast<cudaStream_t>(stream));
     });
 }
@@ -948,6 +1001,7 @@ int nunet_stream_step_mag_dev(nunet_engine* h, const float* mag, int S, float* o
     return guarded([&] {
         if (!h || !mag || !out_mag) fail(NUNET_EINVAL, "null argument");
         h->e.launches = 0;
+        h->e.prof_begin(static_cast<cudaStream_t>(stream));
         h->e.stream_step_mag(mag, S, out_mag, static_cast<cudaStream_t>(stream));
     });
 }
@@ -1009,6 +1063,28 @@ int nunet_state_import(nunet_engine* h, int stream_id, const char* name, const f
 }
 
 int nunet_last_launch_count(nunet_engine* h) { return h ? h->e.launches : NUNET_EINVAL; }
+
+int nunet_profile_enable(nunet_engine* h, int on) {
+    if (!h) return NUNET_EINVAL;
+    h->e.prof_on = on != 0;
+    return NUNET_OK;
+}
+
+int nunet_profile_count(nunet_engine* h) { return h ? (int)h->e.prof.size() : NUNET_EINVAL; }
+
+int nunet_profile_entry(nunet_engine* h, int index, char* name_out, int cap, float* ms_out, double* alg_bytes_out) {
+    return guarded([&] {
+        if (!h || !name_out || !ms_out || !alg_bytes_out) fail(NUNET_EINVAL, "null argument");
+        Engine& E = h->e;
+        if (index < 0 || index >= (int)E.prof.size()) fail(NUNET_EINVAL, "profile index out of range");
+        CUDA_OK(cudaEventSynchronize(E.prof[index].ev));
+        float ms = 0.f;
+        CUDA_OK(cudaEventElapsedTime(&ms, index == 0 ? E.prof_start : E.prof[index - 1].ev, E.prof[index].ev));
+        *ms_out = ms;
+        *alg_bytes_out = E.prof[index].alg_bytes;
+        snprintf(name_out, (size_t)cap, "%s", E.prof[index].name.c_str());
+    });
+}
 
 long long nunet_debug_read(nunet_engine* h, const char* tensor_name, float* buf, long long cap) {
     long long n = 0;

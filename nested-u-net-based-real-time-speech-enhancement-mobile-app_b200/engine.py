@@ -71,6 +71,19 @@ class NunetEngine:
     def last_launch_count(self) -> int:
         return self._L.nunet_last_launch_count(self._h)
 
+    def profile(self, on: bool) -> None:
+        check(self._L.nunet_profile_enable(self._h, int(on)))
+
+    def profile_entries(self):
+        """[(kernel name, device ms, algorithmic bytes)] of the last profiled forward/step call."""
+        out = []
+        buf = C.create_string_buffer(128)
+        ms, nb = C.c_float(), C.c_double()
+        for i in range(check(self._L.nunet_profile_count(self._h))):
+            check(self._L.nunet_profile_entry(self._h, i, buf, 128, C.byref(ms), C.byref(nb)))
+            out.append((buf.value.decode(), float(ms.value), float(nb.value)))
+        return out
+
     # ------------------------------------------------------------------ offline
     def forward_wav(self, wav: torch.Tensor, want_wav: bool = True, want_mag: bool = True):
         """wav [B,N] (cuda) -> (enhanced wav [B,(T-1)*256+512] | None, est magnitudes [B,T,257] | None)."""

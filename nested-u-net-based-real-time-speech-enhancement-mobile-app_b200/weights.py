@@ -23,7 +23,8 @@ from .h5_reader import read_h5
 MAGIC = b"NUNETW01"
 VARIANT_LSTM = 0
 VARIANT_DDB = 1
-_ENTRY = struct.Struct("<64sI4IQ8x")  # name, ndim, dims[4], offset (floats), pad -> 96 bytes
+_ENTRY = struct.Struct("<64sI4IQ4x")  # name, ndim, dims[4], offset (floats), pad -> 96 bytes
+assert _ENTRY.size == 96
 
 # role (Dense that follows <role>_lstm) -> h5 group that actually holds it (proposed.py:47-63)
 DENSE_ROLE_TO_H5 = {
