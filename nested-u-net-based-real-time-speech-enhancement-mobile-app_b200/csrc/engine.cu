@@ -301,10 +301,21 @@ struct Engine {
     };
     std::vector<ProfEntry> prof;
     cudaEvent_t prof_start = nullptr;
+    // A handle owns ONE arena: calls issued on different streams are ordered through this event so that they
+    // never overlap on the device.
+    cudaEvent_t last_done = nullptr;
+    void order_begin(cudaStream_t st) {
+        if (!last_done) CUDA_OK(cudaEventCreateWithFlags(&last_done, cudaEventDisableTiming));
+        else CUDA_OK(cudaStreamWaitEvent(st, last_done, 0));
+    }
+    void order_end(cudaStream_t st) { CUDA_OK(cudaEventRecord(last_done, st)); }
 
     ~Engine() {
         if (h_in) cudaFree(h_in);
         if (h_out) cudaFree(h_out);
+        if (last_done) cudaEventDestroy(last_done);
+        for (auto& pe : prof) cudaEventDestroy(pe.ev);
+        if (prof_start) cudaEventDestroy(prof_start);
         if (own_stream) cudaStreamDestroy(own_stream);
     }
 
@@ -756,6 +767,7 @@ struct Engine {
         if ((long long)B * T > offline.cap) fail(NUNET_ENOMEM, "B*T = %lld exceeds max_frames = %d", (long long)B * T, offline.cap);
         launches = 0;
         cur_op = "framing";
+        order_begin(st);
         prof_begin(st);
         const long long frames = (long long)B * T;
         float* mag = offline.cur(o_mag, 0);
@@ -776,6 +788,7 @@ struct Engine {
             overlap_add_kernel<<<blocks, 256, 0, st>>>(fr, out_wav, B, T, n_out);
             check_launch("overlap_add", frames * 4.0 * (512 + 256));
         }
+        order_end(st);
     }
 
     void check_streams(int S) {
@@ -798,6 +811,7 @@ struct Engine {
         check_streams(S);
         launches = 0;
         cur_op = "framing";
+        order_begin(st);
         prof_begin(st);
         float* mag = stream.cur(s_mag, 0);
         float2* ph = reinterpret_cast<float2*>(stream.cur(s_ph, 0));
@@ -811,13 +825,16 @@ struct Engine {
         stream_synthesis_kernel<<<fblocks, 32 * FRAMES_PER_CTA, 0, st>>>(est, ph, tables(true), stream.cur(s_outbuf, 0), out_hop, S,
                                                                        cfg.dc_mode == NUNET_DC_EDGE);
         check_launch("stream_synthesis", S * 4.0 * (256 + 514 + 512 + 512 + 256));
+        order_end(st);
     }
 
     void stream_reset(int first, int count, cudaStream_t st) {
         if (!stream.arena) fail(NUNET_EINVAL, "streaming path disabled (max_streams = 0)");
         if (first < 0 || count < 0 || first + count > stream.cap) fail(NUNET_EINVAL, "stream range out of bounds");
+        order_begin(st);
         if (first == 0 && count == stream.cap) {
             CUDA_OK(cudaMemsetAsync(stream.arena, 0, stream.unit_floats * (size_t)stream.cap * sizeof(float), st));
+            order_end(st);
             return;
         }
         // every per-stream region is [cap][n] at offset off*cap: zero rows [first, first+count) of each
@@ -827,6 +844,7 @@ struct Engine {
             if (t->pingpong)
                 CUDA_OK(cudaMemsetAsync(stream.ptr(t->off[1]) + (size_t)first * n, 0, (size_t)count * n * sizeof(float), st));
         }
+        order_end(st);
     }
 
     const Plan::StateRef* find_state(const std::string& name) const {
@@ -969,6 +987,7 @@ int nunet_forward_wav_host(nunet_engine* h, const float* wav, int B, int n_sampl
         const size_t n_in = (size_t)B * n_samples, n_out = (size_t)B * ((size_t)(T - 1) * HOP + NFFT);
         if (n_in > E.h_in_cap || n_out > E.h_out_cap) fail(NUNET_ENOMEM, "host-call staging capacity exceeded");
         cudaStream_t st = E.own_stream;
+        E.order_begin(st);
         CUDA_OK(cudaMemcpyAsync(E.h_in, wav, n_in * sizeof(float), cudaMemcpyHostToDevice, st));
         float* est = nullptr;
         E.forward_wav(E.h_in, B, n_samples, out_wav ? E.h_out : nullptr, nullptr, st);
@@ -985,8 +1004,10 @@ int nunet_forward_mag_dev(nunet_engine* h, const float* mag, int B, int T, float
     return guarded([&] {
         if (!h || !mag || !out_mag) fail(NUNET_EINVAL, "null argument");
         h->e.launches = 0;
+        h->e.order_begin(static_cast<cudaStream_t>(stream));
         h->e.prof_begin(static_cast<cudaStream_t>(stream));
         h->e.forward_mag(mag, B, T, out_mag, 256, 0, static_cast<cudaStream_t>(stream));
+        h->e.order_end(static_cast<cudaStream_t>(stream));
     });
 }
 
@@ -1001,8 +1022,10 @@ int nunet_stream_step_mag_dev(nunet_engine* h, const float* mag, int S, float* o
     return guarded([&] {
         if (!h || !mag || !out_mag) fail(NUNET_EINVAL, "null argument");
         h->e.launches = 0;
+        h->e.order_begin(static_cast<cudaStream_t>(stream));
         h->e.prof_begin(static_cast<cudaStream_t>(stream));
         h->e.stream_step_mag(mag, S, out_mag, static_cast<cudaStream_t>(stream));
+        h->e.order_end(static_cast<cudaStream_t>(stream));
     });
 }
 
@@ -1020,6 +1043,7 @@ int nunet_stream_step_wav_host(nunet_engine* h, const float* hop, int S, float* 
         E.check_streams(S);
         cudaStream_t st = E.own_stream;
         const size_t n = (size_t)S * HOP;
+        E.order_begin(st);
         CUDA_OK(cudaMemcpyAsync(E.h_in, hop, n * sizeof(float), cudaMemcpyHostToDevice, st));
         E.stream_step_wav(E.h_in, S, E.h_out, nullptr, st);
         CUDA_OK(cudaMemcpyAsync(out_hop, E.h_out, n * sizeof(float), cudaMemcpyDeviceToHost, st));
