@@ -1,0 +1,439 @@
+// Fused causal convolution unit on the 5th-generation tensor cores (tcgen05, sm_100a), fp32-grade accuracy by
+// 3xTF32 error compensation:  a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi  with  x_hi = rna_tf32(x),
+// x_lo = rna_tf32(x - x_hi), fp32 accumulation in tensor memory (TMEM).  Same layer coverage and the same fused
+// epilogues (bias, two-pass LayerNorm over channels, PReLU, both sub-pixel shuffles) as conv_simt.cuh.
+//
+// "Flat padded implicit GEMM".  For one layer the output positions of the whole batch are laid out on ONE flat
+// axis  q = rho*P + x,  rho = clip*(T+padrow) + (t+padrow)  (one all-zero row in front of every clip when the unit
+// has a time tap),  x in [0,P)  a frequency position including the zero-pad columns.  A tap (kt,kf) of the
+// convolution is then a constant shift of q, so the A operand of every tap is the SAME shared-memory image read
+// through a UMMA descriptor whose start address is shifted by `tap_off` rows.  That only works for a layout in
+// which consecutive rows are a constant 16 bytes apart, hence the K-major *no-swizzle* canonical layout with
+// SBO = 128 B (8-row core matrices back to back) and the 4-channel K chunks in separate planes (LBO = plane):
+//      A_image[hi|lo][k_chunk][slot][4 floats]
+// Stride-2 units read two images (even / odd input bins) so that their taps are unit-stride shifts as well.
+// Pad rows / pad columns produce garbage accumulator rows that the epilogue simply does not store.
+//
+// CTA = 10 warps, persistent over 256-position tile pairs (two M=128 accumulators share every weight stage):
+//   warps 0-3  epilogue   TMEM -> registers (one thread owns one output position, all channels: LayerNorm is
+//                         thread-local), bias/LN/PReLU/shuffle, 128-bit global stores
+//   warps 4-7  A loaders  global NHWC -> hi/lo split -> shared image (double buffered per 16-channel phase)
+//   warp  8    MMA issuer one elected thread, tcgen05.mma kind::tf32, M=128, N=COUT, K=8
+//   warp  9    W producer cp.async.bulk (TMA 1-D) of pre-split, pre-laid-out weight stages, 4-stage mbarrier ring
+// TMEM: 2 (double buffer) x 2 (tile pair) x N columns <= 512.
+#pragma once
+#include "common.cuh"
+#include "conv_simt.cuh"   // Epi enum
+
+namespace nunet {
+
+constexpr int TC_KCH = 16;        // input channels per phase (2 MMA K-steps of 8)
+constexpr int TC_MT = 2;          // M=128 tiles per CTA iteration
+constexpr int TC_WSTAGES = 4;
+constexpr int TC_MAXTAPS = 6;
+constexpr int TC_THREADS = 320;
+
+struct TcParams {
+    const float* src0;   // [frames][F_in][C0]
+    const float* src1;   // [frames][F_in][C1] or null
+    const float* wpk;    // packed weights: [phase][tap][hi|lo][kchunk 4][N][4]
+    const float* bias;
+    const float* gamma;
+    const float* beta;
+    const float* alpha;
+    float* out;
+    int C0, C1;
+    int B, T, F_in, F_conv;
+    int P;               // flat positions per row
+    int padrow;          // 1: a zero row precedes every clip (units with a time tap)
+    int lead;            // image slot j <-> flat position q0 - lead + j
+    int xlo;             // output valid iff xlo <= x < xlo + F_conv; bin f = x - xlo
+    int nimg;
+    int img_mul[2], img_add[2];   // input bin of image position x: fi = mul*x + add (zero outside [0,F_in))
+    int ntaps;
+    int tap_img[TC_MAXTAPS], tap_off[TC_MAXTAPS];   // slot = m + tap_off
+    int nphase;          // (C0 + C1) / 16
+    int slots;           // image length (positions) = 256 + max tap_off
+    int plane_bytes;     // byte stride between K-chunk planes of the image, (plane_bytes/16) % 8 == 2
+    int total_flat;      // B * (T + padrow) * P  (< 2^31, checked on the host)
+    int ntiles;          // tile pairs
+};
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ uint32_t rna_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+// K-major, no swizzle: rows 16 B apart (SBO = 128 B per 8 rows), K chunks `lbo_bytes` apart.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((128u >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+    return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// LayerNorm (two-pass, like the reference's non-fused Keras path) + PReLU over v[0..CG) in place.
+template <int CG, int STRIDE>
+__device__ __forceinline__ void ln_prelu(float* v, const float* gamma, const float* beta, int goff, float alpha) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < CG; ++i) s += v[i * STRIDE];
+    const float mean = s * (1.0f / CG);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < CG; ++i) {
+        const float d = v[i * STRIDE] - mean;
+        q = fmaf(d, d, q);
+    }
+    const float inv = rsqrtf(q * (1.0f / CG) + LN_EPS);
+#pragma unroll
+    for (int i = 0; i < CG; ++i) {
+        const float sc = inv * __ldg(gamma + goff + i);
+        const float y = fmaf(v[i * STRIDE], sc, __ldg(beta + goff + i) - mean * sc);
+        v[i * STRIDE] = y >= 0.f ? y : alpha * y;
+    }
+}
+
+template <int N, int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    // carve: barriers | tmem ptr | W ring | A buffers
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* a_full = bars;                       // [2]
+    uint64_t* a_empty = bars + 2;                  // [2]
+    uint64_t* w_full = bars + 4;                   // [TC_WSTAGES]
+    uint64_t* w_empty = bars + 4 + TC_WSTAGES;     // [TC_WSTAGES]
+    uint64_t* acc_full = bars + 4 + 2 * TC_WSTAGES;   // [2]
+    uint64_t* acc_empty = acc_full + 2;            // [2]
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 24);
+    constexpr uint32_t WSTAGE_BYTES = 2 * (TC_KCH / 4) * N * 16;   // hi + lo
+    uint8_t* wring = smem_raw + 256;
+    const uint32_t abuf_bytes = (uint32_t)p.nimg * 2 * (TC_KCH / 4) * p.plane_bytes;
+    uint8_t* abuf0 = wring + TC_WSTAGES * WSTAGE_BYTES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr uint32_t ACC_COLS = 2 * TC_MT * N;          // 2 buffers x tile pair
+    constexpr uint32_t TMEM_COLS = ACC_COLS <= 32 ? 32 : (ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512)));
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&a_full[i], 128);
+            mbar_init(&a_empty[i], 1);
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 128);
+        }
+        for (int i = 0; i < TC_WSTAGES; ++i) {
+            mbar_init(&w_full[i], 1);
+            mbar_init(&w_empty[i], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_s;
+
+    const int Tp = p.T + p.padrow;
+    const int my_tiles = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles blockIdx.x, +grid, ...
+
+    if (warp < 4) {
+        // ================================================================= epilogue
+        const int row = threadIdx.x;   // TMEM lane == tile row
+        const float alpha = (EPI == EPI_BIAS) ? 0.f : __ldg(p.alpha);
+        for (int it = 0; it < my_tiles; ++it) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int ab = it & 1;
+            mbar_wait(&acc_full[ab], (it >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int mt = 0; mt < TC_MT; ++mt) {
+                const int q = tile * (TC_MT * 128) + mt * 128 + row;
+                const int rho = q / p.P;
+                const int x = q - rho * p.P;
+                const int b = rho / Tp;
+                const int t = (rho - b * Tp) - p.padrow;
+                const bool valid = (q < p.total_flat) && (t >= 0) && (x >= p.xlo) && (x < p.xlo + p.F_conv);
+                const int f = x - p.xlo;
+                const long long frame = (long long)b * p.T + t;
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((ab * TC_MT + mt) * N);
+                if (EPI == EPI_LN || EPI == EPI_BIAS) {
+                    float v[N];
+#pragma unroll
+                    for (int c = 0; c < N; c += 32) tmem_ld32(taddr + c, v + c);
+#pragma unroll
+                    for (int c = 0; c < N; ++c) v[c] += __ldg(p.bias + c);
+                    if (EPI == EPI_LN) ln_prelu<N, 1>(v, p.gamma, p.beta, 0, alpha);
+                    if (valid) {
+                        float4* o = reinterpret_cast<float4*>(p.out + (frame * p.F_conv + f) * N);
+#pragma unroll
+                        for (int c = 0; c < N / 4; ++c) o[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                    }
+                } else if (EPI == EPI_SHUF32) {
+                    // out[frame, 2f+j, i] = y[frame, f, 2i+j], LN over the 32 channels of each parity j
+                    float v[N];
+#pragma unroll
+                    for (int c = 0; c < N; c += 32) tmem_ld32(taddr + c, v + c);
+#pragma unroll
+                    for (int c = 0; c < N; ++c) v[c] += __ldg(p.bias + c);
+                    ln_prelu<N / 2, 2>(v, p.gamma, p.beta, 0, alpha);
+                    ln_prelu<N / 2, 2>(v + 1, p.gamma, p.beta, 0, alpha);
+                    if (valid) {
+                        float4* o = reinterpret_cast<float4*>(p.out + ((frame * p.F_conv + f) * 2) * (N / 2));
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+#pragma unroll
+                            for (int i = 0; i < N / 8; ++i)
+                                o[j * (N / 8) + i] = make_float4(v[8 * i + j], v[8 * i + 2 + j], v[8 * i + 4 + j], v[8 * i + 6 + j]);
+                    }
+                } else {
+                    // EPI_SHUF64: out[frame, 2f+h, 32j+i] = y[frame, f, 64h+2i+j], LN over the 64 channels of half h
+                    constexpr int H = N / 2;
+#pragma unroll 1
+                    for (int h = 0; h < 2; ++h) {
+                        float v[H];
+#pragma unroll
+                        for (int c = 0; c < H; c += 32) tmem_ld32(taddr + h * H + c, v + c);
+#pragma unroll
+                        for (int c = 0; c < H; ++c) v[c] += __ldg(p.bias + h * H + c);
+                        // LN statistics over all 64; gamma/beta are indexed by OUTPUT channel 32j+i for v[2i+j]
+                        float s = 0.f;
+#pragma unroll
+                        for (int c = 0; c < H; ++c) s += v[c];
+                        const float mean = s * (1.0f / H);
+                        float qq = 0.f;
+#pragma unroll
+                        for (int c = 0; c < H; ++c) {
+                            const float d = v[c] - mean;
+                            qq = fmaf(d, d, qq);
+                        }
+                        const float inv = rsqrtf(qq * (1.0f / H) + LN_EPS);
+                        if (valid) {
+                            float4* o = reinterpret_cast<float4*>(p.out + ((frame * p.F_conv + f) * 2 + h) * H);
+#pragma unroll
+                            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                                for (int i4 = 0; i4 < H / 8; ++i4) {
+                                    float r[4];
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        const int i = i4 * 4 + e;
+                                        const int oc = (H / 2) * j + i;
+                                        const float sc = inv * __ldg(p.gamma + oc);
+                                        const float y = fmaf(v[2 * i + j], sc, __ldg(p.beta + oc) - mean * sc);
+                                        r[e] = y >= 0.f ? y : alpha * y;
+                                    }
+                                    o[j * (H / 8) + i4] = make_float4(r[0], r[1], r[2], r[3]);
+                                }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[ab]);
+        }
+    } else if (warp < 8) {
+        // ================================================================= A loaders
+        const int lt = threadIdx.x - 128;   // 0..127
+        const int items = p.nimg * p.slots * (TC_KCH / 4);
+        int gph = 0;   // global phase counter (across tiles) -> buffer + parity
+        for (int it = 0; it < my_tiles; ++it) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int q0 = tile * (TC_MT * 128) - p.lead;
+            for (int ph = 0; ph < p.nphase; ++ph, ++gph) {
+                const int buf = gph & 1;
+                if (gph >= 2) mbar_wait(&a_empty[buf], ((gph >> 1) - 1) & 1);
+                uint8_t* ab = abuf0 + (size_t)buf * abuf_bytes;
+                const int c0 = ph * TC_KCH;
+                const float* src = (c0 < p.C0) ? p.src0 : p.src1;
+                const int C = (c0 < p.C0) ? p.C0 : p.C1;
+                const int cc = (c0 < p.C0) ? c0 : c0 - p.C0;
+                for (int base = 0; base < items; base += 128 * 4) {
+                    float4 val[4];
+                    int dst[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int idx = base + u * 128 + lt;
+                        val[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        dst[u] = -1;
+                        if (idx < items) {
+                            const int c4 = idx & 3;
+                            const int sj = idx >> 2;
+                            const int img = sj / p.slots;
+                            const int slot = sj - img * p.slots;
+                            dst[u] = ((img * 2) * (TC_KCH / 4) + c4) * p.plane_bytes + slot * 16;
+                            const int q = q0 + slot;
+                            if (q >= 0 && q < p.total_flat) {
+                                const int rho = q / p.P;
+                                const int x = q - rho * p.P;
+                                const int b = rho / Tp;
+                                const int t = (rho - b * Tp) - p.padrow;
+                                const int fi = p.img_mul[img] * x + p.img_add[img];
+                                if (t >= 0 && fi >= 0 && fi < p.F_in)
+                                    val[u] = __ldg(reinterpret_cast<const float4*>(
+                                        src + (((long long)b * p.T + t) * p.F_in + fi) * C + cc + c4 * 4));
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (dst[u] >= 0) {
+                            uint4 hi, lo;
+                            hi.x = rna_tf32(val[u].x); hi.y = rna_tf32(val[u].y); hi.z = rna_tf32(val[u].z); hi.w = rna_tf32(val[u].w);
+                            lo.x = rna_tf32(val[u].x - __uint_as_float(hi.x));
+                            lo.y = rna_tf32(val[u].y - __uint_as_float(hi.y));
+                            lo.z = rna_tf32(val[u].z - __uint_as_float(hi.z));
+                            lo.w = rna_tf32(val[u].w - __uint_as_float(hi.w));
+                            *reinterpret_cast<uint4*>(ab + dst[u]) = hi;
+                            *reinterpret_cast<uint4*>(ab + dst[u] + (TC_KCH / 4) * p.plane_bytes) = lo;
+                        }
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(&a_full[buf]);
+            }
+        }
+    } else if (warp == 8) {
+        // ================================================================= MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+            int gph = 0, gws = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                const int accb = it & 1;
+                if (it >= 2) mbar_wait(&acc_empty[accb], ((it >> 1) - 1) & 1);
+                tc_fence_after();
+                for (int ph = 0; ph < p.nphase; ++ph, ++gph) {
+                    const int buf = gph & 1;
+                    mbar_wait(&a_full[buf], (gph >> 1) & 1);
+                    tc_fence_after();
+                    const uint32_t a_base = smem_u32(abuf0 + (size_t)buf * abuf_bytes);
+                    for (int tap = 0; tap < p.ntaps; ++tap, ++gws) {
+                        const int ws = gws % TC_WSTAGES;
+                        mbar_wait(&w_full[ws], (gws / TC_WSTAGES) & 1);
+                        tc_fence_after();
+                        const uint32_t w_base = smem_u32(wring + (size_t)ws * WSTAGE_BYTES);
+                        const uint32_t a_img = a_base + (uint32_t)(p.tap_img[tap] * 2 * (TC_KCH / 4)) * p.plane_bytes +
+                                               (uint32_t)p.tap_off[tap] * 16;
+#pragma unroll
+                        for (int mt = 0; mt < TC_MT; ++mt) {
+                            const uint32_t d = tmem_base + (uint32_t)((accb * TC_MT + mt) * N);
+#pragma unroll
+                            for (int ks = 0; ks < TC_KCH / 8; ++ks) {
+                                const uint32_t a_hi = a_img + (uint32_t)(2 * ks) * p.plane_bytes + mt * 128 * 16;
+                                const uint32_t a_lo = a_hi + (TC_KCH / 4) * p.plane_bytes;
+                                const uint32_t b_hi = w_base + (uint32_t)(2 * ks) * N * 16;
+                                const uint32_t b_lo = b_hi + (TC_KCH / 4) * N * 16;
+                                const uint64_t da_hi = make_desc(a_hi, p.plane_bytes), da_lo = make_desc(a_lo, p.plane_bytes);
+                                const uint64_t db_hi = make_desc(b_hi, N * 16), db_lo = make_desc(b_lo, N * 16);
+                                const uint32_t first = (ph == 0 && tap == 0 && ks == 0) ? 0u : 1u;
+                                tc_mma_tf32(d, da_lo, db_hi, IDESC, first);   // small terms first
+                                tc_mma_tf32(d, da_hi, db_lo, IDESC, 1u);
+                                tc_mma_tf32(d, da_hi, db_hi, IDESC, 1u);
+                            }
+                        }
+                        tc_commit(&w_empty[ws]);
+                    }
+                    tc_commit(&a_empty[buf]);
+                }
+                tc_commit(&acc_full[accb]);
+            }
+        }
+    } else {
+        // ================================================================= weight producer (1-D TMA)
+        if (lane == 0) {
+            int gws = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                for (int ph = 0; ph < p.nphase; ++ph) {
+                    for (int tap = 0; tap < p.ntaps; ++tap, ++gws) {
+                        const int ws = gws % TC_WSTAGES;
+                        if (gws >= TC_WSTAGES) mbar_wait(&w_empty[ws], ((gws / TC_WSTAGES) - 1) & 1);
+                        mbar_arrive_expect_tx(&w_full[ws], WSTAGE_BYTES);
+                        bulk_g2s(wring + (size_t)ws * WSTAGE_BYTES,
+                                 reinterpret_cast<const uint8_t*>(p.wpk) + ((size_t)ph * p.ntaps + tap) * WSTAGE_BYTES, WSTAGE_BYTES,
+                                 &w_full[ws]);
+                    }
+                }
+            }
+        }
+    }
+
+    // ------------------------------------------------------------------ teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// host: round-to-nearest (ties away) fp32 -> tf32, the same rounding as cvt.rna.tf32.f32
+__host__ inline float host_rna_tf32(float x) {
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7F800000u) != 0x7F800000u) u = (u + 0x1000u) & 0xFFFFE000u;
+    float r;
+    memcpy(&r, &u, 4);
+    return r;
+}
+
+}  // namespace nunet

@@ -25,6 +25,7 @@
 
 #include "../../include/nunet_b200.h"
 #include "conv_simt.cuh"
+#include "conv_tc.cuh"
 #include "framing.cuh"
 #include "misc_kernels.cuh"
 
@@ -129,6 +130,7 @@ struct ParamPool {
 
 struct ConvLayer {
     size_t w = 0, bias = 0, gamma = 0, beta = 0, alpha = 0;
+    size_t wpk = 0;   // tensor-core path: hi/lo split weights [phase][tap][hi|lo][kchunk][N][4]
     int CA = 0, CB = 0, COUT = 0, KT = 1, KF = 1, padl = 0, stride = 1, epi = EPI_LN;
 };
 struct MlpLayer {
@@ -150,6 +152,25 @@ static std::vector<float> permute_cols(const std::vector<float>& k, int rows, in
     const int CN = conv_cn(COUT);
     for (int r = 0; r < rows; ++r)
         for (int q = 0; q < COUT; ++q) out[(size_t)r * COUT + q] = k[(size_t)r * COUT + conv_col_to_channel(q, COUT, CN)];
+    return out;
+}
+
+// logical [taps][Cin][COUT] -> 3xTF32 operand stages of conv_tc_kernel
+static std::vector<float> pack_tc(const std::vector<float>& k, int taps, int Cin, int COUT) {
+    const int nph = Cin / TC_KCH, KC4 = TC_KCH / 4;
+    std::vector<float> out((size_t)2 * taps * Cin * COUT);
+    for (int ph = 0; ph < nph; ++ph)
+        for (int tap = 0; tap < taps; ++tap)
+            for (int kc = 0; kc < KC4; ++kc)
+                for (int n = 0; n < COUT; ++n)
+                    for (int e = 0; e < 4; ++e) {
+                        const float w = k[((size_t)tap * Cin + ph * TC_KCH + kc * 4 + e) * COUT + n];
+                        const float hi = host_rna_tf32(w);
+                        const float lo = host_rna_tf32(w - hi);
+                        const size_t stage = ((size_t)ph * taps + tap) * (2 * KC4 * COUT * 4);
+                        out[stage + ((size_t)(0 * KC4 + kc) * COUT + n) * 4 + e] = hi;
+                        out[stage + ((size_t)(1 * KC4 + kc) * COUT + n) * 4 + e] = lo;
+                    }
     return out;
 }
 
@@ -290,6 +311,9 @@ struct Engine {
     size_t h_in_cap = 0, h_out_cap = 0;
     int launches = 0;
     int last_B = 0, last_T = 0;
+    int num_sms = 148;
+    bool use_tc = true;     // NUNET_CONV=simt forces the FP32 SIMT units everywhere
+    int tc_min_bins = 1;    // NUNET_TC_MIN_BINS: units with fewer conv-output bins stay on the SIMT kernel
     // per-launch profiling (bench.py roofline leg): one CUDA event after every launch on the launching stream
     bool prof_on = false;
     cudaStream_t prof_stream = nullptr;
@@ -331,6 +355,7 @@ struct Engine {
         L.CA = CA; L.CB = CB; L.COUT = COUT; L.KT = KT; L.KF = KF; L.padl = padl; L.stride = stride; L.epi = epi;
         std::vector<float> kv(k.data, k.data + k.n);
         L.w = pool.add(permute_cols(kv, KT * KF * (CA + CB), COUT));
+        L.wpk = pool.add(pack_tc(kv, KT * KF, CA + CB, COUT));
         L.bias = add_arr(role + "/bias", {COUT});
         if (epi != EPI_BIAS) {
             const int cln = (epi == EPI_LN) ? COUT : COUT / 2;
@@ -380,6 +405,7 @@ struct Engine {
         ConvLayer L;
         L.CA = 64; L.CB = 64; L.COUT = 128; L.KT = 1; L.KF = 2; L.padl = 1; L.stride = 1; L.epi = EPI_SHUF64;
         L.w = pool.add(permute_cols(W, 2 * 128, 128));
+        L.wpk = pool.add(pack_tc(W, 2, 128, 128));
         L.bias = pool.add(B);
         L.gamma = add_arr(in_role + "/gamma", {64});
         L.beta = add_arr(in_role + "/beta", {64});
@@ -507,8 +533,87 @@ struct Engine {
         check_launch("conv_unit", frames * 4.0 * ((double)p.F_in * (p.CA + p.CB) + (double)p.F_out * COUT));
     }
 
+    template <int N, int EPI>
+    void launch_tc_t(const TcParams& p, int grid, size_t smem, cudaStream_t st) {
+        static bool attr_set = false;
+        auto kfn = conv_tc_kernel<N, EPI>;
+        if (!attr_set) {
+            CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr_set = true;
+        }
+        kfn<<<grid, TC_THREADS, smem, st>>>(p);
+        const double frames = (double)p.B * p.T;
+        check_launch("conv_tc", frames * 4.0 * ((double)p.F_in * (p.C0 + p.C1) + (double)p.F_conv * N));
+    }
+
+    // Tensor-core path (offline plans).  Returns false when the unit is not eligible (caller falls back to SIMT).
+    bool launch_conv_tc(const ConvLayer& L, const float* a_cur, const float* b_cur, float* out, int B, int T, int F_in,
+                        cudaStream_t st) {
+        TcParams p{};
+        p.src0 = a_cur; p.src1 = b_cur; p.C0 = L.CA; p.C1 = L.CB;
+        p.wpk = pool.at(L.wpk); p.bias = pool.at(L.bias);
+        p.gamma = pool.at(L.gamma); p.beta = pool.at(L.beta); p.alpha = pool.at(L.alpha);
+        p.out = out; p.B = B; p.T = T; p.F_in = F_in;
+        p.F_conv = (L.stride == 2) ? F_in / 2 : F_in;
+        p.ntaps = L.KT * L.KF;
+        p.padrow = (L.KT == 2) ? 1 : 0;
+        p.nimg = 1;
+        p.img_mul[0] = 1; p.img_add[0] = 0; p.img_mul[1] = 1; p.img_add[1] = 0;
+        int maxoff = 0;
+        if (L.stride == 1 && L.KF == 3 && L.padl == 1 && L.KT == 2) {          // spconv
+            p.P = F_in + 2; p.img_add[0] = -1; p.lead = p.P + 1; p.xlo = 1;
+            for (int kt = 0; kt < 2; ++kt)
+                for (int kf = 0; kf < 3; ++kf) { p.tap_img[kt * 3 + kf] = 0; p.tap_off[kt * 3 + kf] = kt * p.P + kf; }
+        } else if (L.stride == 2 && L.KF == 3 && L.padl == 1 && L.KT == 2) {   // conv
+            p.P = p.F_conv + 1; p.nimg = 2; p.lead = p.P; p.xlo = 0;
+            p.img_mul[0] = 2; p.img_add[0] = 0; p.img_mul[1] = 2; p.img_add[1] = -1;
+            for (int kt = 0; kt < 2; ++kt) {
+                p.tap_img[kt * 3 + 0] = 1; p.tap_off[kt * 3 + 0] = kt * p.P;
+                p.tap_img[kt * 3 + 1] = 0; p.tap_off[kt * 3 + 1] = kt * p.P;
+                p.tap_img[kt * 3 + 2] = 1; p.tap_off[kt * 3 + 2] = kt * p.P + 1;
+            }
+        } else if (L.KT == 1 && L.KF == 1) {                                   // inconv 1x1
+            p.P = F_in; p.lead = 0; p.xlo = 0; p.tap_img[0] = 0; p.tap_off[0] = 0;
+        } else if (L.KT == 1 && L.KF == 3 && L.stride == 2 && L.padl == 0) {   // down_sampling
+            p.P = p.F_conv + 1; p.nimg = 2; p.lead = 0; p.xlo = 0;
+            p.img_mul[0] = 2; p.img_add[0] = 0; p.img_mul[1] = 2; p.img_add[1] = 1;
+            p.tap_img[0] = 0; p.tap_off[0] = 0; p.tap_img[1] = 1; p.tap_off[1] = 0; p.tap_img[2] = 0; p.tap_off[2] = 1;
+        } else if (L.KT == 1 && L.KF == 2 && L.stride == 1 && L.padl == 1) {   // up_sampling o inconv
+            p.P = F_in + 1; p.img_add[0] = -1; p.lead = 1; p.xlo = 1;
+            p.tap_img[0] = 0; p.tap_off[0] = 0; p.tap_img[1] = 0; p.tap_off[1] = 1;
+        } else {
+            return false;
+        }
+        for (int i = 0; i < p.ntaps; ++i) maxoff = std::max(maxoff, p.tap_off[i]);
+        p.slots = TC_MT * 128 + maxoff;
+        int plane16 = p.slots;
+        while (plane16 % 8 != 2) ++plane16;
+        p.plane_bytes = plane16 * 16;
+        p.nphase = (L.CA + L.CB) / TC_KCH;
+        const long long total = (long long)B * (T + p.padrow) * p.P;
+        if (total >= 0x7fffffffLL - 1024) return false;
+        p.total_flat = (int)total;
+        p.ntiles = (int)((total + TC_MT * 128 - 1) / (TC_MT * 128));
+        const size_t wstage = (size_t)2 * (TC_KCH / 4) * L.COUT * 16;
+        const size_t abuf = (size_t)p.nimg * 2 * (TC_KCH / 4) * p.plane_bytes;
+        const size_t smem = 256 + TC_WSTAGES * wstage + 2 * abuf;
+        if (smem > 227 * 1024) return false;
+        const int grid = std::min(p.ntiles, num_sms);
+        if (L.COUT == 32 && L.epi == EPI_LN) launch_tc_t<32, EPI_LN>(p, grid, smem, st);
+        else if (L.COUT == 64 && L.epi == EPI_LN) launch_tc_t<64, EPI_LN>(p, grid, smem, st);
+        else if (L.COUT == 64 && L.epi == EPI_BIAS) launch_tc_t<64, EPI_BIAS>(p, grid, smem, st);
+        else if (L.COUT == 64 && L.epi == EPI_SHUF32) launch_tc_t<64, EPI_SHUF32>(p, grid, smem, st);
+        else if (L.COUT == 128 && L.epi == EPI_SHUF64) launch_tc_t<128, EPI_SHUF64>(p, grid, smem, st);
+        else return false;
+        return true;
+    }
+
     void launch_conv(const ConvLayer& L, const float* a_cur, const float* a_prev, const float* b_cur,
                      const float* b_prev, float* out, int B, int T, bool has_prev, int F_in, cudaStream_t st) {
+        if (use_tc && !has_prev) {
+            const int F_conv = (L.stride == 2) ? F_in / 2 : F_in;
+            if (F_conv >= tc_min_bins && launch_conv_tc(L, a_cur, b_cur, out, B, T, F_in, st)) return;
+        }
         ConvParams p;
         p.a_cur = a_cur; p.a_prev = a_prev; p.b_cur = b_cur; p.b_prev = b_prev;
         p.w = pool.at(L.w); p.bias = pool.at(L.bias);
@@ -936,6 +1041,9 @@ int nunet_create(const nunet_config* cfg, const void* blob, size_t blob_bytes, n
         h.reset(new nunet_engine());
         Engine& E = h->e;
         E.cfg = *cfg;
+        E.num_sms = prop.multiProcessorCount;
+        if (const char* c = getenv("NUNET_CONV")) E.use_tc = strcmp(c, "simt") != 0;
+        if (const char* c = getenv("NUNET_TC_MIN_BINS")) E.tc_min_bins = atoi(c);
         E.blob.parse(blob, blob_bytes);
         E.pack_params();
         E.pool.upload();
