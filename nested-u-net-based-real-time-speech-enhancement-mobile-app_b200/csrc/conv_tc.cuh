@@ -32,6 +32,8 @@ constexpr int TC_MT = 2;          // M=128 tiles per CTA iteration
 constexpr int TC_WSTAGES = 4;
 constexpr int TC_MAXTAPS = 6;
 constexpr int TC_THREADS = 320;
+constexpr int TC_MAXABUF = 3;
+constexpr int TC_TBL_INTS = 2048;   // slot table: 2 tiles x (nimg*slots <= 1024)
 
 struct TcParams {
     const float* src0;   // [frames][F_in][C0]
@@ -57,6 +59,7 @@ struct TcParams {
     int plane_bytes;     // byte stride between K-chunk planes of the image, (plane_bytes/16) % 8 == 2
     int total_flat;      // B * (T + padrow) * P  (< 2^31, checked on the host)
     int ntiles;          // tile pairs
+    int nabuf;           // A image buffers in the ring (2 or 3)
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -157,15 +160,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
     extern __shared__ __align__(128) uint8_t smem_raw[];
     // carve: barriers | tmem ptr | W ring | A buffers
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
-    uint64_t* a_full = bars;                       // [2]
-    uint64_t* a_empty = bars + 2;                  // [2]
-    uint64_t* w_full = bars + 4;                   // [TC_WSTAGES]
-    uint64_t* w_empty = bars + 4 + TC_WSTAGES;     // [TC_WSTAGES]
-    uint64_t* acc_full = bars + 4 + 2 * TC_WSTAGES;   // [2]
+    uint64_t* a_full = bars;                       // [3]
+    uint64_t* a_empty = bars + 3;                  // [3]
+    uint64_t* w_full = bars + 6;                   // [TC_WSTAGES]
+    uint64_t* w_empty = bars + 6 + TC_WSTAGES;     // [TC_WSTAGES]
+    uint64_t* acc_full = bars + 6 + 2 * TC_WSTAGES;   // [2]
     uint64_t* acc_empty = acc_full + 2;            // [2]
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 24);
     constexpr uint32_t WSTAGE_BYTES = 2 * (TC_KCH / 4) * N * 16;   // hi + lo
-    uint8_t* wring = smem_raw + 256;
+    int* slot_tbl = reinterpret_cast<int*>(smem_raw + 256);        // [2][nimg*slots] input pixel index or -1
+    uint8_t* wring = smem_raw + 256 + TC_TBL_INTS * 4;
     const uint32_t abuf_bytes = (uint32_t)p.nimg * 2 * (TC_KCH / 4) * p.plane_bytes;
     uint8_t* abuf0 = wring + TC_WSTAGES * WSTAGE_BYTES;
 
@@ -174,9 +178,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
     constexpr uint32_t TMEM_COLS = ACC_COLS <= 32 ? 32 : (ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512)));
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < TC_MAXABUF; ++i) {
             mbar_init(&a_full[i], 128);
             mbar_init(&a_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
             mbar_init(&acc_full[i], 1);
             mbar_init(&acc_empty[i], 128);
         }
@@ -295,64 +301,85 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
         }
     } else if (warp < 8) {
         // ================================================================= A loaders
+        // Raw fp32 rows are copied global -> shared with cp.async (zero-filled outside the image) straight into the
+        // hi planes of a ring buffer, NB-1 phases ahead; each thread later converts exactly the items it copied
+        // (hi = rna_tf32(x) in place, lo = rna_tf32(x - hi) into the lo planes).  The position -> input-pixel map is
+        // the same for every phase of a tile, so it is computed once per tile into a small shared table.
         const int lt = threadIdx.x - 128;   // 0..127
-        const int items = p.nimg * p.slots * (TC_KCH / 4);
-        int gph = 0;   // global phase counter (across tiles) -> buffer + parity
-        for (int it = 0; it < my_tiles; ++it) {
+        const int nslot = p.nimg * p.slots;
+        const int items = nslot * (TC_KCH / 4);
+        const int NB = p.nabuf, D = NB - 1;
+        const int gtotal = my_tiles * p.nphase;
+        const uint32_t lo_off = (TC_KCH / 4) * p.plane_bytes;
+
+        auto build_table = [&](int it) {
             const int tile = blockIdx.x + it * gridDim.x;
             const int q0 = tile * (TC_MT * 128) - p.lead;
-            for (int ph = 0; ph < p.nphase; ++ph, ++gph) {
-                const int buf = gph & 1;
-                if (gph >= 2) mbar_wait(&a_empty[buf], ((gph >> 1) - 1) & 1);
-                uint8_t* ab = abuf0 + (size_t)buf * abuf_bytes;
-                const int c0 = ph * TC_KCH;
-                const float* src = (c0 < p.C0) ? p.src0 : p.src1;
-                const int C = (c0 < p.C0) ? p.C0 : p.C1;
-                const int cc = (c0 < p.C0) ? c0 : c0 - p.C0;
-                for (int base = 0; base < items; base += 128 * 4) {
-                    float4 val[4];
-                    int dst[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int idx = base + u * 128 + lt;
-                        val[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        dst[u] = -1;
-                        if (idx < items) {
-                            const int c4 = idx & 3;
-                            const int sj = idx >> 2;
-                            const int img = sj / p.slots;
-                            const int slot = sj - img * p.slots;
-                            dst[u] = ((img * 2) * (TC_KCH / 4) + c4) * p.plane_bytes + slot * 16;
-                            const int q = q0 + slot;
-                            if (q >= 0 && q < p.total_flat) {
-                                const int rho = q / p.P;
-                                const int x = q - rho * p.P;
-                                const int b = rho / Tp;
-                                const int t = (rho - b * Tp) - p.padrow;
-                                const int fi = p.img_mul[img] * x + p.img_add[img];
-                                if (t >= 0 && fi >= 0 && fi < p.F_in)
-                                    val[u] = __ldg(reinterpret_cast<const float4*>(
-                                        src + (((long long)b * p.T + t) * p.F_in + fi) * C + cc + c4 * 4));
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        if (dst[u] >= 0) {
-                            uint4 hi, lo;
-                            hi.x = rna_tf32(val[u].x); hi.y = rna_tf32(val[u].y); hi.z = rna_tf32(val[u].z); hi.w = rna_tf32(val[u].w);
-                            lo.x = rna_tf32(val[u].x - __uint_as_float(hi.x));
-                            lo.y = rna_tf32(val[u].y - __uint_as_float(hi.y));
-                            lo.z = rna_tf32(val[u].z - __uint_as_float(hi.z));
-                            lo.w = rna_tf32(val[u].w - __uint_as_float(hi.w));
-                            *reinterpret_cast<uint4*>(ab + dst[u]) = hi;
-                            *reinterpret_cast<uint4*>(ab + dst[u] + (TC_KCH / 4) * p.plane_bytes) = lo;
-                        }
-                    }
+            int* tb = slot_tbl + (it & 1) * (TC_TBL_INTS / 2);
+            for (int e = lt; e < nslot; e += 128) {
+                const int img = (e >= p.slots) ? 1 : 0;
+                const int slot = e - img * p.slots;
+                const int q = q0 + slot;
+                int off = -1;
+                if (q >= 0 && q < p.total_flat) {
+                    const int rho = q / p.P;
+                    const int x = q - rho * p.P;
+                    const int b = rho / Tp;
+                    const int t = (rho - b * Tp) - p.padrow;
+                    const int fi = p.img_mul[img] * x + p.img_add[img];
+                    if (t >= 0 && fi >= 0 && fi < p.F_in) off = (b * p.T + t) * p.F_in + fi;
                 }
-                fence_proxy_async();
-                mbar_arrive(&a_full[buf]);
+                tb[e] = off;
             }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        };
+        auto issue = [&](int g) {
+            const int it = g / p.nphase, ph = g - it * p.nphase;
+            if (ph == 0) build_table(it);
+            const int buf = g % NB;
+            if (g >= NB) mbar_wait(&a_empty[buf], ((g / NB) - 1) & 1);
+            uint8_t* ab = abuf0 + (size_t)buf * abuf_bytes;
+            const int* tb = slot_tbl + (it & 1) * (TC_TBL_INTS / 2);
+            const int c0 = ph * TC_KCH;
+            const float* src = (c0 < p.C0) ? p.src0 : p.src1;
+            const int C = (c0 < p.C0) ? p.C0 : p.C1;
+            const int cc = (c0 < p.C0) ? c0 : c0 - p.C0;
+            for (int idx = lt; idx < items; idx += 128) {
+                const int c4 = idx & 3, e = idx >> 2;
+                const int img = (e >= p.slots) ? 1 : 0;
+                const int slot = e - img * p.slots;
+                const int off = tb[e];
+                const float* gp = (off >= 0) ? (src + (size_t)off * C + cc + c4 * 4) : src;
+                cp_async16(ab + ((img * 2) * (TC_KCH / 4) + c4) * p.plane_bytes + slot * 16, gp, off >= 0 ? 16 : 0);
+            }
+        };
+        for (int g = 0; g < D && g < gtotal; ++g) {
+            issue(g);
+            cp_async_commit();
+        }
+        for (int g = 0; g < gtotal; ++g) {
+            if (D == 2) cp_async_wait<1>(); else cp_async_wait<0>();   // phase g has landed (this thread's items)
+            const int buf = g % NB;
+            uint8_t* ab = abuf0 + (size_t)buf * abuf_bytes;
+            for (int idx = lt; idx < items; idx += 128) {
+                const int c4 = idx & 3, e = idx >> 2;
+                const int img = (e >= p.slots) ? 1 : 0;
+                const int slot = e - img * p.slots;
+                uint8_t* d = ab + ((img * 2) * (TC_KCH / 4) + c4) * p.plane_bytes + slot * 16;
+                const float4 v = *reinterpret_cast<const float4*>(d);
+                uint4 hi, lo;
+                hi.x = rna_tf32(v.x); hi.y = rna_tf32(v.y); hi.z = rna_tf32(v.z); hi.w = rna_tf32(v.w);
+                lo.x = rna_tf32(v.x - __uint_as_float(hi.x));
+                lo.y = rna_tf32(v.y - __uint_as_float(hi.y));
+                lo.z = rna_tf32(v.z - __uint_as_float(hi.z));
+                lo.w = rna_tf32(v.w - __uint_as_float(hi.w));
+                *reinterpret_cast<uint4*>(d) = hi;
+                *reinterpret_cast<uint4*>(d + lo_off) = lo;
+            }
+            fence_proxy_async();
+            mbar_arrive(&a_full[buf]);
+            if (g + D < gtotal) issue(g + D);   // its buffer was last read by the MMAs of phase g - 1
+            cp_async_commit();
         }
     } else if (warp == 8) {
         // ================================================================= MMA issuer
@@ -364,8 +391,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
                 if (it >= 2) mbar_wait(&acc_empty[accb], ((it >> 1) - 1) & 1);
                 tc_fence_after();
                 for (int ph = 0; ph < p.nphase; ++ph, ++gph) {
-                    const int buf = gph & 1;
-                    mbar_wait(&a_full[buf], (gph >> 1) & 1);
+                    const int buf = gph % p.nabuf;
+                    mbar_wait(&a_full[buf], (gph / p.nabuf) & 1);
                     tc_fence_after();
                     const uint32_t a_base = smem_u32(abuf0 + (size_t)buf * abuf_bytes);
                     for (int tap = 0; tap < p.ntaps; ++tap, ++gws) {

@@ -596,7 +596,10 @@ struct Engine {
         p.ntiles = (int)((total + TC_MT * 128 - 1) / (TC_MT * 128));
         const size_t wstage = (size_t)2 * (TC_KCH / 4) * L.COUT * 16;
         const size_t abuf = (size_t)p.nimg * 2 * (TC_KCH / 4) * p.plane_bytes;
-        const size_t smem = 256 + TC_WSTAGES * wstage + 2 * abuf;
+        if (p.nimg * p.slots > TC_TBL_INTS / 2) return false;
+        const size_t fixed = 256 + TC_TBL_INTS * 4 + TC_WSTAGES * wstage;
+        p.nabuf = (fixed + 3 * abuf <= 227 * 1024) ? 3 : 2;
+        const size_t smem = fixed + p.nabuf * abuf;
         if (smem > 227 * 1024) return false;
         const int grid = std::min(p.ntiles, num_sms);
         if (L.COUT == 32 && L.epi == EPI_LN) launch_tc_t<32, EPI_LN>(p, grid, smem, st);

@@ -169,7 +169,8 @@ def test_streaming_with_ctfa_history_equals_offline(blob):
     eng.stream_reset()
     outs = [eng.stream_step_mag(mag[:, t].contiguous()) for t in range(T)]
     out = torch.stack(outs, dim=1)
-    assert float((out - est[:, :, 1:]).abs().max()) <= 2e-4
+    # offline runs the 3xTF32 tensor-core units, streaming the FP32 SIMT units: same function, different rounding
+    assert float((out - est[:, :, 1:]).abs().max()) <= TOL_MAG
 
 
 def test_streaming_wav_loop_matches_interpreter_loop(blob, oracles, weights):
