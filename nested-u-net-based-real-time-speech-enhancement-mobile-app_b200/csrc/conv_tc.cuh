@@ -34,6 +34,8 @@ constexpr int TC_MAXTAPS = 6;
 constexpr int TC_THREADS = 320;
 constexpr int TC_MAXABUF = 3;
 constexpr int TC_TBL_INTS = 2048;   // slot table: 2 tiles x (nimg*slots <= 1024)
+constexpr int TC_STAGE_PITCH = 68;  // floats per staged output row (64 + 4: conflict-free 128-bit rows)
+constexpr int TC_STAGE_BYTES = 4 * 32 * TC_STAGE_PITCH * 4 + 4 * 32 * 8;   // 4 epilogue warps: rows + row offsets
 
 struct TcParams {
     const float* src0;   // [frames][F_in][C0]
@@ -60,6 +62,7 @@ struct TcParams {
     int total_flat;      // B * (T + padrow) * P  (< 2^31, checked on the host)
     int ntiles;          // tile pairs
     int nabuf;           // A image buffers in the ring (2 or 3)
+    int mt;              // M=128 tiles per CTA iteration (1 or 2); tile = mt*128 flat positions
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -169,7 +172,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 24);
     constexpr uint32_t WSTAGE_BYTES = 2 * (TC_KCH / 4) * N * 16;   // hi + lo
     int* slot_tbl = reinterpret_cast<int*>(smem_raw + 256);        // [2][nimg*slots] input pixel index or -1
-    uint8_t* wring = smem_raw + 256 + TC_TBL_INTS * 4;
+    float* stage_all = reinterpret_cast<float*>(smem_raw + 256 + TC_TBL_INTS * 4);
+    long long* goff_all = reinterpret_cast<long long*>(smem_raw + 256 + TC_TBL_INTS * 4 + 4 * 32 * TC_STAGE_PITCH * 4);
+    uint8_t* wring = smem_raw + 256 + TC_TBL_INTS * 4 + TC_STAGE_BYTES;
     const uint32_t abuf_bytes = (uint32_t)p.nimg * 2 * (TC_KCH / 4) * p.plane_bytes;
     uint8_t* abuf0 = wring + TC_WSTAGES * WSTAGE_BYTES;
 
@@ -206,94 +211,93 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
 
     if (warp < 4) {
         // ================================================================= epilogue
+        // One thread owns one output position (TMEM lane) with all its channels, so LayerNorm is thread-local.
+        // The finished row is staged in shared memory and written out by the whole warp, 16 lanes per 256-byte
+        // row, so that every store instruction covers whole 128-byte lines (8x fewer LSU wavefronts than
+        // per-thread row stores).
         const int row = threadIdx.x;   // TMEM lane == tile row
         const float alpha = (EPI == EPI_BIAS) ? 0.f : __ldg(p.alpha);
+        float* stg = stage_all + warp * 32 * TC_STAGE_PITCH;
+        long long* goff = goff_all + warp * 32;
+        constexpr int ROWF = (N == 32) ? 32 : 64;          // floats per staged row
+        constexpr int PASSES = (EPI == EPI_SHUF64) ? 2 : 1;
+        constexpr int LPR = ROWF / 4;                      // lanes per row in the copy-out
+        constexpr int RPI = 32 / LPR;                      // rows per store instruction
         for (int it = 0; it < my_tiles; ++it) {
             const int tile = blockIdx.x + it * gridDim.x;
             const int ab = it & 1;
             mbar_wait(&acc_full[ab], (it >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int mt = 0; mt < TC_MT; ++mt) {
-                const int q = tile * (TC_MT * 128) + mt * 128 + row;
+            for (int mt = 0; mt < p.mt; ++mt) {
+                const int q = tile * (p.mt * 128) + mt * 128 + row;
                 const int rho = q / p.P;
                 const int x = q - rho * p.P;
                 const int b = rho / Tp;
                 const int t = (rho - b * Tp) - p.padrow;
                 const bool valid = (q < p.total_flat) && (t >= 0) && (x >= p.xlo) && (x < p.xlo + p.F_conv);
-                const int f = x - p.xlo;
-                const long long frame = (long long)b * p.T + t;
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((ab * TC_MT + mt) * N);
-                if (EPI == EPI_LN || EPI == EPI_BIAS) {
-                    float v[N];
-#pragma unroll
-                    for (int c = 0; c < N; c += 32) tmem_ld32(taddr + c, v + c);
-#pragma unroll
-                    for (int c = 0; c < N; ++c) v[c] += __ldg(p.bias + c);
-                    if (EPI == EPI_LN) ln_prelu<N, 1>(v, p.gamma, p.beta, 0, alpha);
-                    if (valid) {
-                        float4* o = reinterpret_cast<float4*>(p.out + (frame * p.F_conv + f) * N);
-#pragma unroll
-                        for (int c = 0; c < N / 4; ++c) o[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-                    }
-                } else if (EPI == EPI_SHUF32) {
-                    // out[frame, 2f+j, i] = y[frame, f, 2i+j], LN over the 32 channels of each parity j
-                    float v[N];
-#pragma unroll
-                    for (int c = 0; c < N; c += 32) tmem_ld32(taddr + c, v + c);
-#pragma unroll
-                    for (int c = 0; c < N; ++c) v[c] += __ldg(p.bias + c);
-                    ln_prelu<N / 2, 2>(v, p.gamma, p.beta, 0, alpha);
-                    ln_prelu<N / 2, 2>(v + 1, p.gamma, p.beta, 0, alpha);
-                    if (valid) {
-                        float4* o = reinterpret_cast<float4*>(p.out + ((frame * p.F_conv + f) * 2) * (N / 2));
-#pragma unroll
-                        for (int j = 0; j < 2; ++j)
-#pragma unroll
-                            for (int i = 0; i < N / 8; ++i)
-                                o[j * (N / 8) + i] = make_float4(v[8 * i + j], v[8 * i + 2 + j], v[8 * i + 4 + j], v[8 * i + 6 + j]);
-                    }
-                } else {
-                    // EPI_SHUF64: out[frame, 2f+h, 32j+i] = y[frame, f, 64h+2i+j], LN over the 64 channels of half h
-                    constexpr int H = N / 2;
+                const long long pix = ((long long)b * p.T + t) * p.F_conv + (x - p.xlo);   // conv-output pixel index
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((ab * p.mt + mt) * N);
 #pragma unroll 1
-                    for (int h = 0; h < 2; ++h) {
-                        float v[H];
+                for (int pass = 0; pass < PASSES; ++pass) {
+                    float v[ROWF];
 #pragma unroll
-                        for (int c = 0; c < H; c += 32) tmem_ld32(taddr + h * H + c, v + c);
+                    for (int c = 0; c < ROWF; c += 32) tmem_ld32(taddr + pass * ROWF + c, v + c);
 #pragma unroll
-                        for (int c = 0; c < H; ++c) v[c] += __ldg(p.bias + h * H + c);
-                        // LN statistics over all 64; gamma/beta are indexed by OUTPUT channel 32j+i for v[2i+j]
-                        float s = 0.f;
+                    for (int c = 0; c < ROWF; ++c) v[c] += __ldg(p.bias + pass * ROWF + c);
+                    if (EPI == EPI_LN) {
+                        ln_prelu<ROWF, 1>(v, p.gamma, p.beta, 0, alpha);
+                    } else if (EPI == EPI_SHUF32) {
+                        // out[frame, 2f+j, i] = y[frame, f, 2i+j]: LN over the 32 channels of each parity j
+                        ln_prelu<ROWF / 2, 2>(v, p.gamma, p.beta, 0, alpha);
+                        ln_prelu<ROWF / 2, 2>(v + 1, p.gamma, p.beta, 0, alpha);
+                    } else if (EPI == EPI_SHUF64) {
+                        // half h = pass: out[frame, 2f+h, 32j+i] = y[frame, f, 64h+2i+j]; LN over the 64 channels of the half,
+                        // gamma/beta indexed by the OUTPUT channel 32j+i
+                        float sum = 0.f;
 #pragma unroll
-                        for (int c = 0; c < H; ++c) s += v[c];
-                        const float mean = s * (1.0f / H);
+                        for (int c = 0; c < ROWF; ++c) sum += v[c];
+                        const float mean = sum * (1.0f / ROWF);
                         float qq = 0.f;
 #pragma unroll
-                        for (int c = 0; c < H; ++c) {
+                        for (int c = 0; c < ROWF; ++c) {
                             const float d = v[c] - mean;
                             qq = fmaf(d, d, qq);
                         }
-                        const float inv = rsqrtf(qq * (1.0f / H) + LN_EPS);
-                        if (valid) {
-                            float4* o = reinterpret_cast<float4*>(p.out + ((frame * p.F_conv + f) * 2 + h) * H);
+                        const float inv = rsqrtf(qq * (1.0f / ROWF) + LN_EPS);
 #pragma unroll
-                            for (int j = 0; j < 2; ++j)
-#pragma unroll
-                                for (int i4 = 0; i4 < H / 8; ++i4) {
-                                    float r[4];
-#pragma unroll
-                                    for (int e = 0; e < 4; ++e) {
-                                        const int i = i4 * 4 + e;
-                                        const int oc = (H / 2) * j + i;
-                                        const float sc = inv * __ldg(p.gamma + oc);
-                                        const float y = fmaf(v[2 * i + j], sc, __ldg(p.beta + oc) - mean * sc);
-                                        r[e] = y >= 0.f ? y : alpha * y;
-                                    }
-                                    o[j * (H / 8) + i4] = make_float4(r[0], r[1], r[2], r[3]);
-                                }
+                        for (int c = 0; c < ROWF; ++c) {
+                            const int oc = (ROWF / 2) * (c & 1) + (c >> 1);
+                            const float sc = inv * __ldg(p.gamma + oc);
+                            const float y = fmaf(v[c], sc, __ldg(p.beta + oc) - mean * sc);
+                            v[c] = y >= 0.f ? y : alpha * y;
                         }
                     }
+                    // stage the row in its final channel order
+                    float4* srow = reinterpret_cast<float4*>(stg + lane * TC_STAGE_PITCH);
+                    if (EPI == EPI_LN || EPI == EPI_BIAS) {
+#pragma unroll
+                        for (int k = 0; k < ROWF / 4; ++k) srow[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+#pragma unroll
+                            for (int i4 = 0; i4 < ROWF / 8; ++i4)
+                                srow[j * (ROWF / 8) + i4] = make_float4(v[8 * i4 + j], v[8 * i4 + 2 + j], v[8 * i4 + 4 + j], v[8 * i4 + 6 + j]);
+                    }
+                    long long off = -1;
+                    if (valid) off = (EPI == EPI_SHUF64) ? (pix * 2 + pass) * ROWF : pix * (long long)ROWF;
+                    goff[lane] = off;
+                    __syncwarp();
+#pragma unroll 4
+                    for (int i = 0; i < 32 / RPI; ++i) {
+                        const int r = i * RPI + lane / LPR, ch4 = lane % LPR;
+                        const long long o = goff[r];
+                        if (o >= 0)
+                            *reinterpret_cast<float4*>(p.out + o + ch4 * 4) =
+                                *reinterpret_cast<const float4*>(stg + r * TC_STAGE_PITCH + ch4 * 4);
+                    }
+                    __syncwarp();
                 }
             }
             tc_fence_before();
@@ -314,7 +318,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
 
         auto build_table = [&](int it) {
             const int tile = blockIdx.x + it * gridDim.x;
-            const int q0 = tile * (TC_MT * 128) - p.lead;
+            const int q0 = tile * (p.mt * 128) - p.lead;
             int* tb = slot_tbl + (it & 1) * (TC_TBL_INTS / 2);
             for (int e = lt; e < nslot; e += 128) {
                 const int img = (e >= p.slots) ? 1 : 0;
@@ -402,9 +406,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
                         const uint32_t w_base = smem_u32(wring + (size_t)ws * WSTAGE_BYTES);
                         const uint32_t a_img = a_base + (uint32_t)(p.tap_img[tap] * 2 * (TC_KCH / 4)) * p.plane_bytes +
                                                (uint32_t)p.tap_off[tap] * 16;
-#pragma unroll
-                        for (int mt = 0; mt < TC_MT; ++mt) {
-                            const uint32_t d = tmem_base + (uint32_t)((accb * TC_MT + mt) * N);
+#pragma unroll 1
+                        for (int mt = 0; mt < p.mt; ++mt) {
+                            const uint32_t d = tmem_base + (uint32_t)((accb * p.mt + mt) * N);
 #pragma unroll
                             for (int ks = 0; ks < TC_KCH / 8; ++ks) {
                                 const uint32_t a_hi = a_img + (uint32_t)(2 * ks) * p.plane_bytes + mt * 128 * 16;

@@ -585,22 +585,33 @@ struct Engine {
             return false;
         }
         for (int i = 0; i < p.ntaps; ++i) maxoff = std::max(maxoff, p.tap_off[i]);
-        p.slots = TC_MT * 128 + maxoff;
-        int plane16 = p.slots;
-        while (plane16 % 8 != 2) ++plane16;
-        p.plane_bytes = plane16 * 16;
         p.nphase = (L.CA + L.CB) / TC_KCH;
         const long long total = (long long)B * (T + p.padrow) * p.P;
         if (total >= 0x7fffffffLL - 1024) return false;
         p.total_flat = (int)total;
-        p.ntiles = (int)((total + TC_MT * 128 - 1) / (TC_MT * 128));
         const size_t wstage = (size_t)2 * (TC_KCH / 4) * L.COUT * 16;
-        const size_t abuf = (size_t)p.nimg * 2 * (TC_KCH / 4) * p.plane_bytes;
-        if (p.nimg * p.slots > TC_TBL_INTS / 2) return false;
-        const size_t fixed = 256 + TC_TBL_INTS * 4 + TC_WSTAGES * wstage;
-        p.nabuf = (fixed + 3 * abuf <= 227 * 1024) ? 3 : 2;
-        const size_t smem = fixed + p.nabuf * abuf;
-        if (smem > 227 * 1024) return false;
+        const size_t fixed = 256 + TC_TBL_INTS * 4 + TC_STAGE_BYTES + TC_WSTAGES * wstage;
+        const size_t limit = 227 * 1024;
+        // tile = mt x 128 positions; prefer two tiles per weight stage and a 3-deep image ring, shrink to fit
+        size_t smem = 0;
+        bool ok = false;
+        for (int mt = TC_MT; mt >= 1 && !ok; --mt)
+            for (int nb = 3; nb >= 2 && !ok; --nb) {
+                if (mt == 1 && nb == 3 && L.COUT == 128) continue;   // MMA-bound units: weight reuse matters more
+                p.mt = mt;
+                p.slots = mt * 128 + maxoff;
+                int plane16 = p.slots;
+                while (plane16 % 8 != 2) ++plane16;
+                p.plane_bytes = plane16 * 16;
+                const size_t abuf = (size_t)p.nimg * 2 * (TC_KCH / 4) * p.plane_bytes;
+                smem = fixed + nb * abuf;
+                if (smem <= limit && p.nimg * p.slots <= TC_TBL_INTS / 2) {
+                    p.nabuf = nb;
+                    ok = true;
+                }
+            }
+        if (!ok) return false;
+        p.ntiles = (int)((total + p.mt * 128 - 1) / (p.mt * 128));
         const int grid = std::min(p.ntiles, num_sms);
         if (L.COUT == 32 && L.epi == EPI_LN) launch_tc_t<32, EPI_LN>(p, grid, smem, st);
         else if (L.COUT == 64 && L.epi == EPI_LN) launch_tc_t<64, EPI_LN>(p, grid, smem, st);
