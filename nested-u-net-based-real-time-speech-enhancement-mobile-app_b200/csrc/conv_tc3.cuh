@@ -1,0 +1,381 @@
+// Fused causal convolution unit on tcgen05 (sm_100a) over "split-half" activations -- the offline hot path.
+//
+// Numerics: every operand x is carried as two IEEE halves  x ~= hi + lo,  hi = rn_f16(x), lo = rn_f16(x - hi)
+// (22 significant bits while |x| < 65504; the products hi*hi, hi*lo, lo*hi are exact in fp32), and a
+// contraction is three kind::f16 MMAs  a_lo*b_hi + a_hi*b_lo + a_hi*b_hi  accumulated in fp32 in tensor memory.
+// That is the accuracy of the 3xTF32 scheme of conv_tc.cuh at twice the tensor rate and half the shared-memory
+// operand traffic, and -- the point of the format -- the split is done ONCE by the producer's epilogue, so the
+// consumer's loaders are pure 16-byte cp.async copies (no conversion pass: the old kernel was bound by it).
+//
+// HBM format "sh16" of an activation tensor [pixel][C]: one 4*C-byte record per pixel, [C halves hi][C halves lo]
+// (same footprint as fp32, so the arena layout of the plan is unchanged).  Weights are pre-split on the host and
+// scaled by a power of two per layer so that their lo parts stay normal halves (undone in the epilogue).
+//
+// Geometry: the "flat padded implicit GEMM" of conv_tc.cuh -- output positions of the whole batch on one flat
+// axis q = rho*P + x with zero pad rows / columns, every tap a constant shift of q, so all taps read the SAME
+// shared-memory image through K-major no-swizzle UMMA descriptors (rows 16 B apart, 8-channel K chunks in planes):
+//      image[img][hi|lo][chunk 2][slot][8 halves],   one image buffer = 16 input channels = one K=16 MMA step.
+// Stride-2 units keep two images (even / odd input bins).
+//
+// Weights stay RESIDENT in shared memory for the whole (persistent) CTA: units with 128 conv channels (last spconv
+// of a block, up_sampling o inconv) are two independent 64-column problems (their LayerNorm runs over each half),
+// so CTA 2c / 2c+1 take half 0 / 1 of the same tiles and every CTA holds <= 96 KB of weights.  The host permutes
+// the weight columns into output-channel order, so the sub-pixel shuffles cost nothing here.
+//
+// CTA = 13 warps, persistent over tiles of mt*128 flat positions:
+//   warps 0-3   epilogue  TMEM -> registers (one thread = one position, all its channels: LayerNorm is
+//                         thread-local) -> bias / two-pass LN / PReLU -> hi/lo split -> staged 128-byte rows ->
+//                         coalesced global stores
+//   warps 4-11  loaders   cp.async (zero-filled pads) into a ring of image buffers, NB-1 buffers ahead
+//   warp  12    MMA       one elected thread: tcgen05.mma kind::f16, M=128, N, K=16; accumulators double-buffered
+#pragma once
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "conv_tc.cuh"   // mbarrier / tcgen05 PTX wrappers, make_desc, tmem_ld32, ln_prelu
+
+namespace nunet {
+
+constexpr int T3_KCH = 16;          // input channels per image buffer (one K=16 MMA step)
+constexpr int T3_MT = 2;            // M=128 tiles per CTA iteration
+constexpr int T3_MAXTAPS = 6;
+constexpr int T3_EPI_WARPS = 4;
+constexpr int T3_LD_WARPS = 8;
+constexpr int T3_LD_THREADS = 32 * T3_LD_WARPS;
+constexpr int T3_THREADS = 32 * (T3_EPI_WARPS + T3_LD_WARPS + 1);
+constexpr int T3_MAXNB = 6;         // image ring depth
+constexpr int T3_TBL_HALF = 1024;   // slot table entries per tile (nimg*slots <= 1024), double buffered
+constexpr int T3_MAXIT = T3_TBL_HALF * 4 / T3_LD_THREADS;   // cp.async items per loader thread per buffer
+constexpr int T3_STG_PITCH = 144;   // bytes per staged output row (128 + 16: conflict-free 16-byte rows)
+constexpr int T3_STG_BYTES = T3_EPI_WARPS * 32 * T3_STG_PITCH + T3_EPI_WARPS * 32 * 8;
+constexpr int T3_FIXED_BYTES = 256 + 2 * T3_TBL_HALF * 4 + T3_STG_BYTES;
+
+struct Tc3Params {
+    const uint8_t* src0;   // sh16 [frames][F_in][C0]
+    const uint8_t* src1;   // sh16 [frames][F_in][C1] or null
+    const uint8_t* wpk;    // [nhalf][phase][tap][hi|lo][chunk 2][N][8 halves]
+    const float* bias;     // [nhalf * N], packed-column order
+    const float* gamma;    // [PC] LayerNorm scale / offset by output channel
+    const float* beta;
+    const float* alpha;
+    uint8_t* out;          // sh16
+    float wscale_inv;      // undoes the power-of-two weight scale
+    int C0, C1;
+    int B, T, F_in, F_conv;
+    int P, padrow, lead, xlo;
+    int nimg;
+    int img_mul[2], img_add[2];
+    int ntaps;
+    int tap_img[T3_MAXTAPS], tap_off[T3_MAXTAPS];
+    int nphase;            // (C0 + C1) / 16
+    int slots;             // image length in positions = mt*128 + max tap_off
+    int plane_bytes;       // byte stride between the planes of an image buffer, (plane_bytes/16) % 8 == 2
+    int total_flat;        // B * (T + padrow) * P
+    int ntiles;
+    int nabuf;             // image ring depth (2..T3_MAXNB)
+    int mt;                // M=128 tiles per iteration (1 or 2)
+    int nhalf;             // 1, or 2: CTA parity selects the 64-column half
+    int w_half_bytes;      // nphase * ntaps * N * 64
+};
+
+__device__ __forceinline__ void cp_async16_s(uint32_t smem_dst, const void* gsrc, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {
+    switch (n) {
+        case 0: cp_async_wait<0>(); break;
+        case 1: cp_async_wait<1>(); break;
+        case 2: cp_async_wait<2>(); break;
+        case 3: cp_async_wait<3>(); break;
+        case 4: cp_async_wait<4>(); break;
+        default: cp_async_wait<5>(); break;
+    }
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// hi/lo split of 8 consecutive values into two 16-byte vectors of halves
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        const float2 hf = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+        h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+// 8 consecutive channels of an sh16 record back to floats
+__device__ __forceinline__ void join8(const uint4& hi, const uint4& lo, float* v) {
+    const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w}, l[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&h[i]));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&l[i]));
+        v[2 * i] = a.x + b.x;
+        v[2 * i + 1] = a.y + b.y;
+    }
+}
+
+// N: conv channels of this CTA (32 / 64); PC: channels per OUTPUT pixel (N, or 32 for the 64-column sub-pixel
+// shuffle that makes two pixels); LN: LayerNorm + PReLU over each PC-channel group (false: bias only).
+template <int N, int PC, bool LN>
+__global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* a_full = bars;                     // [T3_MAXNB]
+    uint64_t* a_empty = bars + T3_MAXNB;         // [T3_MAXNB]
+    uint64_t* acc_full = bars + 2 * T3_MAXNB;    // [2]
+    uint64_t* acc_empty = acc_full + 2;          // [2]
+    uint64_t* w_full = acc_empty + 2;            // [1]
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 24);
+    int* slot_tbl = reinterpret_cast<int*>(smem_raw + 256);
+    uint8_t* stage_all = smem_raw + 256 + 2 * T3_TBL_HALF * 4;
+    long long* goff_all = reinterpret_cast<long long*>(stage_all + T3_EPI_WARPS * 32 * T3_STG_PITCH);
+    uint8_t* wsm = smem_raw + T3_FIXED_BYTES;
+    uint8_t* abuf0 = wsm + p.w_half_bytes;
+    const uint32_t abuf_bytes = (uint32_t)p.nimg * 4 * p.plane_bytes;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int MMA_WARP = T3_EPI_WARPS + T3_LD_WARPS;
+    constexpr uint32_t ACC_COLS = 2 * T3_MT * N;
+    constexpr uint32_t TMEM_COLS = ACC_COLS <= 32 ? 32 : (ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512)));
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < T3_MAXNB; ++i) {
+            mbar_init(&a_full[i], T3_LD_THREADS);
+            mbar_init(&a_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 32 * T3_EPI_WARPS);
+        }
+        mbar_init(w_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_s;
+
+    const int Tp = p.T + p.padrow;
+    const int half = (int)blockIdx.x % p.nhalf;
+    const int cta = (int)blockIdx.x / p.nhalf, ncta = (int)gridDim.x / p.nhalf;
+    const int my_tiles = (cta < p.ntiles) ? (p.ntiles - cta + ncta - 1) / ncta : 0;
+    const int tile_pos = p.mt * 128;
+
+    if (warp < T3_EPI_WARPS) {
+        // ================================================================= epilogue
+        const int row = threadIdx.x;   // TMEM lane == tile row
+        const float alpha = LN ? __ldg(p.alpha) : 0.f;
+        const float* bias = p.bias + half * N;
+        uint8_t* stg = stage_all + warp * 32 * T3_STG_PITCH;
+        long long* goff = goff_all + warp * 32;
+        constexpr int PASSES = N / 32;     // 128-byte passes per row
+        for (int it = 0; it < my_tiles; ++it) {
+            const int tile = cta + it * ncta;
+            const int ab = it & 1;
+            mbar_wait(&acc_full[ab], (it >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int mt = 0; mt < p.mt; ++mt) {
+                const int q = tile * tile_pos + mt * 128 + row;
+                const int rho = q / p.P;
+                const int x = q - rho * p.P;
+                const int b = rho / Tp;
+                const int t = (rho - b * Tp) - p.padrow;
+                const bool valid = (q < p.total_flat) && (t >= 0) && (x >= p.xlo) && (x < p.xlo + p.F_conv);
+                const long long pix = ((long long)b * p.T + t) * p.F_conv + (x - p.xlo);   // conv-output pixel
+                goff[lane] = valid ? (pix * p.nhalf + half) * (long long)(N * 4) : -1;
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((ab * p.mt + mt) * N);
+                float v[N];
+#pragma unroll
+                for (int c = 0; c < N; c += 32) tmem_ld32(taddr + c, v + c);
+#pragma unroll
+                for (int c = 0; c < N; ++c) v[c] = fmaf(v[c], p.wscale_inv, __ldg(bias + c));
+                if (LN) {
+#pragma unroll
+                    for (int g = 0; g < N / PC; ++g) ln_prelu<PC, 1>(v + g * PC, p.gamma, p.beta, 0, alpha);
+                }
+#pragma unroll
+                for (int pass = 0; pass < PASSES; ++pass) {
+                    uint4* srow = reinterpret_cast<uint4*>(stg + lane * T3_STG_PITCH);
+                    if (PC == 32) {
+                        // pass = output pixel: [32 hi][32 lo]
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            uint4 hi, lo;
+                            split8(v + pass * 32 + 8 * k, hi, lo);
+                            srow[k] = hi;
+                            srow[4 + k] = lo;
+                        }
+                    } else {
+                        // 64-channel pixel: pass 0 = the 64 hi halves, pass 1 = the 64 lo halves
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            uint4 hi, lo;
+                            split8(v + 8 * k, hi, lo);
+                            srow[k] = (pass == 0) ? hi : lo;
+                        }
+                    }
+                    __syncwarp();
+#pragma unroll 4
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = i * 4 + (lane >> 3), ch = lane & 7;
+                        const long long o = goff[r];
+                        if (o >= 0)
+                            *reinterpret_cast<uint4*>(p.out + o + pass * 128 + ch * 16) =
+                                *reinterpret_cast<const uint4*>(stg + r * T3_STG_PITCH + ch * 16);
+                    }
+                    __syncwarp();
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[ab]);
+        }
+    } else if (warp < MMA_WARP) {
+        // ================================================================= loaders
+        // Item (slot e, part hi|lo, chunk): one 16-byte cp.async.  Thread lt owns j = lt & 3 = (part, chunk) and
+        // slots e = (lt >> 2) + 64 k: four neighbouring threads fetch the two 32-byte sectors of one pixel.
+        const int lt = threadIdx.x - 32 * T3_EPI_WARPS;
+        const int part = (lt >> 1) & 1, chunk = lt & 1;
+        const int e0 = lt >> 2;
+        const int nslot = p.nimg * p.slots;
+        const int nit = (nslot > e0) ? (nslot - e0 + 63) / 64 : 0;
+        uint32_t dst[T3_MAXIT];
+        int off[T3_MAXIT];
+#pragma unroll
+        for (int k = 0; k < T3_MAXIT; ++k) {
+            const int e = e0 + 64 * k;
+            const int img = (e >= p.slots) ? 1 : 0;
+            const int slot = e - img * p.slots;
+            dst[k] = (uint32_t)((img * 4 + part * 2 + chunk) * p.plane_bytes + slot * 16);
+            off[k] = -1;
+        }
+        const uint32_t abase = smem_u32(abuf0);
+        const int NB = p.nabuf, D = NB - 1;
+        int g = 0;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int tile = cta + it * ncta;
+            const int q0 = tile * tile_pos - p.lead;
+            int* tb = slot_tbl + (it & 1) * T3_TBL_HALF;
+            for (int e = lt; e < nslot; e += T3_LD_THREADS) {
+                const int img = (e >= p.slots) ? 1 : 0;
+                const int slot = e - img * p.slots;
+                const int q = q0 + slot;
+                int o = -1;
+                if (q >= 0 && q < p.total_flat) {
+                    const int rho = q / p.P;
+                    const int x = q - rho * p.P;
+                    const int b = rho / Tp;
+                    const int t = (rho - b * Tp) - p.padrow;
+                    const int fi = p.img_mul[img] * x + p.img_add[img];
+                    if (t >= 0 && fi >= 0 && fi < p.F_in) o = (b * p.T + t) * p.F_in + fi;
+                }
+                tb[e] = o;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(T3_LD_THREADS) : "memory");
+#pragma unroll
+            for (int k = 0; k < T3_MAXIT; ++k)
+                if (k < nit) off[k] = tb[e0 + 64 * k];
+            for (int ph = 0; ph < p.nphase; ++ph, ++g) {
+                const int buf = g % NB;
+                if (g >= NB) mbar_wait(&a_empty[buf], ((g / NB) - 1) & 1);
+                const int c0 = ph * T3_KCH;
+                const bool first = c0 < p.C0;
+                const uint8_t* src = first ? p.src0 : p.src1;
+                const int C = first ? p.C0 : p.C1;
+                const int cc = first ? c0 : c0 - p.C0;
+                const uint8_t* pb = src + part * C * 2 + (cc + chunk * 8) * 2;
+                const long long rec = 4LL * C;
+                const uint32_t bb = abase + (uint32_t)buf * abuf_bytes;
+#pragma unroll
+                for (int k = 0; k < T3_MAXIT; ++k)
+                    if (k < nit) {
+                        const int o = off[k];
+                        cp_async16_s(bb + dst[k], (o >= 0) ? pb + (long long)o * rec : pb, (o >= 0) ? 16 : 0);
+                    }
+                cp_async_commit();
+                if (g >= D) {
+                    cp_async_wait_dyn(D);          // this thread's copies of buffer g - D have landed
+                    fence_proxy_async();
+                    mbar_arrive(&a_full[(g - D) % NB]);
+                }
+            }
+        }
+        for (int r = (g < D ? g : D); r > 0; --r) {   // drain: buffers g - r
+            cp_async_wait_dyn(r - 1);
+            fence_proxy_async();
+            mbar_arrive(&a_full[(g - r) % NB]);
+        }
+    } else {
+        // ================================================================= MMA issuer (+ one-off weight load)
+        if (lane == 0) {
+            if (my_tiles > 0) {
+                mbar_arrive_expect_tx(w_full, (uint32_t)p.w_half_bytes);
+                const uint8_t* wg = p.wpk + (size_t)half * p.w_half_bytes;
+                for (int o = 0; o < p.w_half_bytes; o += 16384) {
+                    const int n = (p.w_half_bytes - o < 16384) ? p.w_half_bytes - o : 16384;
+                    bulk_g2s(wsm + o, wg + o, (uint32_t)n, w_full);
+                }
+                mbar_wait(w_full, 0);
+            }
+            constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);   // f16 x f16 -> f32
+            const uint32_t w_base0 = smem_u32(wsm);
+            const uint32_t a_base0 = smem_u32(abuf0);
+            int g = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                const int accb = it & 1;
+                if (it >= 2) mbar_wait(&acc_empty[accb], ((it >> 1) - 1) & 1);
+                tc_fence_after();
+                for (int ph = 0; ph < p.nphase; ++ph, ++g) {
+                    const int buf = g % p.nabuf;
+                    mbar_wait(&a_full[buf], (g / p.nabuf) & 1);
+                    tc_fence_after();
+                    const uint32_t a_base = a_base0 + (uint32_t)buf * abuf_bytes;
+                    for (int tap = 0; tap < p.ntaps; ++tap) {
+                        const uint32_t w_hi = w_base0 + (uint32_t)(ph * p.ntaps + tap) * (N * 64);
+                        const uint32_t w_lo = w_hi + 2 * N * 16;
+                        const uint64_t db_hi = make_desc(w_hi, N * 16), db_lo = make_desc(w_lo, N * 16);
+                        const uint32_t a_img = a_base + (uint32_t)(p.tap_img[tap] * 4) * p.plane_bytes + (uint32_t)p.tap_off[tap] * 16;
+#pragma unroll 1
+                        for (int mt = 0; mt < p.mt; ++mt) {
+                            const uint32_t d = tmem_base + (uint32_t)((accb * p.mt + mt) * N);
+                            const uint32_t a_hi = a_img + mt * 128 * 16;
+                            const uint32_t a_lo = a_hi + 2 * p.plane_bytes;
+                            const uint64_t da_hi = make_desc(a_hi, p.plane_bytes), da_lo = make_desc(a_lo, p.plane_bytes);
+                            const uint32_t acc = (ph == 0 && tap == 0) ? 0u : 1u;
+                            tc_mma_f16(d, da_lo, db_hi, IDESC, acc);   // small terms first
+                            tc_mma_f16(d, da_hi, db_lo, IDESC, 1u);
+                            tc_mma_f16(d, da_hi, db_hi, IDESC, 1u);
+                        }
+                    }
+                    tc_commit(&a_empty[buf]);
+                }
+                tc_commit(&acc_full[accb]);
+            }
+        }
+    }
+
+    // ------------------------------------------------------------------ teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+}  // namespace nunet

@@ -26,8 +26,10 @@
 #include "../../include/nunet_b200.h"
 #include "conv_simt.cuh"
 #include "conv_tc.cuh"
+#include "conv_tc3.cuh"
 #include "framing.cuh"
 #include "misc_kernels.cuh"
+#include "sh16_kernels.cuh"
 
 namespace nunet {
 
@@ -132,6 +134,10 @@ struct ConvLayer {
     size_t w = 0, bias = 0, gamma = 0, beta = 0, alpha = 0;
     size_t wpk = 0;   // tensor-core path: hi/lo split weights [phase][tap][hi|lo][kchunk][N][4]
     int CA = 0, CB = 0, COUT = 0, KT = 1, KF = 1, padl = 0, stride = 1, epi = EPI_LN;
+    // split-half tensor-core path (conv_tc3.cuh): fp16 hi/lo weights, columns in output-channel order
+    size_t w3 = 0, b3 = 0;   // float offsets into the pool (w3 holds raw halves)
+    int N3 = 0, PC3 = 0, nhalf3 = 1;
+    float wscale_inv = 1.0f;
 };
 struct MlpLayer {
     size_t k0, b0, k1, b1;
@@ -174,12 +180,55 @@ static std::vector<float> pack_tc(const std::vector<float>& k, int taps, int Cin
     return out;
 }
 
+// Packed column n of half h  <->  logical conv channel (the sub-pixel shuffles of models/proposed.py:227-237 are
+// folded into this order so that every output pixel's channels are contiguous columns).
+static int tc3_col_to_channel(int epi, int h, int n) {
+    if (epi == EPI_SHUF32) return 2 * (n % 32) + n / 32;             // column j*32+i  <-> channel 2i+j (pixel 2f+j)
+    if (epi == EPI_SHUF64) return 64 * h + 2 * (n % 32) + n / 32;    // column 32j+i of half h <-> channel 64h+2i+j
+    return n;
+}
+
+// logical [taps][Cin][COUT] -> resident fp16 hi/lo operand image of conv_tc3_kernel:
+// [half][phase][tap][hi|lo][chunk 2][N][8 halves], scaled by 2^s (s chosen so that max |w| lands in [2^14, 2^15)).
+static std::vector<float> pack_tc3(const std::vector<float>& k, int taps, int Cin, int COUT, int epi, int nhalf, int N,
+                                   float* scale_inv) {
+    float mx = 0.f;
+    for (float w : k) mx = std::max(mx, std::fabs(w));
+    int e = 0;
+    if (mx > 0.f) e = 14 - (int)std::floor(std::log2((double)mx));
+    e = std::max(-20, std::min(40, e));
+    const float scale = std::ldexp(1.0f, e);
+    *scale_inv = std::ldexp(1.0f, -e);
+    const int nph = Cin / T3_KCH;
+    std::vector<__half> out((size_t)nhalf * nph * taps * N * 32);
+    for (int h = 0; h < nhalf; ++h)
+        for (int ph = 0; ph < nph; ++ph)
+            for (int tap = 0; tap < taps; ++tap) {
+                const size_t stage = (((size_t)h * nph + ph) * taps + tap) * ((size_t)N * 32);
+                for (int ch = 0; ch < 2; ++ch)
+                    for (int n = 0; n < N; ++n)
+                        for (int e8 = 0; e8 < 8; ++e8) {
+                            const int ci = ph * T3_KCH + ch * 8 + e8;
+                            const int co = tc3_col_to_channel(epi, h, n);
+                            const float w = k[((size_t)tap * Cin + ci) * COUT + co] * scale;
+                            const __half hi = __float2half_rn(w);
+                            const __half lo = __float2half_rn(w - __half2float(hi));
+                            out[stage + ((size_t)(0 * 2 + ch) * N + n) * 8 + e8] = hi;
+                            out[stage + ((size_t)(1 * 2 + ch) * N + n) * 8 + e8] = lo;
+                        }
+            }
+    std::vector<float> raw(out.size() / 2);
+    memcpy(raw.data(), out.data(), out.size() * sizeof(__half));
+    return raw;
+}
+
 // ------------------------------------------------------------------------------------------ tensors / plans
 struct Ten {
     int F = 0, C = 0;
     size_t off[2] = {0, 0};   // float offset per unit (frame / stream) inside the arena; [1] only when ping-ponged
     bool scratch = false;     // offline: lives on the recyclable stack (offset fixed up by Plan::finalize)
     bool pingpong = false;    // streaming: two copies selected by step parity
+    bool sh = false;          // holds split-half records (sh16 plans) rather than floats
     std::string name;
     size_t numel() const { return (size_t)F * C; }
 };
@@ -202,6 +251,7 @@ using Op = std::function<void(Engine&, const Run&)>;
 // `scratch` (recycled by each nested sub-U-Net); streaming plans keep everything and ping-pong activations.
 struct Plan {
     bool streaming = false;
+    bool sh16 = false;           // activations are split-half records (conv_tc3.cuh) instead of fp32
     int cap = 0;                 // frames or streams
     float* arena = nullptr;
     size_t unit_floats = 0;      // floats per frame / stream
@@ -313,6 +363,7 @@ struct Engine {
     int last_B = 0, last_T = 0;
     int num_sms = 148;
     bool use_tc = true;     // NUNET_CONV=simt forces the FP32 SIMT units everywhere
+    bool use_tc3 = true;    // NUNET_CONV=tc keeps the 3xTF32 kernel (fp32 activations) for the offline plan
     int tc_min_bins = 1;    // NUNET_TC_MIN_BINS: units with fewer conv-output bins stay on the SIMT kernel
     // per-launch profiling (bench.py roofline leg): one CUDA event after every launch on the launching stream
     bool prof_on = false;
@@ -357,6 +408,10 @@ struct Engine {
         L.w = pool.add(permute_cols(kv, KT * KF * (CA + CB), COUT));
         L.wpk = pool.add(pack_tc(kv, KT * KF, CA + CB, COUT));
         L.bias = add_arr(role + "/bias", {COUT});
+        {
+            const Arr& bb = blob.get(role + "/bias", {COUT});
+            add_tc3(L, kv, std::vector<float>(bb.data, bb.data + bb.n));
+        }
         if (epi != EPI_BIAS) {
             const int cln = (epi == EPI_LN) ? COUT : COUT / 2;
             L.gamma = add_arr(role + "/gamma", {cln});
@@ -364,6 +419,17 @@ struct Engine {
             L.alpha = add_arr(role + "/alpha", {1});
         }
         convs[role] = L;
+    }
+
+    void add_tc3(ConvLayer& L, const std::vector<float>& kv, const std::vector<float>& bias) {
+        L.nhalf3 = (L.COUT == 128) ? 2 : 1;
+        L.N3 = L.COUT / L.nhalf3;
+        L.PC3 = (L.epi == EPI_SHUF32) ? 32 : L.N3;
+        L.w3 = pool.add(pack_tc3(kv, L.KT * L.KF, L.CA + L.CB, L.COUT, L.epi, L.nhalf3, L.N3, &L.wscale_inv));
+        std::vector<float> b3((size_t)L.COUT);
+        for (int h = 0; h < L.nhalf3; ++h)
+            for (int n = 0; n < L.N3; ++n) b3[(size_t)h * L.N3 + n] = bias[tc3_col_to_channel(L.epi, h, n)];
+        L.b3 = pool.add(b3);
     }
 
     // up_sampling (Conv2DTranspose (1,3) stride (1,2) 'same', models/proposed.py:260) followed by the decoder
@@ -407,6 +473,7 @@ struct Engine {
         L.w = pool.add(permute_cols(W, 2 * 128, 128));
         L.wpk = pool.add(pack_tc(W, 2, 128, 128));
         L.bias = pool.add(B);
+        add_tc3(L, W, B);
         L.gamma = add_arr(in_role + "/gamma", {64});
         L.beta = add_arr(in_role + "/beta", {64});
         L.alpha = add_arr(in_role + "/alpha", {1});
@@ -622,6 +689,103 @@ struct Engine {
         return true;
     }
 
+    template <int N, int PC, bool LN>
+    void launch_tc3_t(const Tc3Params& p, int grid, size_t smem, cudaStream_t st) {
+        static bool attr_set = false;
+        auto kfn = conv_tc3_kernel<N, PC, LN>;
+        if (!attr_set) {
+            CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr_set = true;
+        }
+        kfn<<<grid, T3_THREADS, smem, st>>>(p);
+        const double frames = (double)p.B * p.T;
+        check_launch("conv_tc3", frames * 4.0 * ((double)p.F_in * (p.C0 + p.C1) + (double)p.F_conv * N * p.nhalf));
+    }
+
+    // Split-half tensor-core path (offline plans with sh16 tensors): every conv unit of the topology is eligible.
+    void launch_conv_tc3(const ConvLayer& L, const float* a_cur, const float* b_cur, float* out, int B, int T, int F_in,
+                         cudaStream_t st) {
+        Tc3Params p{};
+        p.src0 = reinterpret_cast<const uint8_t*>(a_cur);
+        p.src1 = reinterpret_cast<const uint8_t*>(b_cur);
+        p.C0 = L.CA; p.C1 = L.CB;
+        p.wpk = reinterpret_cast<const uint8_t*>(pool.at(L.w3));
+        p.bias = pool.at(L.b3);
+        p.gamma = pool.at(L.gamma); p.beta = pool.at(L.beta); p.alpha = pool.at(L.alpha);
+        p.out = reinterpret_cast<uint8_t*>(out);
+        p.wscale_inv = L.wscale_inv;
+        p.B = B; p.T = T; p.F_in = F_in;
+        p.F_conv = (L.stride == 2) ? F_in / 2 : F_in;
+        p.ntaps = L.KT * L.KF;
+        p.padrow = (L.KT == 2) ? 1 : 0;
+        p.nimg = 1;
+        p.img_mul[0] = 1; p.img_add[0] = 0; p.img_mul[1] = 1; p.img_add[1] = 0;
+        if (L.stride == 1 && L.KF == 3 && L.padl == 1 && L.KT == 2) {          // spconv
+            p.P = F_in + 2; p.img_add[0] = -1; p.lead = p.P + 1; p.xlo = 1;
+            for (int kt = 0; kt < 2; ++kt)
+                for (int kf = 0; kf < 3; ++kf) { p.tap_img[kt * 3 + kf] = 0; p.tap_off[kt * 3 + kf] = kt * p.P + kf; }
+        } else if (L.stride == 2 && L.KF == 3 && L.padl == 1 && L.KT == 2) {   // conv
+            p.P = p.F_conv + 1; p.nimg = 2; p.lead = p.P; p.xlo = 0;
+            p.img_mul[0] = 2; p.img_add[0] = 0; p.img_mul[1] = 2; p.img_add[1] = -1;
+            for (int kt = 0; kt < 2; ++kt) {
+                p.tap_img[kt * 3 + 0] = 1; p.tap_off[kt * 3 + 0] = kt * p.P;
+                p.tap_img[kt * 3 + 1] = 0; p.tap_off[kt * 3 + 1] = kt * p.P;
+                p.tap_img[kt * 3 + 2] = 1; p.tap_off[kt * 3 + 2] = kt * p.P + 1;
+            }
+        } else if (L.KT == 1 && L.KF == 1) {                                   // inconv 1x1
+            p.P = F_in; p.lead = 0; p.xlo = 0; p.tap_img[0] = 0; p.tap_off[0] = 0;
+        } else if (L.KT == 1 && L.KF == 3 && L.stride == 2 && L.padl == 0) {   // down_sampling
+            p.P = p.F_conv + 1; p.nimg = 2; p.lead = 0; p.xlo = 0;
+            p.img_mul[0] = 2; p.img_add[0] = 0; p.img_mul[1] = 2; p.img_add[1] = 1;
+            p.tap_img[0] = 0; p.tap_off[0] = 0; p.tap_img[1] = 1; p.tap_off[1] = 0; p.tap_img[2] = 0; p.tap_off[2] = 1;
+        } else if (L.KT == 1 && L.KF == 2 && L.stride == 1 && L.padl == 1) {   // up_sampling o inconv
+            p.P = F_in + 1; p.img_add[0] = -1; p.lead = 1; p.xlo = 1;
+            p.tap_img[0] = 0; p.tap_off[0] = 0; p.tap_img[1] = 0; p.tap_off[1] = 1;
+        } else {
+            fail(NUNET_EINVAL, "conv_tc3: unsupported unit geometry");
+        }
+        int maxoff = 0;
+        for (int i = 0; i < p.ntaps; ++i) maxoff = std::max(maxoff, p.tap_off[i]);
+        p.nphase = (L.CA + L.CB) / T3_KCH;
+        p.nhalf = L.nhalf3;
+        p.w_half_bytes = p.nphase * p.ntaps * L.N3 * 64;
+        const long long total = (long long)B * (T + p.padrow) * p.P;
+        if (total >= 0x7fffffffLL - 1024) fail(NUNET_EINVAL, "conv_tc3: more than 2^31 flat positions");
+        p.total_flat = (int)total;
+        const size_t fixed = (size_t)T3_FIXED_BYTES + (size_t)p.w_half_bytes;
+        const size_t limit = 227 * 1024;
+        // tile = mt x 128 positions; prefer two tiles per iteration unless that leaves a ring of fewer than three
+        // image buffers while one tile would allow it (the ring depth is what hides the HBM latency)
+        auto geometry = [&](int mt, int& slots, int& plane_bytes, size_t& abuf) {
+            slots = mt * 128 + maxoff;
+            int plane16 = slots;
+            while (plane16 % 8 != 2) ++plane16;
+            plane_bytes = plane16 * 16;
+            abuf = (size_t)p.nimg * 4 * plane_bytes;
+            if (p.nimg * slots > T3_TBL_HALF || fixed + 2 * abuf > limit) return 0;
+            return (int)std::min<size_t>((limit - fixed) / abuf, (size_t)T3_MAXNB);
+        };
+        int slots2, plane2, slots1, plane1;
+        size_t abuf2, abuf1;
+        const int nb2 = geometry(2, slots2, plane2, abuf2), nb1 = geometry(1, slots1, plane1, abuf1);
+        const bool ok = nb2 >= 2 || nb1 >= 2;
+        const bool two = nb2 >= 3 || (nb2 >= 2 && nb1 < 3);
+        p.mt = two ? 2 : 1;
+        p.slots = two ? slots2 : slots1;
+        p.plane_bytes = two ? plane2 : plane1;
+        p.nabuf = two ? nb2 : nb1;
+        const size_t smem = fixed + (size_t)p.nabuf * (two ? abuf2 : abuf1);
+        if (!ok) fail(NUNET_EINVAL, "conv_tc3: unit does not fit shared memory");
+        p.ntiles = (int)((total + p.mt * 128 - 1) / (p.mt * 128));
+        const int grid = std::max(1, std::min(p.ntiles, num_sms / p.nhalf)) * p.nhalf;
+        const bool ln = (L.epi != EPI_BIAS);
+        if (L.N3 == 32 && L.PC3 == 32 && ln) launch_tc3_t<32, 32, true>(p, grid, smem, st);
+        else if (L.N3 == 64 && L.PC3 == 64 && ln) launch_tc3_t<64, 64, true>(p, grid, smem, st);
+        else if (L.N3 == 64 && L.PC3 == 64 && !ln) launch_tc3_t<64, 64, false>(p, grid, smem, st);
+        else if (L.N3 == 64 && L.PC3 == 32 && ln) launch_tc3_t<64, 32, true>(p, grid, smem, st);
+        else fail(NUNET_EINVAL, "conv_tc3: no kernel for N=%d PC=%d", L.N3, L.PC3);
+    }
+
     void launch_conv(const ConvLayer& L, const float* a_cur, const float* a_prev, const float* b_cur,
                      const float* b_prev, float* out, int B, int T, bool has_prev, int F_in, cudaStream_t st) {
         if (use_tc && !has_prev) {
@@ -678,9 +842,15 @@ struct Engine {
         const int F_conv = (L.stride == 2) ? F_in / 2 : F_in;
         const bool shuf = (L.epi == EPI_SHUF32 || L.epi == EPI_SHUF64);
         Ten* o = P.make(out_name, shuf ? 2 * F_conv : F_conv, shuf ? L.COUT / 2 : L.COUT, persistent);
+        o->sh = P.sh16;
         Plan* pp = &P;
         P.ops.push_back([=](Engine& E, const Run& r) {
             E.cur_op = out_name;
+            if (pp->sh16) {
+                E.launch_conv_tc3(L, pp->cur(a, r.parity), b ? pp->cur(b, r.parity) : nullptr, pp->cur(o, r.parity), r.B, r.T,
+                                  F_in, r.st);
+                return;
+            }
             E.launch_conv(L, pp->cur(a, r.parity), pp->prev(a, r.parity), b ? pp->cur(b, r.parity) : nullptr,
                           b ? pp->prev(b, r.parity) : nullptr, pp->cur(o, r.parity), r.B, r.T, pp->streaming, F_in, r.st);
         });
@@ -706,6 +876,7 @@ struct Engine {
             P.states.push_back(sc);
         }
         Ten* o = P.make(out_name, x->F, x->C, persistent);
+        o->sh = P.sh16;
         Plan* pp = &P;
         P.ops.push_back([=](Engine& E, const Run& r) {
             E.cur_op = out_name;
@@ -713,14 +884,23 @@ struct Engine {
             const int blocks = (int)((rows + DENSE_RB - 1) / DENSE_RB);
             float* xwp = pp->cur(xw, 0);
             float* hsp = pp->cur(hs, 0);
-            dense_rows_kernel<<<blocks, 128, DENSE_RB * D * sizeof(float), r.st>>>(pp->cur(x, r.parity), E.pool.at(L.wk),
-                                                                                 E.pool.at(L.wb), xwp, rows, D, LSTM_GATES);
+            const int xC = x->C;
+            if (pp->sh16)
+                dense_rows_sh_kernel<true, false><<<blocks, 128, DENSE_RB * D * sizeof(float), r.st>>>(
+                    pp->cur(x, r.parity), E.pool.at(L.wk), E.pool.at(L.wb), xwp, rows, D, LSTM_GATES, xC);
+            else
+                dense_rows_kernel<<<blocks, 128, DENSE_RB * D * sizeof(float), r.st>>>(pp->cur(x, r.parity), E.pool.at(L.wk),
+                                                                                     E.pool.at(L.wb), xwp, rows, D, LSTM_GATES);
             E.check_launch("lstm_in_proj", rows * 4.0 * (D + LSTM_GATES));
             lstm_recur_kernel<<<r.B, 96, 0, r.st>>>(xwp, E.pool.at(L.wr), hst ? pp->cur(hst, 0) : nullptr,
                                                    cst ? pp->cur(cst, 0) : nullptr, hsp, r.T);
             E.check_launch("lstm_recur", rows * 4.0 * (LSTM_GATES + LSTM_UNITS));
-            dense_rows_kernel<<<blocks, 128, DENSE_RB * LSTM_UNITS * sizeof(float), r.st>>>(
-                hsp, E.pool.at(L.dk), E.pool.at(L.db), pp->cur(o, r.parity), rows, LSTM_UNITS, D);
+            if (pp->sh16)
+                dense_rows_sh_kernel<false, true><<<blocks, 128, DENSE_RB * LSTM_UNITS * sizeof(float), r.st>>>(
+                    hsp, E.pool.at(L.dk), E.pool.at(L.db), pp->cur(o, r.parity), rows, LSTM_UNITS, D, xC);
+            else
+                dense_rows_kernel<<<blocks, 128, DENSE_RB * LSTM_UNITS * sizeof(float), r.st>>>(
+                    hsp, E.pool.at(L.dk), E.pool.at(L.db), pp->cur(o, r.parity), rows, LSTM_UNITS, D);
             E.check_launch("lstm_dense", rows * 4.0 * (D + LSTM_UNITS));
         });
         return o;
@@ -773,24 +953,38 @@ struct Engine {
             P.rings.push_back(ring);
         }
         Ten* out = P.make(blk + "_out", F0, 64, out_persistent);
+        out->sh = P.sh16;
         const MlpLayer mta = mlps.at(blk + "_ta"), mfa = mlps.at(blk + "_fa");
         Plan* pp = &P;
         const int off_mode = cfg.ctfa_mode;
         P.ops.push_back([=](Engine& E, const Run& r) {
             E.cur_op = blk;
             const int frames = r.B * r.T;
-            ctfa_ta_kernel<<<frames, 256, 0, r.st>>>(pp->cur(x, r.parity), E.mlpw(mta), pp->cur(ta, 0), F0);
+            if (pp->sh16)
+                ctfa_ta_sh_kernel<<<frames, 256, 0, r.st>>>(reinterpret_cast<const uint8_t*>(pp->cur(x, r.parity)), E.mlpw(mta),
+                                                           pp->cur(ta, 0), F0);
+            else
+                ctfa_ta_kernel<<<frames, 256, 0, r.st>>>(pp->cur(x, r.parity), E.mlpw(mta), pp->cur(ta, 0), F0);
             E.check_launch("ctfa_ta", frames * 4.0 * (F0 * 64 + 64));
             const int div32 = pp->streaming ? 1 : (off_mode == NUNET_CTFA_FRAME_DIV32);
             ctfa_gate_kernel<<<frames, 64, 0, r.st>>>(pp->cur(ta, 0), E.mlpw(mfa), pp->cur(gate, 0), r.T, div32,
                                                      ring ? pp->cur(ring, 0) : nullptr, r.ring_pos);
             E.check_launch("ctfa_gate", frames * 4.0 * (64 + 64));
             const long long n4 = (long long)frames * F0 * 16;
-            const int blocks = (int)std::min<long long>((n4 + 255) / 256, 148LL * 16);
-            gate_residual_kernel<<<blocks, 256, 0, r.st>>>(reinterpret_cast<const float4*>(pp->cur(x, r.parity)),
-                                                          reinterpret_cast<const float4*>(pp->cur(en_in, r.parity)),
-                                                          reinterpret_cast<const float4*>(pp->cur(gate, 0)),
-                                                          reinterpret_cast<float4*>(pp->cur(out, r.parity)), n4, F0);
+            if (pp->sh16) {
+                const long long n8 = n4 / 2;
+                const int blocks8 = (int)std::min<long long>((n8 + 255) / 256, 148LL * 16);
+                gate_residual_sh_kernel<<<blocks8, 256, 0, r.st>>>(reinterpret_cast<const uint8_t*>(pp->cur(x, r.parity)),
+                                                                  reinterpret_cast<const uint8_t*>(pp->cur(en_in, r.parity)),
+                                                                  pp->cur(gate, 0),
+                                                                  reinterpret_cast<uint8_t*>(pp->cur(out, r.parity)), n8, F0);
+            } else {
+                const int blocks = (int)std::min<long long>((n4 + 255) / 256, 148LL * 16);
+                gate_residual_kernel<<<blocks, 256, 0, r.st>>>(reinterpret_cast<const float4*>(pp->cur(x, r.parity)),
+                                                              reinterpret_cast<const float4*>(pp->cur(en_in, r.parity)),
+                                                              reinterpret_cast<const float4*>(pp->cur(gate, 0)),
+                                                              reinterpret_cast<float4*>(pp->cur(out, r.parity)), n4, F0);
+            }
             E.check_launch("gate_residual", frames * 4.0 * (3.0 * F0 * 64 + 64));
         });
         return out;
@@ -800,13 +994,19 @@ struct Engine {
         Plan* pp = &P;
         const bool recycle = !P.streaming && !getenv("NUNET_NO_RECYCLE");
         Ten* x0 = P.make("input_layer", 256, 64, false);
+        x0->sh = P.sh16;
         P.ops.push_back([=](Engine& E, const Run& r) {
             E.cur_op = "input_layer";
             const long long npix = (long long)r.B * r.T * 256;
             const int blocks = (int)((npix * 8 + 255) / 256);
             const VecLayer& v = E.in_layer;
-            input_layer_kernel<<<blocks, 256, 0, r.st>>>(r.mag_in, E.pool.at(v.w), E.pool.at(v.b), E.pool.at(v.gamma),
-                                                        E.pool.at(v.beta), E.pool.at(v.alpha), pp->cur(x0, r.parity), npix);
+            if (pp->sh16)
+                input_layer_sh_kernel<<<blocks, 256, 0, r.st>>>(r.mag_in, E.pool.at(v.w), E.pool.at(v.b), E.pool.at(v.gamma),
+                                                               E.pool.at(v.beta), E.pool.at(v.alpha),
+                                                               reinterpret_cast<uint8_t*>(pp->cur(x0, r.parity)), npix);
+            else
+                input_layer_kernel<<<blocks, 256, 0, r.st>>>(r.mag_in, E.pool.at(v.w), E.pool.at(v.b), E.pool.at(v.gamma),
+                                                            E.pool.at(v.beta), E.pool.at(v.alpha), pp->cur(x0, r.parity), npix);
             E.check_launch("input_layer", npix * 4.0 * 65);
         });
         Ten* x = x0;
@@ -834,14 +1034,20 @@ struct Engine {
             E.cur_op = "out_conv";
             const long long npix = (long long)r.B * r.T * 256;
             const int blocks = (int)((npix * 16 + 255) / 256);
-            out_conv_kernel<<<blocks, 256, 0, r.st>>>(pp->cur(y, r.parity), E.pool.at(E.out_layer.w), E.pool.at(E.out_layer.b),
-                                                     r.est_out, npix, 256, r.est_stride, r.est_off);
+            if (pp->sh16)
+                out_conv_sh_kernel<<<(int)((npix * 8 + 255) / 256), 256, 0, r.st>>>(
+                    reinterpret_cast<const uint8_t*>(pp->cur(y, r.parity)), E.pool.at(E.out_layer.w), E.pool.at(E.out_layer.b),
+                    r.est_out, npix, 256, r.est_stride, r.est_off);
+            else
+                out_conv_kernel<<<blocks, 256, 0, r.st>>>(pp->cur(y, r.parity), E.pool.at(E.out_layer.w), E.pool.at(E.out_layer.b),
+                                                         r.est_out, npix, 256, r.est_stride, r.est_off);
             E.check_launch("out_conv", npix * 4.0 * 65);
         });
     }
 
     void alloc_plan(Plan& P, int cap, bool streaming) {
         P.streaming = streaming;
+        P.sh16 = !streaming && use_tc && use_tc3;
         P.cap = cap;
         build_plan(P);
         if (streaming) {
@@ -1056,7 +1262,10 @@ int nunet_create(const nunet_config* cfg, const void* blob, size_t blob_bytes, n
         Engine& E = h->e;
         E.cfg = *cfg;
         E.num_sms = prop.multiProcessorCount;
-        if (const char* c = getenv("NUNET_CONV")) E.use_tc = strcmp(c, "simt") != 0;
+        if (const char* c = getenv("NUNET_CONV")) {
+            E.use_tc = strcmp(c, "simt") != 0;
+            E.use_tc3 = strcmp(c, "tc") != 0;
+        }
         if (const char* c = getenv("NUNET_TC_MIN_BINS")) E.tc_min_bins = atoi(c);
         E.blob.parse(blob, blob_bytes);
         E.pack_params();
@@ -1245,6 +1454,14 @@ long long nunet_debug_read(nunet_engine* h, const char* tensor_name, float* buf,
             if (cap < n) fail(NUNET_EINVAL, "buffer too small");
             CUDA_OK(cudaDeviceSynchronize());
             CUDA_OK(cudaMemcpy(buf, E.offline.cur(t, 0), (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+            if (t->sh) {   // records [C halves hi][C halves lo] -> floats, in place
+                const int C = t->C;
+                std::vector<__half> rec((size_t)2 * C);
+                for (long long px = 0; px < n / C; ++px) {
+                    memcpy(rec.data(), buf + px * C, (size_t)4 * C);
+                    for (int c = 0; c < C; ++c) buf[px * C + c] = __half2float(rec[c]) + __half2float(rec[C + c]);
+                }
+            }
         }
     });
     return rc == NUNET_OK ? n : rc;
