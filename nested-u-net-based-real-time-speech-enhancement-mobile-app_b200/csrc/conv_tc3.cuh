@@ -14,8 +14,8 @@
 // Geometry: the "flat padded implicit GEMM" of conv_tc.cuh -- output positions of the whole batch on one flat
 // axis q = rho*P + x with zero pad rows / columns, every tap a constant shift of q, so all taps read the SAME
 // shared-memory image through K-major no-swizzle UMMA descriptors (rows 16 B apart, 8-channel K chunks in planes):
-//      image[img][hi|lo][chunk 2][slot][8 halves],   one image buffer = 16 input channels = one K=16 MMA step.
-// Stride-2 units keep two images (even / odd input bins).
+//      buffer[hi|lo][chunk 2][img][slot][8 halves],   one image buffer = 16 input channels = one K=16 MMA step.
+// Stride-2 units keep two images (even / odd input bins) back to back inside every plane.
 //
 // Weights stay RESIDENT in shared memory for the whole (persistent) CTA: units with 128 conv channels (last spconv
 // of a block, up_sampling o inconv) are two independent 64-column problems (their LayerNorm runs over each half),
@@ -23,10 +23,11 @@
 // the weight columns into output-channel order, so the sub-pixel shuffles cost nothing here.
 //
 // CTA = 13 warps, persistent over tiles of mt*128 flat positions:
-//   warps 0-3   epilogue  TMEM -> registers (one thread = one position, all its channels: LayerNorm is
-//                         thread-local) -> bias / two-pass LN / PReLU -> hi/lo split -> staged 128-byte rows ->
-//                         coalesced global stores
-//   warps 4-11  loaders   cp.async (zero-filled pads) into a ring of image buffers, NB-1 buffers ahead
+//   warps 0-7   epilogue  two groups of four warps (one M=128 accumulator each, so two warps share every SM
+//                         sub-partition and hide each other's latencies): TMEM -> registers (one thread = one
+//                         position, all its channels: LayerNorm is thread-local) -> bias / two-pass LN / PReLU ->
+//                         hi/lo split -> staged 128-byte rows -> coalesced global stores
+//   warps 8-11  loaders   cp.async (zero-filled pads) into a ring of image buffers, NB-1 buffers ahead
 //   warp  12    MMA       one elected thread: tcgen05.mma kind::f16, M=128, N, K=16; accumulators double-buffered
 #pragma once
 #include <cuda_fp16.h>
@@ -39,16 +40,19 @@ namespace nunet {
 constexpr int T3_KCH = 16;          // input channels per image buffer (one K=16 MMA step)
 constexpr int T3_MT = 2;            // M=128 tiles per CTA iteration
 constexpr int T3_MAXTAPS = 6;
-constexpr int T3_EPI_WARPS = 4;
-constexpr int T3_LD_WARPS = 8;
+constexpr int T3_EPI_WARPS = 8;
+constexpr int T3_LD_WARPS = 4;
 constexpr int T3_LD_THREADS = 32 * T3_LD_WARPS;
 constexpr int T3_THREADS = 32 * (T3_EPI_WARPS + T3_LD_WARPS + 1);
 constexpr int T3_MAXNB = 6;         // image ring depth
-constexpr int T3_TBL_HALF = 1024;   // slot table entries per tile (nimg*slots <= 1024), double buffered
-constexpr int T3_MAXIT = T3_TBL_HALF * 4 / T3_LD_THREADS;   // cp.async items per loader thread per buffer
+constexpr int T3_TBL = 1024;        // slot table entries (nimg*slots <= 1024)
+constexpr int T3_MAXIT = T3_TBL * 4 / T3_LD_THREADS;   // cp.async items per loader thread per buffer
 constexpr int T3_STG_PITCH = 144;   // bytes per staged output row (128 + 16: conflict-free 16-byte rows)
-constexpr int T3_STG_BYTES = T3_EPI_WARPS * 32 * T3_STG_PITCH + T3_EPI_WARPS * 32 * 8;
-constexpr int T3_FIXED_BYTES = 256 + 2 * T3_TBL_HALF * 4 + T3_STG_BYTES;
+constexpr int T3_STG_ROWS = 16;     // rows staged at a time per epilogue warp (half a warp)
+constexpr int T3_STG_BYTES = T3_EPI_WARPS * T3_STG_ROWS * T3_STG_PITCH + T3_EPI_WARPS * 32 * 8;
+constexpr int T3_PAR_OFF = 256;     // bias / gamma / beta staged as floats: 3 x 64
+constexpr int T3_TBL_OFF = 1024;
+constexpr int T3_FIXED_BYTES = T3_TBL_OFF + T3_TBL * 4 + T3_STG_BYTES;
 
 struct Tc3Params {
     const uint8_t* src0;   // sh16 [frames][F_in][C0]
@@ -69,13 +73,14 @@ struct Tc3Params {
     int tap_img[T3_MAXTAPS], tap_off[T3_MAXTAPS];
     int nphase;            // (C0 + C1) / 16
     int slots;             // image length in positions = mt*128 + max tap_off
-    int plane_bytes;       // byte stride between the planes of an image buffer, (plane_bytes/16) % 8 == 2
+    int plane_bytes;       // byte stride between the 4 planes of a buffer: >= 16 * roundup(nimg*slots, 32), (/16) % 8 == 2
     int total_flat;        // B * (T + padrow) * P
     int ntiles;
     int nabuf;             // image ring depth (2..T3_MAXNB)
     int mt;                // M=128 tiles per iteration (1 or 2)
     int nhalf;             // 1, or 2: CTA parity selects the 64-column half
     int w_half_bytes;      // nphase * ntaps * N * 64
+    int fence_mode;        // 0: loaders fence.proxy.async before arriving; 1: the MMA thread fences after its wait
 };
 
 __device__ __forceinline__ void cp_async16_s(uint32_t smem_dst, const void* gsrc, int src_bytes) {
@@ -126,6 +131,37 @@ __device__ __forceinline__ void join8(const uint4& hi, const uint4& lo, float* v
     }
 }
 
+// LayerNorm (two-pass: mean, centred variance -- the reference's non-fused Keras path) + PReLU over v[0..CG) in
+// place, gamma / beta from shared memory.  Four partial sums keep the reductions off one dependent chain.
+template <int CG>
+__device__ __forceinline__ void ln_prelu_s(float* v, const float* gamma_s, const float* beta_s, float alpha) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < CG; i += 4) {
+        s0 += v[i]; s1 += v[i + 1]; s2 += v[i + 2]; s3 += v[i + 3];
+    }
+    const float mean = ((s0 + s1) + (s2 + s3)) * (1.0f / CG);
+    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < CG; i += 4) {
+        const float d0 = v[i] - mean, d1 = v[i + 1] - mean, d2 = v[i + 2] - mean, d3 = v[i + 3] - mean;
+        q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
+    }
+    const float inv = rsqrtf(((q0 + q1) + (q2 + q3)) * (1.0f / CG) + LN_EPS);
+    const float minv = -mean * inv;
+#pragma unroll
+    for (int i = 0; i < CG; i += 4) {
+        const float4 g = *reinterpret_cast<const float4*>(gamma_s + i);
+        const float4 b = *reinterpret_cast<const float4*>(beta_s + i);
+        const float gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float y = fmaf(fmaf(v[i + e], inv, minv), gg[e], bb[e]);
+            v[i + e] = y >= 0.f ? y : alpha * y;
+        }
+    }
+}
+
 // N: conv channels of this CTA (32 / 64); PC: channels per OUTPUT pixel (N, or 32 for the 64-column sub-pixel
 // shuffle that makes two pixels); LN: LayerNorm + PReLU over each PC-channel group (false: bias only).
 template <int N, int PC, bool LN>
@@ -138,18 +174,20 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
     uint64_t* acc_empty = acc_full + 2;          // [2]
     uint64_t* w_full = acc_empty + 2;            // [1]
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 24);
-    int* slot_tbl = reinterpret_cast<int*>(smem_raw + 256);
-    uint8_t* stage_all = smem_raw + 256 + 2 * T3_TBL_HALF * 4;
-    long long* goff_all = reinterpret_cast<long long*>(stage_all + T3_EPI_WARPS * 32 * T3_STG_PITCH);
+    float* par_s = reinterpret_cast<float*>(smem_raw + T3_PAR_OFF);   // bias[64] | gamma[64] | beta[64]
+    int* slot_tbl = reinterpret_cast<int*>(smem_raw + T3_TBL_OFF);
+    uint8_t* stage_all = smem_raw + T3_TBL_OFF + T3_TBL * 4;
+    long long* goff_all = reinterpret_cast<long long*>(stage_all + T3_EPI_WARPS * T3_STG_ROWS * T3_STG_PITCH);
     uint8_t* wsm = smem_raw + T3_FIXED_BYTES;
     uint8_t* abuf0 = wsm + p.w_half_bytes;
-    const uint32_t abuf_bytes = (uint32_t)p.nimg * 4 * p.plane_bytes;
+    const uint32_t abuf_bytes = 4u * (uint32_t)p.plane_bytes;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int MMA_WARP = T3_EPI_WARPS + T3_LD_WARPS;
     constexpr uint32_t ACC_COLS = 2 * T3_MT * N;
     constexpr uint32_t TMEM_COLS = ACC_COLS <= 32 ? 32 : (ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512)));
 
+    const int half = (int)blockIdx.x % p.nhalf;
     if (threadIdx.x == 0) {
         for (int i = 0; i < T3_MAXNB; ++i) {
             mbar_init(&a_full[i], T3_LD_THREADS);
@@ -157,10 +195,15 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&acc_full[i], 1);
-            mbar_init(&acc_empty[i], 32 * T3_EPI_WARPS);
+            mbar_init(&acc_empty[i], 128 * p.mt);
         }
         mbar_init(w_full, 1);
         fence_barrier_init();
+    }
+    if (threadIdx.x < 64) {
+        par_s[threadIdx.x] = (threadIdx.x < N) ? __ldg(p.bias + half * N + threadIdx.x) : 0.f;
+        par_s[64 + threadIdx.x] = (LN && threadIdx.x < PC) ? __ldg(p.gamma + threadIdx.x) : 0.f;
+        par_s[128 + threadIdx.x] = (LN && threadIdx.x < PC) ? __ldg(p.beta + threadIdx.x) : 0.f;
     }
     if (warp == MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "r"(TMEM_COLS) : "memory");
@@ -172,70 +215,102 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
     const uint32_t tmem_base = *tmem_ptr_s;
 
     const int Tp = p.T + p.padrow;
-    const int half = (int)blockIdx.x % p.nhalf;
     const int cta = (int)blockIdx.x / p.nhalf, ncta = (int)gridDim.x / p.nhalf;
     const int my_tiles = (cta < p.ntiles) ? (p.ntiles - cta + ncta - 1) / ncta : 0;
     const int tile_pos = p.mt * 128;
 
     if (warp < T3_EPI_WARPS) {
         // ================================================================= epilogue
-        const int row = threadIdx.x;   // TMEM lane == tile row
+        // Accumulator (it, mt) is drained by warp group ((it * p.mt + mt) & 1): with two tiles per iteration each
+        // group owns one of them, with one tile per iteration the groups alternate iterations.
+        const int eg = warp >> 2, wq = warp & 3;
+        const int row = wq * 32 + lane;   // TMEM lane == tile row
         const float alpha = LN ? __ldg(p.alpha) : 0.f;
-        const float* bias = p.bias + half * N;
-        uint8_t* stg = stage_all + warp * 32 * T3_STG_PITCH;
+        uint8_t* stg = stage_all + warp * T3_STG_ROWS * T3_STG_PITCH;
         long long* goff = goff_all + warp * 32;
         constexpr int PASSES = N / 32;     // 128-byte passes per row
         for (int it = 0; it < my_tiles; ++it) {
+            const int mt = (p.mt == 2) ? eg : 0;
+            if (p.mt == 1 && (it & 1) != eg) continue;
             const int tile = cta + it * ncta;
             const int ab = it & 1;
             mbar_wait(&acc_full[ab], (it >> 1) & 1);
             tc_fence_after();
-#pragma unroll 1
-            for (int mt = 0; mt < p.mt; ++mt) {
-                const int q = tile * tile_pos + mt * 128 + row;
-                const int rho = q / p.P;
-                const int x = q - rho * p.P;
-                const int b = rho / Tp;
-                const int t = (rho - b * Tp) - p.padrow;
-                const bool valid = (q < p.total_flat) && (t >= 0) && (x >= p.xlo) && (x < p.xlo + p.F_conv);
-                const long long pix = ((long long)b * p.T + t) * p.F_conv + (x - p.xlo);   // conv-output pixel
-                goff[lane] = valid ? (pix * p.nhalf + half) * (long long)(N * 4) : -1;
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((ab * p.mt + mt) * N);
-                float v[N];
+            const int q = tile * tile_pos + mt * 128 + row;
+            const int rho = q / p.P;
+            const int x = q - rho * p.P;
+            const int b = rho / Tp;
+            const int t = (rho - b * Tp) - p.padrow;
+            const bool valid = (q < p.total_flat) && (t >= 0) && (x >= p.xlo) && (x < p.xlo + p.F_conv);
+            const long long pix = ((long long)b * p.T + t) * p.F_conv + (x - p.xlo);   // conv-output pixel
+            goff[lane] = valid ? (pix * p.nhalf + half) * (long long)(N * 4) : -1;
+            const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((ab * p.mt + mt) * N);
+            float v[N];
 #pragma unroll
-                for (int c = 0; c < N; c += 32) tmem_ld32(taddr + c, v + c);
+            for (int c = 0; c < N; c += 32) tmem_ld32(taddr + c, v + c);
+            // the accumulator is in registers: hand the TMEM buffer back to the MMA warp right away
+            tc_fence_before();
+            mbar_arrive(&acc_empty[ab]);
 #pragma unroll
-                for (int c = 0; c < N; ++c) v[c] = fmaf(v[c], p.wscale_inv, __ldg(bias + c));
-                if (LN) {
+            for (int c = 0; c < N; c += 4) {
+                const float4 bv = *reinterpret_cast<const float4*>(par_s + c);
+                v[c] = fmaf(v[c], p.wscale_inv, bv.x);
+                v[c + 1] = fmaf(v[c + 1], p.wscale_inv, bv.y);
+                v[c + 2] = fmaf(v[c + 2], p.wscale_inv, bv.z);
+                v[c + 3] = fmaf(v[c + 3], p.wscale_inv, bv.w);
+            }
+            if (LN) {
 #pragma unroll
-                    for (int g = 0; g < N / PC; ++g) ln_prelu<PC, 1>(v + g * PC, p.gamma, p.beta, 0, alpha);
-                }
+                for (int g = 0; g < N / PC; ++g) ln_prelu_s<PC>(v + g * PC, par_s + 64, par_s + 128, alpha);
+            }
 #pragma unroll
-                for (int pass = 0; pass < PASSES; ++pass) {
-                    uint4* srow = reinterpret_cast<uint4*>(stg + lane * T3_STG_PITCH);
-                    if (PC == 32) {
-                        // pass = output pixel: [32 hi][32 lo]
+            for (int pass = 0; pass < PASSES; ++pass) {
+                // 128 bytes of this row's record: PC == 32: output pixel `pass` = [32 hi][32 lo];
+                // PC == 64: pass 0 = the 64 hi halves (v becomes the residual), pass 1 = the 64 lo halves
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            uint4 hi, lo;
-                            split8(v + pass * 32 + 8 * k, hi, lo);
-                            srow[k] = hi;
-                            srow[4 + k] = lo;
-                        }
-                    } else {
-                        // 64-channel pixel: pass 0 = the 64 hi halves, pass 1 = the 64 lo halves
+                for (int hw = 0; hw < 2; ++hw) {
+                    if ((lane >> 4) == hw) {
+                        uint4* srow = reinterpret_cast<uint4*>(stg + (lane & 15) * T3_STG_PITCH);
+                        if (PC == 32) {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            uint4 hi, lo;
-                            split8(v + 8 * k, hi, lo);
-                            srow[k] = (pass == 0) ? hi : lo;
+                            for (int k = 0; k < 4; ++k) {
+                                uint4 hi, lo;
+                                split8(v + pass * 32 + 8 * k, hi, lo);
+                                srow[k] = hi;
+                                srow[4 + k] = lo;
+                            }
+                        } else if (pass == 0) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                uint32_t h[4];
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const __half2 hh = __floats2half2_rn(v[8 * k + 2 * i], v[8 * k + 2 * i + 1]);
+                                    const float2 hf = __half22float2(hh);
+                                    v[8 * k + 2 * i] -= hf.x;
+                                    v[8 * k + 2 * i + 1] -= hf.y;
+                                    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+                                }
+                                srow[k] = make_uint4(h[0], h[1], h[2], h[3]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                uint32_t l[4];
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const __half2 ll = __floats2half2_rn(v[8 * k + 2 * i], v[8 * k + 2 * i + 1]);
+                                    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+                                }
+                                srow[k] = make_uint4(l[0], l[1], l[2], l[3]);
+                            }
                         }
                     }
                     __syncwarp();
-#pragma unroll 4
-                    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
                         const int r = i * 4 + (lane >> 3), ch = lane & 7;
-                        const long long o = goff[r];
+                        const long long o = goff[hw * 16 + r];
                         if (o >= 0)
                             *reinterpret_cast<uint4*>(p.out + o + pass * 128 + ch * 16) =
                                 *reinterpret_cast<const uint4*>(stg + r * T3_STG_PITCH + ch * 16);
@@ -243,41 +318,33 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
                     __syncwarp();
                 }
             }
-            tc_fence_before();
-            mbar_arrive(&acc_empty[ab]);
         }
     } else if (warp < MMA_WARP) {
         // ================================================================= loaders
-        // Item (slot e, part hi|lo, chunk): one 16-byte cp.async.  Thread lt owns j = lt & 3 = (part, chunk) and
-        // slots e = (lt >> 2) + 64 k: four neighbouring threads fetch the two 32-byte sectors of one pixel.
+        // Item (table entry e, part hi|lo, chunk): one 16-byte cp.async.  Thread lt owns j = lt & 3 = (part, chunk)
+        // and entries e = (lt >> 2) + 32 k: four neighbouring threads fetch the two 32-byte sectors of one pixel.
+        // Entry e = img * slots + slot; the planes of a buffer hold both images back to back, so the destination is
+        // plane(j) + 16 e and the per-item work is: table load, one wide multiply-add, the copy.
         const int lt = threadIdx.x - 32 * T3_EPI_WARPS;
         const int part = (lt >> 1) & 1, chunk = lt & 1;
+        constexpr int ESTEP = T3_LD_THREADS / 4;
         const int e0 = lt >> 2;
         const int nslot = p.nimg * p.slots;
-        const int nit = (nslot > e0) ? (nslot - e0 + 63) / 64 : 0;
-        uint32_t dst[T3_MAXIT];
-        int off[T3_MAXIT];
-#pragma unroll
-        for (int k = 0; k < T3_MAXIT; ++k) {
-            const int e = e0 + 64 * k;
-            const int img = (e >= p.slots) ? 1 : 0;
-            const int slot = e - img * p.slots;
-            dst[k] = (uint32_t)((img * 4 + part * 2 + chunk) * p.plane_bytes + slot * 16);
-            off[k] = -1;
-        }
-        const uint32_t abase = smem_u32(abuf0);
-        const int NB = p.nabuf, D = NB - 1;
+        const int nit = (nslot + ESTEP - 1) / ESTEP;           // uniform; entries >= nslot are -1 (zero fill into padding)
+        const uint32_t dst0 = smem_u32(abuf0) + (uint32_t)((part * 2 + chunk) * p.plane_bytes + e0 * 16);
+        const int NB = p.nabuf;
+        int buf = 0, round = 0;        // ring position of phase g and the parity of its use count
         int g = 0;
         for (int it = 0; it < my_tiles; ++it) {
             const int tile = cta + it * ncta;
             const int q0 = tile * tile_pos - p.lead;
-            int* tb = slot_tbl + (it & 1) * T3_TBL_HALF;
-            for (int e = lt; e < nslot; e += T3_LD_THREADS) {
+            if (it > 0) asm volatile("bar.sync 1, %0;" ::"n"(T3_LD_THREADS) : "memory");   // everyone is done with the old table
+            for (int e = lt; e < nit * ESTEP; e += T3_LD_THREADS) {
                 const int img = (e >= p.slots) ? 1 : 0;
                 const int slot = e - img * p.slots;
                 const int q = q0 + slot;
                 int o = -1;
-                if (q >= 0 && q < p.total_flat) {
+                if (e < nslot && q >= 0 && q < p.total_flat) {
                     const int rho = q / p.P;
                     const int x = q - rho * p.P;
                     const int b = rho / Tp;
@@ -285,41 +352,44 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
                     const int fi = p.img_mul[img] * x + p.img_add[img];
                     if (t >= 0 && fi >= 0 && fi < p.F_in) o = (b * p.T + t) * p.F_in + fi;
                 }
-                tb[e] = o;
+                slot_tbl[e] = o;
             }
             asm volatile("bar.sync 1, %0;" ::"n"(T3_LD_THREADS) : "memory");
-#pragma unroll
-            for (int k = 0; k < T3_MAXIT; ++k)
-                if (k < nit) off[k] = tb[e0 + 64 * k];
             for (int ph = 0; ph < p.nphase; ++ph, ++g) {
-                const int buf = g % NB;
-                if (g >= NB) mbar_wait(&a_empty[buf], ((g / NB) - 1) & 1);
+                if (g >= NB) mbar_wait(&a_empty[buf], round ^ 1);
                 const int c0 = ph * T3_KCH;
                 const bool first = c0 < p.C0;
                 const uint8_t* src = first ? p.src0 : p.src1;
                 const int C = first ? p.C0 : p.C1;
                 const int cc = first ? c0 : c0 - p.C0;
                 const uint8_t* pb = src + part * C * 2 + (cc + chunk * 8) * 2;
-                const long long rec = 4LL * C;
-                const uint32_t bb = abase + (uint32_t)buf * abuf_bytes;
-#pragma unroll
-                for (int k = 0; k < T3_MAXIT; ++k)
-                    if (k < nit) {
-                        const int o = off[k];
-                        cp_async16_s(bb + dst[k], (o >= 0) ? pb + (long long)o * rec : pb, (o >= 0) ? 16 : 0);
-                    }
-                cp_async_commit();
-                if (g >= D) {
-                    cp_async_wait_dyn(D);          // this thread's copies of buffer g - D have landed
-                    fence_proxy_async();
-                    mbar_arrive(&a_full[(g - D) % NB]);
+                const unsigned rec = 4u * (unsigned)C;
+                uint32_t d = dst0 + (uint32_t)buf * abuf_bytes;
+                const int* tb = slot_tbl + e0;
+#pragma unroll 4
+                for (int k = 0; k < nit; ++k) {
+                    const int o = tb[k * ESTEP];
+                    cp_async16_s(d, pb + (unsigned long long)(unsigned)(o < 0 ? 0 : o) * rec, (o >= 0) ? 16 : 0);
+                    d += ESTEP * 16;
                 }
+                cp_async_commit();
+                const int nxt = (buf + 1 == NB) ? 0 : buf + 1;
+                if (g >= NB - 1) {
+                    cp_async_wait_dyn(NB - 1);     // this thread's copies of phase g - (NB - 1) (buffer nxt) have landed
+                    if (p.fence_mode == 0) fence_proxy_async();
+                    mbar_arrive(&a_full[nxt]);
+                }
+                if (nxt == 0) round ^= 1;
+                buf = nxt;
             }
         }
-        for (int r = (g < D ? g : D); r > 0; --r) {   // drain: buffers g - r
-            cp_async_wait_dyn(r - 1);
-            fence_proxy_async();
-            mbar_arrive(&a_full[(g - r) % NB]);
+        {   // drain: the last min(g, NB - 1) phases
+            const int D = NB - 1;
+            for (int r = (g < D ? g : D); r > 0; --r) {
+                cp_async_wait_dyn(r - 1);
+                if (p.fence_mode == 0) fence_proxy_async();
+                mbar_arrive(&a_full[(g - r) % NB]);
+            }
         }
     } else {
         // ================================================================= MMA issuer (+ one-off weight load)
@@ -334,36 +404,54 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
                 mbar_wait(w_full, 0);
             }
             constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);   // f16 x f16 -> f32
-            const uint32_t w_base0 = smem_u32(wsm);
-            const uint32_t a_base0 = smem_u32(abuf0);
-            int g = 0;
+            // Descriptors differ only in their 14-bit start-address field (bytes >> 4): keep the invariant high word
+            // and per-(tap, mt) address deltas in registers so that one MMA costs a couple of integer adds.
+            const uint64_t da0 = make_desc(smem_u32(abuf0), p.plane_bytes);
+            const uint64_t db0 = make_desc(smem_u32(wsm), N * 16);
+            const uint32_t da_hiw = (uint32_t)(da0 >> 32), db_hiw = (uint32_t)(db0 >> 32);
+            const uint32_t da_low0 = (uint32_t)da0, db_low0 = (uint32_t)db0;
+            const uint32_t a_lo_delta = (uint32_t)(2 * p.plane_bytes) >> 4;
+            const uint32_t abuf16 = abuf_bytes >> 4;
+            uint32_t tapd[T3_MAXTAPS];
+#pragma unroll
+            for (int tap = 0; tap < T3_MAXTAPS; ++tap)
+                tapd[tap] = (tap < p.ntaps) ? (uint32_t)(p.tap_img[tap] * p.slots + p.tap_off[tap]) : 0u;
+            auto desc = [](uint32_t low, uint32_t high) { return ((uint64_t)high << 32) | low; };
+            int buf = 0, round = 0;
             for (int it = 0; it < my_tiles; ++it) {
                 const int accb = it & 1;
                 if (it >= 2) mbar_wait(&acc_empty[accb], ((it >> 1) - 1) & 1);
                 tc_fence_after();
-                for (int ph = 0; ph < p.nphase; ++ph, ++g) {
-                    const int buf = g % p.nabuf;
-                    mbar_wait(&a_full[buf], (g / p.nabuf) & 1);
+                uint32_t wlow = db_low0;
+                for (int ph = 0; ph < p.nphase; ++ph) {
+                    mbar_wait(&a_full[buf], round);
+                    if (p.fence_mode == 1) fence_proxy_async();
                     tc_fence_after();
-                    const uint32_t a_base = a_base0 + (uint32_t)buf * abuf_bytes;
-                    for (int tap = 0; tap < p.ntaps; ++tap) {
-                        const uint32_t w_hi = w_base0 + (uint32_t)(ph * p.ntaps + tap) * (N * 64);
-                        const uint32_t w_lo = w_hi + 2 * N * 16;
-                        const uint64_t db_hi = make_desc(w_hi, N * 16), db_lo = make_desc(w_lo, N * 16);
-                        const uint32_t a_img = a_base + (uint32_t)(p.tap_img[tap] * 4) * p.plane_bytes + (uint32_t)p.tap_off[tap] * 16;
-#pragma unroll 1
-                        for (int mt = 0; mt < p.mt; ++mt) {
-                            const uint32_t d = tmem_base + (uint32_t)((accb * p.mt + mt) * N);
-                            const uint32_t a_hi = a_img + mt * 128 * 16;
-                            const uint32_t a_lo = a_hi + 2 * p.plane_bytes;
-                            const uint64_t da_hi = make_desc(a_hi, p.plane_bytes), da_lo = make_desc(a_lo, p.plane_bytes);
-                            const uint32_t acc = (ph == 0 && tap == 0) ? 0u : 1u;
-                            tc_mma_f16(d, da_lo, db_hi, IDESC, acc);   // small terms first
-                            tc_mma_f16(d, da_hi, db_lo, IDESC, 1u);
-                            tc_mma_f16(d, da_hi, db_hi, IDESC, 1u);
+                    const uint32_t alow = da_low0 + (uint32_t)buf * abuf16;
+#pragma unroll
+                    for (int tap = 0; tap < T3_MAXTAPS; ++tap) {
+                        if (tap < p.ntaps) {
+                            const uint64_t db_hi = desc(wlow, db_hiw), db_lo = desc(wlow + 2 * N, db_hiw);
+#pragma unroll
+                            for (int mt = 0; mt < T3_MT; ++mt) {
+                                if (mt < p.mt) {
+                                    const uint32_t d = tmem_base + (uint32_t)((accb * p.mt + mt) * N);
+                                    const uint32_t al = alow + tapd[tap] + mt * 128;
+                                    const uint64_t da_hi = desc(al, da_hiw), da_lo = desc(al + a_lo_delta, da_hiw);
+                                    const uint32_t acc = (ph == 0 && tap == 0) ? 0u : 1u;
+                                    tc_mma_f16(d, da_lo, db_hi, IDESC, acc);   // small terms first
+                                    tc_mma_f16(d, da_hi, db_lo, IDESC, 1u);
+                                    tc_mma_f16(d, da_hi, db_hi, IDESC, 1u);
+                                }
+                            }
+                            wlow += N * 4;   // next (phase, tap) stage: N * 64 bytes
                         }
                     }
                     tc_commit(&a_empty[buf]);
+                    if (++buf == p.nabuf) {
+                        buf = 0;
+                        round ^= 1;
+                    }
                 }
                 tc_commit(&acc_full[accb]);
             }

@@ -363,6 +363,7 @@ struct Engine {
     int last_B = 0, last_T = 0;
     int num_sms = 148;
     bool use_tc = true;     // NUNET_CONV=simt forces the FP32 SIMT units everywhere
+    int tc3_fence_mode = 0;  // NUNET_TC3_FENCE
     bool use_tc3 = true;    // NUNET_CONV=tc keeps the 3xTF32 kernel (fp32 activations) for the offline plan
     int tc_min_bins = 1;    // NUNET_TC_MIN_BINS: units with fewer conv-output bins stay on the SIMT kernel
     // per-launch profiling (bench.py roofline leg): one CUDA event after every launch on the launching stream
@@ -714,6 +715,7 @@ struct Engine {
         p.gamma = pool.at(L.gamma); p.beta = pool.at(L.beta); p.alpha = pool.at(L.alpha);
         p.out = reinterpret_cast<uint8_t*>(out);
         p.wscale_inv = L.wscale_inv;
+        p.fence_mode = tc3_fence_mode;
         p.B = B; p.T = T; p.F_in = F_in;
         p.F_conv = (L.stride == 2) ? F_in / 2 : F_in;
         p.ntaps = L.KT * L.KF;
@@ -758,11 +760,11 @@ struct Engine {
         // image buffers while one tile would allow it (the ring depth is what hides the HBM latency)
         auto geometry = [&](int mt, int& slots, int& plane_bytes, size_t& abuf) {
             slots = mt * 128 + maxoff;
-            int plane16 = slots;
+            int plane16 = (p.nimg * slots + 31) / 32 * 32;   // both images + the loaders' round-up padding
             while (plane16 % 8 != 2) ++plane16;
             plane_bytes = plane16 * 16;
-            abuf = (size_t)p.nimg * 4 * plane_bytes;
-            if (p.nimg * slots > T3_TBL_HALF || fixed + 2 * abuf > limit) return 0;
+            abuf = (size_t)4 * plane_bytes;
+            if (p.nimg * slots > T3_TBL - 32 || fixed + 2 * abuf > limit) return 0;
             return (int)std::min<size_t>((limit - fixed) / abuf, (size_t)T3_MAXNB);
         };
         int slots2, plane2, slots1, plane1;
@@ -1267,6 +1269,7 @@ int nunet_create(const nunet_config* cfg, const void* blob, size_t blob_bytes, n
             E.use_tc3 = strcmp(c, "tc") != 0;
         }
         if (const char* c = getenv("NUNET_TC_MIN_BINS")) E.tc_min_bins = atoi(c);
+        if (const char* c = getenv("NUNET_TC3_FENCE")) E.tc3_fence_mode = atoi(c);
         E.blob.parse(blob, blob_bytes);
         E.pack_params();
         E.pool.upload();
