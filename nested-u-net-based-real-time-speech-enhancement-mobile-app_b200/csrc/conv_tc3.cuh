@@ -7,9 +7,14 @@
 // operand traffic, and -- the point of the format -- the split is done ONCE by the producer's epilogue, so the
 // consumer's loaders are pure 16-byte cp.async copies (no conversion pass: the old kernel was bound by it).
 //
-// HBM format "sh16" of an activation tensor [pixel][C]: one 4*C-byte record per pixel, [C halves hi][C halves lo]
-// (same footprint as fp32, so the arena layout of the plan is unchanged).  Weights are pre-split on the host and
-// scaled by a power of two per layer so that their lo parts stay normal halves (undone in the epilogue).
+// HBM format "sh16" of an activation tensor [frame][F][C] (same footprint as fp32, so the arena layout of the plan
+// is unchanged): every frame row is stored PLANAR, exactly like the shared-memory operand image,
+//      row[hi|lo][chunk C/8][f][8 halves]          (a "plane" = F x 16 bytes, one 8-channel chunk of one part)
+// so that (a) consecutive bins of a plane are consecutive 16-byte units both in HBM and in the image: a loader warp
+// copies 512 contiguous bytes per cp.async instruction, and (b) the epilogue, where lane = output position, writes
+// 512 contiguous bytes per store instruction straight from registers -- no staging through shared memory.
+// Weights are pre-split on the host and scaled by a power of two per layer so that their lo parts stay normal
+// halves (undone in the epilogue).
 //
 // Geometry: the "flat padded implicit GEMM" of conv_tc.cuh -- output positions of the whole batch on one flat
 // axis q = rho*P + x with zero pad rows / columns, every tap a constant shift of q, so all taps read the SAME
@@ -26,8 +31,9 @@
 //   warps 0-7   epilogue  two groups of four warps (one M=128 accumulator each, so two warps share every SM
 //                         sub-partition and hide each other's latencies): TMEM -> registers (one thread = one
 //                         position, all its channels: LayerNorm is thread-local) -> bias / two-pass LN / PReLU ->
-//                         hi/lo split -> staged 128-byte rows -> coalesced global stores
-//   warps 8-11  loaders   cp.async (zero-filled pads) into a ring of image buffers, NB-1 buffers ahead
+//                         hi/lo split -> 16-byte stores, coalesced across the warp by the planar layout
+//   warps 8-11  loaders   one warp per plane (hi|lo x chunk): cp.async (zero-filled pads) into a ring of image
+//                         buffers, NB-1 buffers ahead
 //   warp  12    MMA       one elected thread: tcgen05.mma kind::f16, M=128, N, K=16; accumulators double-buffered
 #pragma once
 #include <cuda_fp16.h>
@@ -46,23 +52,20 @@ constexpr int T3_LD_THREADS = 32 * T3_LD_WARPS;
 constexpr int T3_THREADS = 32 * (T3_EPI_WARPS + T3_LD_WARPS + 1);
 constexpr int T3_MAXNB = 6;         // image ring depth
 constexpr int T3_TBL = 1024;        // slot table entries (nimg*slots <= 1024)
-constexpr int T3_MAXIT = T3_TBL * 4 / T3_LD_THREADS;   // cp.async items per loader thread per buffer
-constexpr int T3_STG_PITCH = 144;   // bytes per staged output row (128 + 16: conflict-free 16-byte rows)
-constexpr int T3_STG_ROWS = 16;     // rows staged at a time per epilogue warp (half a warp)
-constexpr int T3_STG_BYTES = T3_EPI_WARPS * T3_STG_ROWS * T3_STG_PITCH + T3_EPI_WARPS * 32 * 8;
 constexpr int T3_PAR_OFF = 256;     // bias / gamma / beta staged as floats: 3 x 64
 constexpr int T3_TBL_OFF = 1024;
-constexpr int T3_FIXED_BYTES = T3_TBL_OFF + T3_TBL * 4 + T3_STG_BYTES;
+constexpr int T3_FIXED_BYTES = T3_TBL_OFF + T3_TBL * 4;
 
 struct Tc3Params {
     const uint8_t* src0;   // sh16 [frames][F_in][C0]
-    const uint8_t* src1;   // sh16 [frames][F_in][C1] or null
+    const uint8_t* src1;   // sh16 [frames][F_in][C1] or null (C1 == C0 when present)
     const uint8_t* wpk;    // [nhalf][phase][tap][hi|lo][chunk 2][N][8 halves]
     const float* bias;     // [nhalf * N], packed-column order
     const float* gamma;    // [PC] LayerNorm scale / offset by output channel
     const float* beta;
     const float* alpha;
-    uint8_t* out;          // sh16
+    uint8_t* out;          // sh16 [frames][F_out][PC], F_out = F_conv * nhalf * N / PC
+    int F_out;
     float wscale_inv;      // undoes the power-of-two weight scale
     int C0, C1;
     int B, T, F_in, F_conv;
@@ -176,8 +179,6 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 24);
     float* par_s = reinterpret_cast<float*>(smem_raw + T3_PAR_OFF);   // bias[64] | gamma[64] | beta[64]
     int* slot_tbl = reinterpret_cast<int*>(smem_raw + T3_TBL_OFF);
-    uint8_t* stage_all = smem_raw + T3_TBL_OFF + T3_TBL * 4;
-    long long* goff_all = reinterpret_cast<long long*>(stage_all + T3_EPI_WARPS * T3_STG_ROWS * T3_STG_PITCH);
     uint8_t* wsm = smem_raw + T3_FIXED_BYTES;
     uint8_t* abuf0 = wsm + p.w_half_bytes;
     const uint32_t abuf_bytes = 4u * (uint32_t)p.plane_bytes;
@@ -226,9 +227,11 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
         const int eg = warp >> 2, wq = warp & 3;
         const int row = wq * 32 + lane;   // TMEM lane == tile row
         const float alpha = LN ? __ldg(p.alpha) : 0.f;
-        uint8_t* stg = stage_all + warp * T3_STG_ROWS * T3_STG_PITCH;
-        long long* goff = goff_all + warp * 32;
-        constexpr int PASSES = N / 32;     // 128-byte passes per row
+        constexpr int NPX = N / PC;            // output pixels per conv pixel made by this CTA
+        constexpr int CPP = PC / 8;            // 16-byte chunks per part of an output pixel
+        const int npx = NPX * p.nhalf;         // output bins per conv bin
+        const long long out_rs = (long long)p.F_out * (PC * 4);   // bytes per output frame row
+        const long long plane = (long long)p.F_out * 16;          // bytes per output plane
         for (int it = 0; it < my_tiles; ++it) {
             const int mt = (p.mt == 2) ? eg : 0;
             if (p.mt == 1 && (it & 1) != eg) continue;
@@ -242,8 +245,8 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
             const int b = rho / Tp;
             const int t = (rho - b * Tp) - p.padrow;
             const bool valid = (q < p.total_flat) && (t >= 0) && (x >= p.xlo) && (x < p.xlo + p.F_conv);
-            const long long pix = ((long long)b * p.T + t) * p.F_conv + (x - p.xlo);   // conv-output pixel
-            goff[lane] = valid ? (pix * p.nhalf + half) * (long long)(N * 4) : -1;
+            // first output bin of this conv pixel inside its frame row
+            uint8_t* orow = p.out + ((long long)b * p.T + t) * out_rs + (long long)((x - p.xlo) * npx + half * NPX) * 16;
             const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((ab * p.mt + mt) * N);
             float v[N];
 #pragma unroll
@@ -261,77 +264,38 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
             }
             if (LN) {
 #pragma unroll
-                for (int g = 0; g < N / PC; ++g) ln_prelu_s<PC>(v + g * PC, par_s + 64, par_s + 128, alpha);
+                for (int g = 0; g < NPX; ++g) ln_prelu_s<PC>(v + g * PC, par_s + 64, par_s + 128, alpha);
             }
+            if (valid) {
 #pragma unroll
-            for (int pass = 0; pass < PASSES; ++pass) {
-                // 128 bytes of this row's record: PC == 32: output pixel `pass` = [32 hi][32 lo];
-                // PC == 64: pass 0 = the 64 hi halves (v becomes the residual), pass 1 = the 64 lo halves
+                for (int g = 0; g < NPX; ++g) {
+                    uint8_t* o = orow + g * 16;
 #pragma unroll
-                for (int hw = 0; hw < 2; ++hw) {
-                    if ((lane >> 4) == hw) {
-                        uint4* srow = reinterpret_cast<uint4*>(stg + (lane & 15) * T3_STG_PITCH);
-                        if (PC == 32) {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                uint4 hi, lo;
-                                split8(v + pass * 32 + 8 * k, hi, lo);
-                                srow[k] = hi;
-                                srow[4 + k] = lo;
-                            }
-                        } else if (pass == 0) {
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) {
-                                uint32_t h[4];
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    const __half2 hh = __floats2half2_rn(v[8 * k + 2 * i], v[8 * k + 2 * i + 1]);
-                                    const float2 hf = __half22float2(hh);
-                                    v[8 * k + 2 * i] -= hf.x;
-                                    v[8 * k + 2 * i + 1] -= hf.y;
-                                    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
-                                }
-                                srow[k] = make_uint4(h[0], h[1], h[2], h[3]);
-                            }
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) {
-                                uint32_t l[4];
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    const __half2 ll = __floats2half2_rn(v[8 * k + 2 * i], v[8 * k + 2 * i + 1]);
-                                    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
-                                }
-                                srow[k] = make_uint4(l[0], l[1], l[2], l[3]);
-                            }
-                        }
+                    for (int c = 0; c < CPP; ++c) {
+                        uint4 hi, lo;
+                        split8(v + g * PC + 8 * c, hi, lo);
+                        *reinterpret_cast<uint4*>(o + c * plane) = hi;
+                        *reinterpret_cast<uint4*>(o + (CPP + c) * plane) = lo;
                     }
-                    __syncwarp();
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int r = i * 4 + (lane >> 3), ch = lane & 7;
-                        const long long o = goff[hw * 16 + r];
-                        if (o >= 0)
-                            *reinterpret_cast<uint4*>(p.out + o + pass * 128 + ch * 16) =
-                                *reinterpret_cast<const uint4*>(stg + r * T3_STG_PITCH + ch * 16);
-                    }
-                    __syncwarp();
                 }
             }
         }
     } else if (warp < MMA_WARP) {
         // ================================================================= loaders
-        // Item (table entry e, part hi|lo, chunk): one 16-byte cp.async.  Thread lt owns j = lt & 3 = (part, chunk)
-        // and entries e = (lt >> 2) + 32 k: four neighbouring threads fetch the two 32-byte sectors of one pixel.
-        // Entry e = img * slots + slot; the planes of a buffer hold both images back to back, so the destination is
-        // plane(j) + 16 e and the per-item work is: table load, one wide multiply-add, the copy.
+        // Loader warp w owns plane w = (part hi|lo, chunk) of every buffer; its lanes walk the table entries
+        // e = lane + 32 k, so one cp.async instruction moves 32 consecutive 16-byte slots.  A table entry is the
+        // 16-byte-unit offset of (frame row, bin) inside a source plane 0; the plane of the current phase adds
+        // a constant.  Entry e = img * slots + slot; the planes of a buffer hold both images back to back.
         const int lt = threadIdx.x - 32 * T3_EPI_WARPS;
-        const int part = (lt >> 1) & 1, chunk = lt & 1;
-        constexpr int ESTEP = T3_LD_THREADS / 4;
-        const int e0 = lt >> 2;
+        const int lw = lt >> 5;
+        const int part = lw >> 1, chunk = lw & 1;
+        constexpr int ESTEP = 32;
+        const int e0 = lane;
         const int nslot = p.nimg * p.slots;
-        const int nit = (nslot + ESTEP - 1) / ESTEP;           // uniform; entries >= nslot are -1 (zero fill into padding)
-        const uint32_t dst0 = smem_u32(abuf0) + (uint32_t)((part * 2 + chunk) * p.plane_bytes + e0 * 16);
+        const int nit = (nslot + ESTEP - 1) / ESTEP;           // entries >= nslot are -1 (zero fill into padding)
+        const uint32_t dst0 = smem_u32(abuf0) + (uint32_t)(lw * p.plane_bytes + e0 * 16);
+        const int cpp0 = p.C0 >> 3;                            // chunks per part of a source (C1 == C0)
+        const int rs16 = p.F_in * (p.C0 >> 2);                 // 16-byte units per source frame row
         const int NB = p.nabuf;
         int buf = 0, round = 0;        // ring position of phase g and the parity of its use count
         int g = 0;
@@ -350,7 +314,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
                     const int b = rho / Tp;
                     const int t = (rho - b * Tp) - p.padrow;
                     const int fi = p.img_mul[img] * x + p.img_add[img];
-                    if (t >= 0 && fi >= 0 && fi < p.F_in) o = (b * p.T + t) * p.F_in + fi;
+                    if (t >= 0 && fi >= 0 && fi < p.F_in) o = (b * p.T + t) * rs16 + fi;
                 }
                 slot_tbl[e] = o;
             }
@@ -360,16 +324,14 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
                 const int c0 = ph * T3_KCH;
                 const bool first = c0 < p.C0;
                 const uint8_t* src = first ? p.src0 : p.src1;
-                const int C = first ? p.C0 : p.C1;
                 const int cc = first ? c0 : c0 - p.C0;
-                const uint8_t* pb = src + part * C * 2 + (cc + chunk * 8) * 2;
-                const unsigned rec = 4u * (unsigned)C;
+                const uint8_t* pb = src + (long long)((part * cpp0 + (cc >> 3) + chunk) * p.F_in) * 16;   // source plane
                 uint32_t d = dst0 + (uint32_t)buf * abuf_bytes;
                 const int* tb = slot_tbl + e0;
 #pragma unroll 4
                 for (int k = 0; k < nit; ++k) {
                     const int o = tb[k * ESTEP];
-                    cp_async16_s(d, pb + (unsigned long long)(unsigned)(o < 0 ? 0 : o) * rec, (o >= 0) ? 16 : 0);
+                    cp_async16_s(d, pb + (long long)(o < 0 ? 0 : o) * 16, (o >= 0) ? 16 : 0);
                     d += ESTEP * 16;
                 }
                 cp_async_commit();

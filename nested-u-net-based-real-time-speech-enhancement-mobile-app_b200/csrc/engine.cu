@@ -718,6 +718,8 @@ struct Engine {
         p.fence_mode = tc3_fence_mode;
         p.B = B; p.T = T; p.F_in = F_in;
         p.F_conv = (L.stride == 2) ? F_in / 2 : F_in;
+        p.F_out = p.F_conv * L.COUT / L.PC3;
+        if (L.CB != 0 && L.CB != L.CA) fail(NUNET_EINVAL, "conv_tc3: the two sources must have the same width");
         p.ntaps = L.KT * L.KF;
         p.padrow = (L.KT == 2) ? 1 : 0;
         p.nimg = 1;
@@ -1003,9 +1005,9 @@ struct Engine {
             const int blocks = (int)((npix * 8 + 255) / 256);
             const VecLayer& v = E.in_layer;
             if (pp->sh16)
-                input_layer_sh_kernel<<<blocks, 256, 0, r.st>>>(r.mag_in, E.pool.at(v.w), E.pool.at(v.b), E.pool.at(v.gamma),
-                                                               E.pool.at(v.beta), E.pool.at(v.alpha),
-                                                               reinterpret_cast<uint8_t*>(pp->cur(x0, r.parity)), npix);
+                input_layer_sh_kernel<<<(int)((npix + 127) / 128), 128, 0, r.st>>>(
+                    r.mag_in, E.pool.at(v.w), E.pool.at(v.b), E.pool.at(v.gamma), E.pool.at(v.beta), E.pool.at(v.alpha),
+                    reinterpret_cast<uint8_t*>(pp->cur(x0, r.parity)), npix, 256);
             else
                 input_layer_kernel<<<blocks, 256, 0, r.st>>>(r.mag_in, E.pool.at(v.w), E.pool.at(v.b), E.pool.at(v.gamma),
                                                             E.pool.at(v.beta), E.pool.at(v.alpha), pp->cur(x0, r.parity), npix);
@@ -1037,7 +1039,7 @@ struct Engine {
             const long long npix = (long long)r.B * r.T * 256;
             const int blocks = (int)((npix * 16 + 255) / 256);
             if (pp->sh16)
-                out_conv_sh_kernel<<<(int)((npix * 8 + 255) / 256), 256, 0, r.st>>>(
+                out_conv_sh_kernel<<<(int)((npix + 127) / 128), 128, 0, r.st>>>(
                     reinterpret_cast<const uint8_t*>(pp->cur(y, r.parity)), E.pool.at(E.out_layer.w), E.pool.at(E.out_layer.b),
                     r.est_out, npix, 256, r.est_stride, r.est_off);
             else
@@ -1457,12 +1459,18 @@ long long nunet_debug_read(nunet_engine* h, const char* tensor_name, float* buf,
             if (cap < n) fail(NUNET_EINVAL, "buffer too small");
             CUDA_OK(cudaDeviceSynchronize());
             CUDA_OK(cudaMemcpy(buf, E.offline.cur(t, 0), (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
-            if (t->sh) {   // records [C halves hi][C halves lo] -> floats, in place
-                const int C = t->C;
-                std::vector<__half> rec((size_t)2 * C);
-                for (long long px = 0; px < n / C; ++px) {
-                    memcpy(rec.data(), buf + px * C, (size_t)4 * C);
-                    for (int c = 0; c < C; ++c) buf[px * C + c] = __half2float(rec[c]) + __half2float(rec[C + c]);
+            if (t->sh) {   // planar frame rows [hi|lo][chunk][f][8 halves] -> floats [f][c], in place
+                const int C = t->C, F = t->F;
+                std::vector<__half> row((size_t)2 * F * C);
+                for (long long fr = 0; fr < n / ((long long)F * C); ++fr) {
+                    float* dst = buf + fr * (long long)F * C;
+                    memcpy(row.data(), dst, (size_t)4 * F * C);
+                    for (int f = 0; f < F; ++f)
+                        for (int c = 0; c < C; ++c) {
+                            const size_t hi = ((size_t)(c >> 3) * F + f) * 8 + (c & 7);
+                            const size_t lo = ((size_t)((C >> 3) + (c >> 3)) * F + f) * 8 + (c & 7);
+                            dst[(size_t)f * C + c] = __half2float(row[hi]) + __half2float(row[lo]);
+                        }
                 }
             }
         }
