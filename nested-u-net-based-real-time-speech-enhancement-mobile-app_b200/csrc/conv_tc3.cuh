@@ -83,8 +83,23 @@ struct Tc3Params {
     int mt;                // M=128 tiles per iteration (1 or 2)
     int nhalf;             // 1, or 2: CTA parity selects the 64-column half
     int w_half_bytes;      // nphase * ntaps * N * 64
-    int fence_mode;        // 0: loaders fence.proxy.async before arriving; 1: the MMA thread fences after its wait
+    int fence_mode;        // experiments only: 2 = skip the consumer-side fence.proxy.async
+    int dbg;               // experiments only: 1 = no loads, 2 = no stores, 4 = no MMAs, 8 = no LN/split math
 };
+
+// mbarrier wait for warps that are NOT on the critical path (epilogue, loaders): the try_wait carries a suspend-time
+// hint so that a waiting warp sleeps in hardware instead of competing for issue slots with the MMA-issuing thread.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAITR_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra WAITR_DONE;\n\t"
+        "bra WAITR_LOOP;\n\t"
+        "WAITR_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
+}
 
 __device__ __forceinline__ void cp_async16_s(uint32_t smem_dst, const void* gsrc, int src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes));
@@ -237,7 +252,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
             if (p.mt == 1 && (it & 1) != eg) continue;
             const int tile = cta + it * ncta;
             const int ab = it & 1;
-            mbar_wait(&acc_full[ab], (it >> 1) & 1);
+            mbar_wait_relaxed(&acc_full[ab], (it >> 1) & 1);
             tc_fence_after();
             const int q = tile * tile_pos + mt * 128 + row;
             const int rho = q / p.P;
@@ -262,11 +277,11 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
                 v[c + 2] = fmaf(v[c + 2], p.wscale_inv, bv.z);
                 v[c + 3] = fmaf(v[c + 3], p.wscale_inv, bv.w);
             }
-            if (LN) {
+            if (LN && !(p.dbg & 8)) {
 #pragma unroll
                 for (int g = 0; g < NPX; ++g) ln_prelu_s<PC>(v + g * PC, par_s + 64, par_s + 128, alpha);
             }
-            if (valid) {
+            if (valid && !(p.dbg & 2)) {
 #pragma unroll
                 for (int g = 0; g < NPX; ++g) {
                     uint8_t* o = orow + g * 16;
@@ -320,7 +335,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
             }
             asm volatile("bar.sync 1, %0;" ::"n"(T3_LD_THREADS) : "memory");
             for (int ph = 0; ph < p.nphase; ++ph, ++g) {
-                if (g >= NB) mbar_wait(&a_empty[buf], round ^ 1);
+                if (g >= NB) mbar_wait_relaxed(&a_empty[buf], round ^ 1);
                 const int c0 = ph * T3_KCH;
                 const bool first = c0 < p.C0;
                 const uint8_t* src = first ? p.src0 : p.src1;
@@ -328,31 +343,24 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
                 const uint8_t* pb = src + (long long)((part * cpp0 + (cc >> 3) + chunk) * p.F_in) * 16;   // source plane
                 uint32_t d = dst0 + (uint32_t)buf * abuf_bytes;
                 const int* tb = slot_tbl + e0;
+                if (!(p.dbg & 1))
 #pragma unroll 4
                 for (int k = 0; k < nit; ++k) {
                     const int o = tb[k * ESTEP];
                     cp_async16_s(d, pb + (long long)(o < 0 ? 0 : o) * 16, (o >= 0) ? 16 : 0);
                     d += ESTEP * 16;
                 }
-                cp_async_commit();
-                const int nxt = (buf + 1 == NB) ? 0 : buf + 1;
-                if (g >= NB - 1) {
-                    cp_async_wait_dyn(NB - 1);     // this thread's copies of phase g - (NB - 1) (buffer nxt) have landed
-                    if (p.fence_mode == 0) fence_proxy_async();
-                    mbar_arrive(&a_full[nxt]);
+                // completion is signalled by the copy engine itself: a_full[buf] collects one arrival per loader
+                // thread, each triggered when that thread's copies above have landed -- the loaders never wait for
+                // data, only for a free buffer, so signalling is decoupled from how far ahead they can issue
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&a_full[buf])) : "memory");
+                if (++buf == NB) {
+                    buf = 0;
+                    round ^= 1;
                 }
-                if (nxt == 0) round ^= 1;
-                buf = nxt;
             }
         }
-        {   // drain: the last min(g, NB - 1) phases
-            const int D = NB - 1;
-            for (int r = (g < D ? g : D); r > 0; --r) {
-                cp_async_wait_dyn(r - 1);
-                if (p.fence_mode == 0) fence_proxy_async();
-                mbar_arrive(&a_full[(g - r) % NB]);
-            }
-        }
+        cp_async_wait<0>();
     } else {
         // ================================================================= MMA issuer (+ one-off weight load)
         if (lane == 0) {
@@ -387,7 +395,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
                 uint32_t wlow = db_low0;
                 for (int ph = 0; ph < p.nphase; ++ph) {
                     mbar_wait(&a_full[buf], round);
-                    if (p.fence_mode == 1) fence_proxy_async();
+                    if (p.fence_mode != 2) fence_proxy_async();   // cp.async wrote through the generic proxy, the MMA reads through the async proxy
                     tc_fence_after();
                     const uint32_t alow = da_low0 + (uint32_t)buf * abuf16;
 #pragma unroll
@@ -401,6 +409,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
                                     const uint32_t al = alow + tapd[tap] + mt * 128;
                                     const uint64_t da_hi = desc(al, da_hiw), da_lo = desc(al + a_lo_delta, da_hiw);
                                     const uint32_t acc = (ph == 0 && tap == 0) ? 0u : 1u;
+                                    if (p.dbg & 4) continue;
                                     tc_mma_f16(d, da_lo, db_hi, IDESC, acc);   // small terms first
                                     tc_mma_f16(d, da_hi, db_lo, IDESC, 1u);
                                     tc_mma_f16(d, da_hi, db_hi, IDESC, 1u);

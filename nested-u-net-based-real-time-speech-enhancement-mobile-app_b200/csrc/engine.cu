@@ -364,6 +364,7 @@ struct Engine {
     int num_sms = 148;
     bool use_tc = true;     // NUNET_CONV=simt forces the FP32 SIMT units everywhere
     int tc3_fence_mode = 0;  // NUNET_TC3_FENCE
+    int tc3_dbg = 0;         // NUNET_TC3_DBG (experiments)
     bool use_tc3 = true;    // NUNET_CONV=tc keeps the 3xTF32 kernel (fp32 activations) for the offline plan
     int tc_min_bins = 1;    // NUNET_TC_MIN_BINS: units with fewer conv-output bins stay on the SIMT kernel
     // per-launch profiling (bench.py roofline leg): one CUDA event after every launch on the launching stream
@@ -716,6 +717,7 @@ struct Engine {
         p.out = reinterpret_cast<uint8_t*>(out);
         p.wscale_inv = L.wscale_inv;
         p.fence_mode = tc3_fence_mode;
+        p.dbg = tc3_dbg;
         p.B = B; p.T = T; p.F_in = F_in;
         p.F_conv = (L.stride == 2) ? F_in / 2 : F_in;
         p.F_out = p.F_conv * L.COUT / L.PC3;
@@ -1272,6 +1274,7 @@ int nunet_create(const nunet_config* cfg, const void* blob, size_t blob_bytes, n
         }
         if (const char* c = getenv("NUNET_TC_MIN_BINS")) E.tc_min_bins = atoi(c);
         if (const char* c = getenv("NUNET_TC3_FENCE")) E.tc3_fence_mode = atoi(c);
+        if (const char* c = getenv("NUNET_TC3_DBG")) E.tc3_dbg = atoi(c);
         E.blob.parse(blob, blob_bytes);
         E.pack_params();
         E.pool.upload();
