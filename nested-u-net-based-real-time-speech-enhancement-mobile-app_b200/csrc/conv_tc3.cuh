@@ -2,7 +2,10 @@
 //
 // Numerics: every operand x is carried as two IEEE halves  x ~= hi + lo,  hi = rn_f16(x), lo = rn_f16(x - hi)
 // (22 significant bits while |x| < 65504; the products hi*hi, hi*lo, lo*hi are exact in fp32), and a
-// contraction is three kind::f16 MMAs  a_lo*b_hi + a_hi*b_lo + a_hi*b_hi  accumulated in fp32 in tensor memory.
+// contraction is the three products  a_hi*b_hi + a_hi*b_lo + a_lo*b_hi  accumulated in fp32 in tensor memory,
+// issued as TWO kind::f16 MMAs per K step:  a_hi x [b_hi | b_lo]  (2N accumulator columns) and  a_lo x b_hi
+// (into the first N columns); the epilogue adds the two column blocks.  Sharing the a_hi read between two products
+// matters because at M = 128 the shared-memory read of A, not the tensor pipe, bounds an N <= 64 MMA.
 // That is the accuracy of the 3xTF32 scheme of conv_tc.cuh at twice the tensor rate and half the shared-memory
 // operand traffic, and -- the point of the format -- the split is done ONCE by the producer's epilogue, so the
 // consumer's loaders are pure 16-byte cp.async copies (no conversion pass: the old kernel was bound by it).
@@ -59,7 +62,7 @@ constexpr int T3_FIXED_BYTES = T3_TBL_OFF + T3_TBL * 4;
 struct Tc3Params {
     const uint8_t* src0;   // sh16 [frames][F_in][C0]
     const uint8_t* src1;   // sh16 [frames][F_in][C1] or null (C1 == C0 when present)
-    const uint8_t* wpk;    // [nhalf][phase][tap][hi|lo][chunk 2][N][8 halves]
+    const uint8_t* wpk;    // [nhalf][phase][tap][chunk 2][hi N | lo N][8 halves]
     const float* bias;     // [nhalf * N], packed-column order
     const float* gamma;    // [PC] LayerNorm scale / offset by output channel
     const float* beta;
@@ -99,6 +102,30 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
         "bra WAITR_LOOP;\n\t"
         "WAITR_DONE:\n\t"
         "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
+}
+
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(pred));
+    return pred;
+}
+// one MMA from 32-bit descriptor words (the high words are loop invariants)
+__device__ __forceinline__ void tc_mma_f16_w(uint32_t d_tmem, uint32_t a_low, uint32_t a_high, uint32_t b_low, uint32_t b_high,
+                                             uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_low), "r"(a_high), "r"(b_low), "r"(b_high), "r"(idesc), "r"(accumulate) : "memory");
 }
 
 __device__ __forceinline__ void cp_async16_s(uint32_t smem_dst, const void* gsrc, int src_bytes) {
@@ -200,7 +227,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int MMA_WARP = T3_EPI_WARPS + T3_LD_WARPS;
-    constexpr uint32_t ACC_COLS = 2 * T3_MT * N;
+    constexpr uint32_t ACC_COLS = 2 * T3_MT * 2 * N;   // 2 buffers x 2 tiles x (N + N) columns
     constexpr uint32_t TMEM_COLS = ACC_COLS <= 32 ? 32 : (ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512)));
 
     const int half = (int)blockIdx.x % p.nhalf;
@@ -262,10 +289,17 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
             const bool valid = (q < p.total_flat) && (t >= 0) && (x >= p.xlo) && (x < p.xlo + p.F_conv);
             // first output bin of this conv pixel inside its frame row
             uint8_t* orow = p.out + ((long long)b * p.T + t) * out_rs + (long long)((x - p.xlo) * npx + half * NPX) * 16;
-            const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((ab * p.mt + mt) * N);
+            const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((ab * p.mt + mt) * 2 * N);
             float v[N];
 #pragma unroll
-            for (int c = 0; c < N; c += 32) tmem_ld32(taddr + c, v + c);
+            for (int c = 0; c < N; c += 32) tmem_ld32(taddr + c, v + c);            // a_hi*b_hi + a_lo*b_hi
+#pragma unroll
+            for (int c = 0; c < N; c += 32) {                                        // + a_hi*b_lo
+                float u[32];
+                tmem_ld32(taddr + N + c, u);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[c + i] += u[i];
+            }
             // the accumulator is in registers: hand the TMEM buffer back to the MMA warp right away
             tc_fence_before();
             mbar_arrive(&acc_empty[ab]);
@@ -363,69 +397,73 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
         cp_async_wait<0>();
     } else {
         // ================================================================= MMA issuer (+ one-off weight load)
-        if (lane == 0) {
-            if (my_tiles > 0) {
+        // The whole warp stays converged (waits are warp-wide); one elected lane issues, so the tcgen05
+        // instructions see warp-uniform operands and need no per-lane serialisation loop.
+        const uint32_t leader = elect_one();
+        if (my_tiles > 0) {
+            if (leader) {
                 mbar_arrive_expect_tx(w_full, (uint32_t)p.w_half_bytes);
                 const uint8_t* wg = p.wpk + (size_t)half * p.w_half_bytes;
                 for (int o = 0; o < p.w_half_bytes; o += 16384) {
                     const int n = (p.w_half_bytes - o < 16384) ? p.w_half_bytes - o : 16384;
                     bulk_g2s(wsm + o, wg + o, (uint32_t)n, w_full);
                 }
-                mbar_wait(w_full, 0);
             }
-            constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);   // f16 x f16 -> f32
-            // Descriptors differ only in their 14-bit start-address field (bytes >> 4): keep the invariant high word
-            // and per-(tap, mt) address deltas in registers so that one MMA costs a couple of integer adds.
-            const uint64_t da0 = make_desc(smem_u32(abuf0), p.plane_bytes);
-            const uint64_t db0 = make_desc(smem_u32(wsm), N * 16);
-            const uint32_t da_hiw = (uint32_t)(da0 >> 32), db_hiw = (uint32_t)(db0 >> 32);
-            const uint32_t da_low0 = (uint32_t)da0, db_low0 = (uint32_t)db0;
-            const uint32_t a_lo_delta = (uint32_t)(2 * p.plane_bytes) >> 4;
-            const uint32_t abuf16 = abuf_bytes >> 4;
-            uint32_t tapd[T3_MAXTAPS];
+            mbar_wait(w_full, 0);
+        }
+        constexpr uint32_t IDESC_2N = (1u << 4) | ((uint32_t)((2 * N) >> 3) << 17) | ((128u >> 4) << 24);   // f16 x f16 -> f32, N' = 2N
+        constexpr uint32_t IDESC_N = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+        // Descriptors differ only in their 14-bit start-address field (bytes >> 4): keep the invariant high words and
+        // per-tap address deltas in registers so that one MMA costs a couple of integer adds.
+        const uint64_t da0 = make_desc(smem_u32(abuf0), p.plane_bytes);
+        const uint64_t db0 = make_desc(smem_u32(wsm), 2 * N * 16);
+        const uint32_t da_hiw = (uint32_t)(da0 >> 32), db_hiw = (uint32_t)(db0 >> 32);
+        const uint32_t da_low0 = (uint32_t)da0, db_low0 = (uint32_t)db0;
+        const uint32_t a_lo_delta = (uint32_t)(2 * p.plane_bytes) >> 4;
+        const uint32_t abuf16 = abuf_bytes >> 4;
+        uint32_t tapd[T3_MAXTAPS];
 #pragma unroll
-            for (int tap = 0; tap < T3_MAXTAPS; ++tap)
-                tapd[tap] = (tap < p.ntaps) ? (uint32_t)(p.tap_img[tap] * p.slots + p.tap_off[tap]) : 0u;
-            auto desc = [](uint32_t low, uint32_t high) { return ((uint64_t)high << 32) | low; };
-            int buf = 0, round = 0;
-            for (int it = 0; it < my_tiles; ++it) {
-                const int accb = it & 1;
-                if (it >= 2) mbar_wait(&acc_empty[accb], ((it >> 1) - 1) & 1);
+        for (int tap = 0; tap < T3_MAXTAPS; ++tap)
+            tapd[tap] = (tap < p.ntaps) ? (uint32_t)(p.tap_img[tap] * p.slots + p.tap_off[tap]) : 0u;
+        int buf = 0, round = 0;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int accb = it & 1;
+            if (it >= 2) mbar_wait(&acc_empty[accb], ((it >> 1) - 1) & 1);
+            tc_fence_after();
+            uint32_t wlow = db_low0;
+            const uint32_t d0 = tmem_base + (uint32_t)(accb * p.mt * 2 * N);
+            for (int ph = 0; ph < p.nphase; ++ph) {
+                mbar_wait(&a_full[buf], round);
+                if (p.fence_mode != 2) fence_proxy_async();   // cp.async wrote through the generic proxy, the MMA reads through the async proxy
                 tc_fence_after();
-                uint32_t wlow = db_low0;
-                for (int ph = 0; ph < p.nphase; ++ph) {
-                    mbar_wait(&a_full[buf], round);
-                    if (p.fence_mode != 2) fence_proxy_async();   // cp.async wrote through the generic proxy, the MMA reads through the async proxy
-                    tc_fence_after();
+                if (leader) {
                     const uint32_t alow = da_low0 + (uint32_t)buf * abuf16;
 #pragma unroll
                     for (int tap = 0; tap < T3_MAXTAPS; ++tap) {
                         if (tap < p.ntaps) {
-                            const uint64_t db_hi = desc(wlow, db_hiw), db_lo = desc(wlow + 2 * N, db_hiw);
-#pragma unroll
-                            for (int mt = 0; mt < T3_MT; ++mt) {
-                                if (mt < p.mt) {
-                                    const uint32_t d = tmem_base + (uint32_t)((accb * p.mt + mt) * N);
-                                    const uint32_t al = alow + tapd[tap] + mt * 128;
-                                    const uint64_t da_hi = desc(al, da_hiw), da_lo = desc(al + a_lo_delta, da_hiw);
-                                    const uint32_t acc = (ph == 0 && tap == 0) ? 0u : 1u;
-                                    if (p.dbg & 4) continue;
-                                    tc_mma_f16(d, da_lo, db_hi, IDESC, acc);   // small terms first
-                                    tc_mma_f16(d, da_hi, db_lo, IDESC, 1u);
-                                    tc_mma_f16(d, da_hi, db_hi, IDESC, 1u);
+                            const uint32_t acc = (ph == 0 && tap == 0) ? 0u : 1u;
+                            if (!(p.dbg & 4)) {
+                                const uint32_t al = alow + tapd[tap];
+                                tc_mma_f16_w(d0, al, da_hiw, wlow, db_hiw, IDESC_2N, acc);                  // a_hi x [b_hi | b_lo]
+                                tc_mma_f16_w(d0, al + a_lo_delta, da_hiw, wlow, db_hiw, IDESC_N, 1u);       // a_lo x b_hi
+                                if (p.mt == 2) {
+                                    tc_mma_f16_w(d0 + 2 * N, al + 128, da_hiw, wlow, db_hiw, IDESC_2N, acc);
+                                    tc_mma_f16_w(d0 + 2 * N, al + 128 + a_lo_delta, da_hiw, wlow, db_hiw, IDESC_N, 1u);
                                 }
                             }
                             wlow += N * 4;   // next (phase, tap) stage: N * 64 bytes
                         }
                     }
                     tc_commit(&a_empty[buf]);
-                    if (++buf == p.nabuf) {
-                        buf = 0;
-                        round ^= 1;
-                    }
                 }
-                tc_commit(&acc_full[accb]);
+                __syncwarp();
+                if (++buf == p.nabuf) {
+                    buf = 0;
+                    round ^= 1;
+                }
             }
+            if (leader) tc_commit(&acc_full[accb]);
+            __syncwarp();
         }
     }
 

@@ -189,7 +189,7 @@ static int tc3_col_to_channel(int epi, int h, int n) {
 }
 
 // logical [taps][Cin][COUT] -> resident fp16 hi/lo operand image of conv_tc3_kernel:
-// [half][phase][tap][hi|lo][chunk 2][N][8 halves], scaled by 2^s (s chosen so that max |w| lands in [2^14, 2^15)).
+// [half][phase][tap][chunk 2][hi N | lo N][8 halves], scaled by 2^s (s chosen so that max |w| lands in [2^14, 2^15)).
 static std::vector<float> pack_tc3(const std::vector<float>& k, int taps, int Cin, int COUT, int epi, int nhalf, int N,
                                    float* scale_inv) {
     float mx = 0.f;
@@ -213,8 +213,8 @@ static std::vector<float> pack_tc3(const std::vector<float>& k, int taps, int Ci
                             const float w = k[((size_t)tap * Cin + ci) * COUT + co] * scale;
                             const __half hi = __float2half_rn(w);
                             const __half lo = __float2half_rn(w - __half2float(hi));
-                            out[stage + ((size_t)(0 * 2 + ch) * N + n) * 8 + e8] = hi;
-                            out[stage + ((size_t)(1 * 2 + ch) * N + n) * 8 + e8] = lo;
+                            out[stage + ((size_t)ch * 2 * N + n) * 8 + e8] = hi;
+                            out[stage + ((size_t)ch * 2 * N + N + n) * 8 + e8] = lo;
                         }
             }
     std::vector<float> raw(out.size() / 2);
