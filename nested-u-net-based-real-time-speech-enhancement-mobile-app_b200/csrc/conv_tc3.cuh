@@ -16,6 +16,9 @@
 // so that (a) consecutive bins of a plane are consecutive 16-byte units both in HBM and in the image: a loader warp
 // copies 512 contiguous bytes per cp.async instruction, and (b) the epilogue, where lane = output position, writes
 // 512 contiguous bytes per store instruction straight from registers -- no staging through shared memory.
+// A tensor may keep its bins in "even/odd" order inside every plane, [even bins | odd bins] (flag eo): that is the
+// order in which the two CTAs of a 128-channel unit produce them (each writes one contiguous half) and the order in
+// which the stride-2 units consume them (their even / odd images become contiguous copies).
 // Weights are pre-split on the host and scaled by a power of two per layer so that their lo parts stay normal
 // halves (undone in the epilogue).
 //
@@ -87,6 +90,8 @@ struct Tc3Params {
     int nhalf;             // 1, or 2: CTA parity selects the 64-column half
     int w_half_bytes;      // nphase * ntaps * N * 64
     int fence_mode;        // experiments only: 2 = skip the consumer-side fence.proxy.async
+    int src_eo, out_eo;    // bins of the sources / of the output are stored [even | odd] inside each plane
+    int tma;               // 1: stride-1 single-image unit with F_in >= 32: row segments move with bulk copies (TMA)
     int dbg;               // experiments only: 1 = no loads, 2 = no stores, 4 = no MMAs, 8 = no LN/split math
 };
 
@@ -104,6 +109,9 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
         "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
 }
 
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ uint32_t elect_one() {
     uint32_t pred;
     asm volatile(
@@ -148,6 +156,11 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ void st_global_32B(void* p, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+                 "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
 }
 
 // hi/lo split of 8 consecutive values into two 16-byte vectors of halves
@@ -287,8 +300,10 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
             const int b = rho / Tp;
             const int t = (rho - b * Tp) - p.padrow;
             const bool valid = (q < p.total_flat) && (t >= 0) && (x >= p.xlo) && (x < p.xlo + p.F_conv);
-            // first output bin of this conv pixel inside its frame row
-            uint8_t* orow = p.out + ((long long)b * p.T + t) * out_rs + (long long)((x - p.xlo) * npx + half * NPX) * 16;
+            // output bins of this conv pixel: obin0 + g (g < NPX); storage position inside a plane of the frame row
+            const int obin0 = (x - p.xlo) * npx + half * NPX;
+            const int opos0 = p.out_eo ? (obin0 & 1) * (p.F_out >> 1) + (obin0 >> 1) : obin0;
+            uint8_t* orow = p.out + ((long long)b * p.T + t) * out_rs + (long long)opos0 * 16;
             const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((ab * p.mt + mt) * 2 * N);
             float v[N];
 #pragma unroll
@@ -316,15 +331,28 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
                 for (int g = 0; g < NPX; ++g) ln_prelu_s<PC>(v + g * PC, par_s + 64, par_s + 128, alpha);
             }
             if (valid && !(p.dbg & 2)) {
-#pragma unroll
-                for (int g = 0; g < NPX; ++g) {
-                    uint8_t* o = orow + g * 16;
+                if (NPX == 2 && !p.out_eo) {
+                    // two neighbouring output bins per thread: one 32-byte store per chunk (whole sectors)
 #pragma unroll
                     for (int c = 0; c < CPP; ++c) {
-                        uint4 hi, lo;
-                        split8(v + g * PC + 8 * c, hi, lo);
-                        *reinterpret_cast<uint4*>(o + c * plane) = hi;
-                        *reinterpret_cast<uint4*>(o + (CPP + c) * plane) = lo;
+                        uint4 h0, l0, h1, l1;
+                        split8(v + 8 * c, h0, l0);
+                        split8(v + PC + 8 * c, h1, l1);
+                        st_global_32B(orow + c * plane, h0, h1);
+                        st_global_32B(orow + (CPP + c) * plane, l0, l1);
+                    }
+                } else {
+#pragma unroll
+                    for (int g = 0; g < NPX; ++g) {
+                        // with [even | odd] storage the second bin of a pair lives half a plane further
+                        uint8_t* o = orow + (p.out_eo ? (long long)g * (p.F_out >> 1) * 16 : (long long)g * 16);
+#pragma unroll
+                        for (int c = 0; c < CPP; ++c) {
+                            uint4 hi, lo;
+                            split8(v + g * PC + 8 * c, hi, lo);
+                            *reinterpret_cast<uint4*>(o + c * plane) = hi;
+                            *reinterpret_cast<uint4*>(o + (CPP + c) * plane) = lo;
+                        }
                     }
                 }
             }
@@ -363,11 +391,29 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
                     const int b = rho / Tp;
                     const int t = (rho - b * Tp) - p.padrow;
                     const int fi = p.img_mul[img] * x + p.img_add[img];
-                    if (t >= 0 && fi >= 0 && fi < p.F_in) o = (b * p.T + t) * rs16 + fi;
+                    if (t >= 0 && fi >= 0 && fi < p.F_in)
+                        o = (b * p.T + t) * rs16 + (p.src_eo ? (fi & 1) * (p.F_in >> 1) + (fi >> 1) : fi);
                 }
                 slot_tbl[e] = o;
             }
             asm volatile("bar.sync 1, %0;" ::"n"(T3_LD_THREADS) : "memory");
+            // TMA mode: lane r describes the part of frame row (first row of the tile + r) that lies inside the image
+            int seg_dst = 0, seg_src = 0, seg_n = 0;
+            if (p.tma) {
+                const int rho0 = (q0 >= 0) ? q0 / p.P : -((-q0 + p.P - 1) / p.P);
+                const int rho = rho0 + lane;
+                const int qs = rho * p.P;                           // flat position of x = 0 of this row
+                int xa = max(q0 - qs, -p.img_add[0]);               // first x with a real source bin
+                int xb = min(q0 + p.slots - qs, p.F_in - p.img_add[0]);
+                xb = min(xb, p.P);
+                const int b = (rho >= 0) ? rho / Tp : 0;
+                const int t = rho - b * Tp - p.padrow;
+                if (rho >= 0 && (long long)qs < (long long)p.total_flat && t >= 0 && xb > xa) {
+                    seg_dst = qs + xa - q0;
+                    seg_src = (b * p.T + t) * rs16 + xa + p.img_add[0];
+                    seg_n = xb - xa;
+                }
+            }
             for (int ph = 0; ph < p.nphase; ++ph, ++g) {
                 if (g >= NB) mbar_wait_relaxed(&a_empty[buf], round ^ 1);
                 const int c0 = ph * T3_KCH;
@@ -377,17 +423,32 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
                 const uint8_t* pb = src + (long long)((part * cpp0 + (cc >> 3) + chunk) * p.F_in) * 16;   // source plane
                 uint32_t d = dst0 + (uint32_t)buf * abuf_bytes;
                 const int* tb = slot_tbl + e0;
-                if (!(p.dbg & 1))
+                if (p.tma) {
+                    // zero the pad slots of this plane (generic proxy), then hand the row segments to the copy engine
+                    for (int k = 0; k < nit; ++k) {
+                        if (tb[k * ESTEP] < 0) asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(d), "r"(0) : "memory");
+                        d += ESTEP * 16;
+                    }
+                    fence_proxy_async();
+                    if (seg_n > 0 && !(p.dbg & 1)) {
+                        mbar_expect_tx(&a_full[buf], (uint32_t)seg_n * 16);
+                        bulk_g2s(abuf0 + (size_t)buf * abuf_bytes + (size_t)lw * p.plane_bytes + (size_t)seg_dst * 16,
+                                 pb + (long long)seg_src * 16, (uint32_t)seg_n * 16, &a_full[buf]);
+                    }
+                    mbar_arrive(&a_full[buf]);
+                } else {
+                    if (!(p.dbg & 1))
 #pragma unroll 4
-                for (int k = 0; k < nit; ++k) {
-                    const int o = tb[k * ESTEP];
-                    cp_async16_s(d, pb + (long long)(o < 0 ? 0 : o) * 16, (o >= 0) ? 16 : 0);
-                    d += ESTEP * 16;
+                    for (int k = 0; k < nit; ++k) {
+                        const int o = tb[k * ESTEP];
+                        cp_async16_s(d, pb + (long long)(o < 0 ? 0 : o) * 16, (o >= 0) ? 16 : 0);
+                        d += ESTEP * 16;
+                    }
+                    // completion is signalled by the copy engine itself: a_full[buf] collects one arrival per loader
+                    // thread, each triggered when that thread's copies above have landed -- the loaders never wait for
+                    // data, only for a free buffer, so signalling is decoupled from how far ahead they can issue
+                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&a_full[buf])) : "memory");
                 }
-                // completion is signalled by the copy engine itself: a_full[buf] collects one arrival per loader
-                // thread, each triggered when that thread's copies above have landed -- the loaders never wait for
-                // data, only for a free buffer, so signalling is decoupled from how far ahead they can issue
-                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&a_full[buf])) : "memory");
                 if (++buf == NB) {
                     buf = 0;
                     round ^= 1;

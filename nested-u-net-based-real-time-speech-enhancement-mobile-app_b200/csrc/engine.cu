@@ -229,6 +229,7 @@ struct Ten {
     bool scratch = false;     // offline: lives on the recyclable stack (offset fixed up by Plan::finalize)
     bool pingpong = false;    // streaming: two copies selected by step parity
     bool sh = false;          // holds split-half records (sh16 plans) rather than floats
+    bool eo = false;          // sh16: bins stored [even | odd] inside every plane
     std::string name;
     size_t numel() const { return (size_t)F * C; }
 };
@@ -365,6 +366,7 @@ struct Engine {
     bool use_tc = true;     // NUNET_CONV=simt forces the FP32 SIMT units everywhere
     int tc3_fence_mode = 0;  // NUNET_TC3_FENCE
     int tc3_dbg = 0;         // NUNET_TC3_DBG (experiments)
+    int tc3_tma = 0;         // NUNET_TC3_TMA=1 moves the row segments of stride-1 units (F_in >= 32) with bulk copies
     bool use_tc3 = true;    // NUNET_CONV=tc keeps the 3xTF32 kernel (fp32 activations) for the offline plan
     int tc_min_bins = 1;    // NUNET_TC_MIN_BINS: units with fewer conv-output bins stay on the SIMT kernel
     // per-launch profiling (bench.py roofline leg): one CUDA event after every launch on the launching stream
@@ -706,8 +708,10 @@ struct Engine {
 
     // Split-half tensor-core path (offline plans with sh16 tensors): every conv unit of the topology is eligible.
     void launch_conv_tc3(const ConvLayer& L, const float* a_cur, const float* b_cur, float* out, int B, int T, int F_in,
-                         cudaStream_t st) {
+                         bool src_eo, bool out_eo, cudaStream_t st) {
         Tc3Params p{};
+        p.src_eo = src_eo ? 1 : 0;
+        p.out_eo = out_eo ? 1 : 0;
         p.src0 = reinterpret_cast<const uint8_t*>(a_cur);
         p.src1 = reinterpret_cast<const uint8_t*>(b_cur);
         p.C0 = L.CA; p.C1 = L.CB;
@@ -752,6 +756,7 @@ struct Engine {
         }
         int maxoff = 0;
         for (int i = 0; i < p.ntaps; ++i) maxoff = std::max(maxoff, p.tap_off[i]);
+        p.tma = (tc3_tma && p.nimg == 1 && F_in >= 32 && !src_eo) ? 1 : 0;
         p.nphase = (L.CA + L.CB) / T3_KCH;
         p.nhalf = L.nhalf3;
         p.w_half_bytes = p.nphase * p.ntaps * L.N3 * 64;
@@ -841,7 +846,8 @@ struct Engine {
 
     // -------------------------------------------------------------------------------- topology -> plan
     // conv unit reading one or two tensors
-    Ten* op_conv(Plan& P, const std::string& role, Ten* a, Ten* b, const std::string& out_name, bool persistent) {
+    Ten* op_conv(Plan& P, const std::string& role, Ten* a, Ten* b, const std::string& out_name, bool persistent,
+                 bool out_eo = false) {
         const ConvLayer& L = convs.at(role);
         if (a->C != L.CA || (b ? b->C : 0) != L.CB || (b && b->F != a->F)) fail(NUNET_EINVAL, "plan: %s wiring", role.c_str());
         const int F_in = a->F;
@@ -849,12 +855,15 @@ struct Engine {
         const bool shuf = (L.epi == EPI_SHUF32 || L.epi == EPI_SHUF64);
         Ten* o = P.make(out_name, shuf ? 2 * F_conv : F_conv, shuf ? L.COUT / 2 : L.COUT, persistent);
         o->sh = P.sh16;
+        o->eo = P.sh16 && out_eo;
+        if (b && b->eo != a->eo) fail(NUNET_EINVAL, "plan: %s sources disagree on the bin order", role.c_str());
+        const bool src_eo = a->eo, dst_eo = o->eo;
         Plan* pp = &P;
         P.ops.push_back([=](Engine& E, const Run& r) {
             E.cur_op = out_name;
             if (pp->sh16) {
                 E.launch_conv_tc3(L, pp->cur(a, r.parity), b ? pp->cur(b, r.parity) : nullptr, pp->cur(o, r.parity), r.B, r.T,
-                                  F_in, r.st);
+                                  F_in, src_eo, dst_eo, r.st);
                 return;
             }
             E.launch_conv(L, pp->cur(a, r.parity), pp->prev(a, r.parity), b ? pp->cur(b, r.parity) : nullptr,
@@ -914,7 +923,7 @@ struct Engine {
 
     // One nested sub-U-Net (MSFE): returns ctfa(de_1) + en_in; fills des_out[k-1] = de_k (k = 1..n, F0 >> (k-1) bins)
     Ten* op_msfe(Plan& P, const std::string& blk, int n, Ten* en_in, Ten* const* skips, Ten** des_out,
-                 bool des_persistent, bool out_persistent) {
+                 bool des_persistent, bool out_persistent, bool out_eo) {
         std::string pc, ps;
         state_prefixes(blk, pc, ps);
         std::vector<Ten*> ens;
@@ -943,7 +952,8 @@ struct Engine {
                 s.b = sk;
                 P.states.push_back(s);
             }
-            cur = op_conv(P, blk + "_spconv" + std::to_string(k), cur, sk, blk + "_spconv" + std::to_string(k), des_persistent);
+            cur = op_conv(P, blk + "_spconv" + std::to_string(k), cur, sk, blk + "_spconv" + std::to_string(k), des_persistent,
+                          /*out_eo=*/k == n);
             des.push_back(cur);
         }
         if (des_out)
@@ -960,6 +970,9 @@ struct Engine {
         }
         Ten* out = P.make(blk + "_out", F0, 64, out_persistent);
         out->sh = P.sh16;
+        out->eo = P.sh16 && out_eo;
+        if (P.sh16 && (x->eo != en_in->eo)) fail(NUNET_EINVAL, "plan: %s gate operands disagree on the bin order", blk.c_str());
+        const int in_eo = x->eo ? 1 : 0, o_eo = out->eo ? 1 : 0;
         const MlpLayer mta = mlps.at(blk + "_ta"), mfa = mlps.at(blk + "_fa");
         Plan* pp = &P;
         const int off_mode = cfg.ctfa_mode;
@@ -983,7 +996,8 @@ struct Engine {
                 gate_residual_sh_kernel<<<blocks8, 256, 0, r.st>>>(reinterpret_cast<const uint8_t*>(pp->cur(x, r.parity)),
                                                                   reinterpret_cast<const uint8_t*>(pp->cur(en_in, r.parity)),
                                                                   pp->cur(gate, 0),
-                                                                  reinterpret_cast<uint8_t*>(pp->cur(out, r.parity)), n8, F0);
+                                                                  reinterpret_cast<uint8_t*>(pp->cur(out, r.parity)), n8, F0,
+                                                                  in_eo, o_eo);
             } else {
                 const int blocks = (int)std::min<long long>((n4 + 255) / 256, 148LL * 16);
                 gate_residual_kernel<<<blocks, 256, 0, r.st>>>(reinterpret_cast<const float4*>(pp->cur(x, r.parity)),
@@ -1021,8 +1035,8 @@ struct Engine {
         for (int i = 0; i < 6; ++i) {
             const std::string blk = ENC_NAMES[i];
             const size_t m = P.mark();
-            Ten* en_in = op_conv(P, blk + "_in", x, nullptr, blk + "_in", false);
-            Ten* out = op_msfe(P, blk, ENC_N[i], en_in, nullptr, enc_des[i], true, false);
+            Ten* en_in = op_conv(P, blk + "_in", x, nullptr, blk + "_in", false, /*out_eo=*/true);
+            Ten* out = op_msfe(P, blk, ENC_N[i], en_in, nullptr, enc_des[i], true, false, /*out_eo=*/true);
             x = op_conv(P, DOWN_NAMES[i], out, nullptr, DOWN_NAMES[i], true);
             enc_out[i] = x;
             if (recycle) P.release(m);
@@ -1032,8 +1046,8 @@ struct Engine {
             const std::string blk = DEC_NAMES[i];
             const int j = 5 - i;
             const size_t m = P.mark();
-            Ten* en_in = op_conv(P, blk + "_in", y, enc_out[j], blk + "_in", false);
-            y = op_msfe(P, blk, DEC_N[i], en_in, enc_des[j], nullptr, false, true);
+            Ten* en_in = op_conv(P, blk + "_in", y, enc_out[j], blk + "_in", false, /*out_eo=*/true);
+            y = op_msfe(P, blk, DEC_N[i], en_in, enc_des[j], nullptr, false, true, /*out_eo=*/false);
             if (recycle) P.release(m);
         }
         P.ops.push_back([=](Engine& E, const Run& r) {
@@ -1275,6 +1289,7 @@ int nunet_create(const nunet_config* cfg, const void* blob, size_t blob_bytes, n
         if (const char* c = getenv("NUNET_TC_MIN_BINS")) E.tc_min_bins = atoi(c);
         if (const char* c = getenv("NUNET_TC3_FENCE")) E.tc3_fence_mode = atoi(c);
         if (const char* c = getenv("NUNET_TC3_DBG")) E.tc3_dbg = atoi(c);
+        if (const char* c = getenv("NUNET_TC3_TMA")) E.tc3_tma = atoi(c);
         E.blob.parse(blob, blob_bytes);
         E.pack_params();
         E.pool.upload();
@@ -1470,8 +1485,9 @@ long long nunet_debug_read(nunet_engine* h, const char* tensor_name, float* buf,
                     memcpy(row.data(), dst, (size_t)4 * F * C);
                     for (int f = 0; f < F; ++f)
                         for (int c = 0; c < C; ++c) {
-                            const size_t hi = ((size_t)(c >> 3) * F + f) * 8 + (c & 7);
-                            const size_t lo = ((size_t)((C >> 3) + (c >> 3)) * F + f) * 8 + (c & 7);
+                            const int pos = t->eo ? (f & 1) * (F >> 1) + (f >> 1) : f;
+                            const size_t hi = ((size_t)(c >> 3) * F + pos) * 8 + (c & 7);
+                            const size_t lo = ((size_t)((C >> 3) + (c >> 3)) * F + pos) * 8 + (c & 7);
                             dst[(size_t)f * C + c] = __half2float(row[hi]) + __half2float(row[lo]);
                         }
                 }

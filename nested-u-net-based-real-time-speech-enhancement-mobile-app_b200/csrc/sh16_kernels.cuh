@@ -107,20 +107,26 @@ __global__ void __launch_bounds__(256) ctfa_ta_sh_kernel(const uint8_t* __restri
     }
 }
 
-// CTFA stage 3 + residual (models/proposed.py:319): out = x * gate[frame] + res.  Item = (frame, chunk, f): 8 channels.
+// storage position of bin f inside a plane: natural order, or [even bins | odd bins]
+__device__ __forceinline__ int sh16_pos(int f, int F, int eo) { return eo ? (f & 1) * (F >> 1) + (f >> 1) : f; }
+
+// CTFA stage 3 + residual (models/proposed.py:319): out = x * gate[frame] + res.  Item = (frame, chunk, output
+// position): 8 channels.  x and res are stored [even | odd] (in_eo), the output as the consumer wants it (out_eo).
 __global__ void __launch_bounds__(256) gate_residual_sh_kernel(const uint8_t* __restrict__ x, const uint8_t* __restrict__ res,
                                                               const float* __restrict__ gate /*[frames][64]*/,
-                                                              uint8_t* __restrict__ out, long long n8, int F) {
+                                                              uint8_t* __restrict__ out, long long n8, int F, int in_eo, int out_eo) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
         const long long fc = i / F;                 // frame * 8 + chunk
-        const int f = (int)(i - fc * F);
+        const int po = (int)(i - fc * F);           // output storage position
+        const int f = out_eo ? ((po < (F >> 1)) ? 2 * po : 2 * (po - (F >> 1)) + 1) : po;   // its bin
+        const int pi = sh16_pos(f, F, in_eo);
         const long long frame = fc >> 3;
         const int c8 = (int)(fc & 7);
         const long long rowoff = frame * ((long long)F * 256);
         float xv[8], rv[8];
-        sh16_load8(x + rowoff, F, 64, f, c8, xv);
-        sh16_load8(res + rowoff, F, 64, f, c8, rv);
+        sh16_load8(x + rowoff, F, 64, pi, c8, xv);
+        sh16_load8(res + rowoff, F, 64, pi, c8, rv);
         const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + frame * 64 + c8 * 8));
         const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + frame * 64 + c8 * 8) + 1);
         float o[8];
@@ -128,7 +134,7 @@ __global__ void __launch_bounds__(256) gate_residual_sh_kernel(const uint8_t* __
         o[2] = fmaf(xv[2], g0.z, rv[2]); o[3] = fmaf(xv[3], g0.w, rv[3]);
         o[4] = fmaf(xv[4], g1.x, rv[4]); o[5] = fmaf(xv[5], g1.y, rv[5]);
         o[6] = fmaf(xv[6], g1.z, rv[6]); o[7] = fmaf(xv[7], g1.w, rv[7]);
-        sh16_store8(out + rowoff, F, 64, f, c8, o);
+        sh16_store8(out + rowoff, F, 64, po, c8, o);
     }
 }
 
