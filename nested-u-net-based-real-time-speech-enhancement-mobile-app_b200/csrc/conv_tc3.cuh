@@ -56,7 +56,7 @@ constexpr int T3_EPI_WARPS = 8;
 constexpr int T3_LD_WARPS = 4;
 constexpr int T3_LD_THREADS = 32 * T3_LD_WARPS;
 constexpr int T3_THREADS = 32 * (T3_EPI_WARPS + T3_LD_WARPS + 1);
-constexpr int T3_MAXNB = 6;         // image ring depth
+constexpr int T3_MAXNB = 8;         // image ring depth
 constexpr int T3_TBL = 1024;        // slot table entries (nimg*slots <= 1024)
 constexpr int T3_PAR_OFF = 256;     // bias / gamma / beta staged as floats: 3 x 64
 constexpr int T3_TBL_OFF = 1024;
@@ -109,6 +109,14 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
         "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
 }
 
+// n / d for 0 <= n < 2^22 with a float reciprocal and a one-step fix-up
+__device__ __forceinline__ int small_div(int n, int d, float rcp) {
+    int q = (int)((float)n * rcp);
+    const int r = n - q * d;
+    q += (r >= d) ? 1 : 0;
+    q -= (r < 0) ? 1 : 0;
+    return q;
+}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -189,35 +197,57 @@ __device__ __forceinline__ void join8(const uint4& hi, const uint4& lo, float* v
     }
 }
 
-// LayerNorm (two-pass: mean, centred variance -- the reference's non-fused Keras path) + PReLU over v[0..CG) in
-// place, gamma / beta from shared memory.  Four partial sums keep the reductions off one dependent chain.
+// LayerNorm (two-pass: mean, centred variance -- the reference's non-fused Keras path) + PReLU over the CG values
+// v[0..CG/2) (float2 pairs) in place, gamma / beta from shared memory.  Packed fp32x2 arithmetic (FADD2 / FFMA2 on
+// sm_100) halves the instruction count of the element-wise passes; four partial sums keep the reductions off one
+// dependent chain.
 template <int CG>
-__device__ __forceinline__ void ln_prelu_s(float* v, const float* gamma_s, const float* beta_s, float alpha) {
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+__device__ __forceinline__ void ln_prelu_s(float2* v, const float* gamma_s, const float* beta_s, float alpha) {
+    float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int i = 0; i < CG; i += 4) {
-        s0 += v[i]; s1 += v[i + 1]; s2 += v[i + 2]; s3 += v[i + 3];
+    for (int i = 0; i < CG / 2; i += 2) {
+        s0 = __fadd2_rn(s0, v[i]);
+        s1 = __fadd2_rn(s1, v[i + 1]);
     }
-    const float mean = ((s0 + s1) + (s2 + s3)) * (1.0f / CG);
-    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+    const float mean = ((s0.x + s0.y) + (s1.x + s1.y)) * (1.0f / CG);
+    const float2 nmean = make_float2(-mean, -mean);
+    float2 q0 = make_float2(0.f, 0.f), q1 = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int i = 0; i < CG; i += 4) {
-        const float d0 = v[i] - mean, d1 = v[i + 1] - mean, d2 = v[i + 2] - mean, d3 = v[i + 3] - mean;
-        q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
+    for (int i = 0; i < CG / 2; i += 2) {
+        const float2 d0 = __fadd2_rn(v[i], nmean), d1 = __fadd2_rn(v[i + 1], nmean);
+        q0 = __ffma2_rn(d0, d0, q0);
+        q1 = __ffma2_rn(d1, d1, q1);
     }
-    const float inv = rsqrtf(((q0 + q1) + (q2 + q3)) * (1.0f / CG) + LN_EPS);
-    const float minv = -mean * inv;
+    const float inv = rsqrtf(((q0.x + q0.y) + (q1.x + q1.y)) * (1.0f / CG) + LN_EPS);
+    const float2 inv2 = make_float2(inv, inv), minv2 = make_float2(-mean * inv, -mean * inv);
 #pragma unroll
-    for (int i = 0; i < CG; i += 4) {
-        const float4 g = *reinterpret_cast<const float4*>(gamma_s + i);
-        const float4 b = *reinterpret_cast<const float4*>(beta_s + i);
-        const float gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float y = fmaf(fmaf(v[i + e], inv, minv), gg[e], bb[e]);
-            v[i + e] = y >= 0.f ? y : alpha * y;
-        }
+    for (int i = 0; i < CG / 2; i += 2) {
+        const float4 g = *reinterpret_cast<const float4*>(gamma_s + 2 * i);
+        const float4 b = *reinterpret_cast<const float4*>(beta_s + 2 * i);
+        float2 y0 = __ffma2_rn(__ffma2_rn(v[i], inv2, minv2), make_float2(g.x, g.y), make_float2(b.x, b.y));
+        float2 y1 = __ffma2_rn(__ffma2_rn(v[i + 1], inv2, minv2), make_float2(g.z, g.w), make_float2(b.z, b.w));
+        if (y0.x < 0.f) y0.x *= alpha;
+        if (y0.y < 0.f) y0.y *= alpha;
+        if (y1.x < 0.f) y1.x *= alpha;
+        if (y1.y < 0.f) y1.y *= alpha;
+        v[i] = y0;
+        v[i + 1] = y1;
     }
+}
+
+// hi/lo split of 8 consecutive values (4 float2 pairs) into two 16-byte vectors of halves
+__device__ __forceinline__ void split8p(const float2* v, uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half2 hh = __float22half2_rn(v[i]);
+        const float2 r = __fadd2_rn(v[i], make_float2(-__low2float(hh), -__high2float(hh)));
+        const __half2 ll = __float22half2_rn(r);
+        h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 // N: conv channels of this CTA (32 / 64); PC: channels per OUTPUT pixel (N, or 32 for the 64-column sub-pixel
@@ -305,30 +335,32 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
             const int opos0 = p.out_eo ? (obin0 & 1) * (p.F_out >> 1) + (obin0 >> 1) : obin0;
             uint8_t* orow = p.out + ((long long)b * p.T + t) * out_rs + (long long)opos0 * 16;
             const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((ab * p.mt + mt) * 2 * N);
-            float v[N];
+            float2 v[N / 2];
+            float* vf = reinterpret_cast<float*>(v);
 #pragma unroll
-            for (int c = 0; c < N; c += 32) tmem_ld32(taddr + c, v + c);            // a_hi*b_hi + a_lo*b_hi
+            for (int c = 0; c < N; c += 32) tmem_ld32(taddr + c, vf + c);           // a_hi*b_hi + a_lo*b_hi
 #pragma unroll
             for (int c = 0; c < N; c += 32) {                                        // + a_hi*b_lo
-                float u[32];
-                tmem_ld32(taddr + N + c, u);
+                float2 u[16];
+                tmem_ld32(taddr + N + c, reinterpret_cast<float*>(u));
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[c + i] += u[i];
+                for (int i = 0; i < 16; ++i) v[c / 2 + i] = __fadd2_rn(v[c / 2 + i], u[i]);
             }
             // the accumulator is in registers: hand the TMEM buffer back to the MMA warp right away
             tc_fence_before();
             mbar_arrive(&acc_empty[ab]);
+            {
+                const float2 sc = make_float2(p.wscale_inv, p.wscale_inv);
 #pragma unroll
-            for (int c = 0; c < N; c += 4) {
-                const float4 bv = *reinterpret_cast<const float4*>(par_s + c);
-                v[c] = fmaf(v[c], p.wscale_inv, bv.x);
-                v[c + 1] = fmaf(v[c + 1], p.wscale_inv, bv.y);
-                v[c + 2] = fmaf(v[c + 2], p.wscale_inv, bv.z);
-                v[c + 3] = fmaf(v[c + 3], p.wscale_inv, bv.w);
+                for (int c = 0; c < N; c += 4) {
+                    const float4 bv = *reinterpret_cast<const float4*>(par_s + c);
+                    v[c / 2] = __ffma2_rn(v[c / 2], sc, make_float2(bv.x, bv.y));
+                    v[c / 2 + 1] = __ffma2_rn(v[c / 2 + 1], sc, make_float2(bv.z, bv.w));
+                }
             }
             if (LN && !(p.dbg & 8)) {
 #pragma unroll
-                for (int g = 0; g < NPX; ++g) ln_prelu_s<PC>(v + g * PC, par_s + 64, par_s + 128, alpha);
+                for (int g = 0; g < NPX; ++g) ln_prelu_s<PC>(v + g * PC / 2, par_s + 64, par_s + 128, alpha);
             }
             if (valid && !(p.dbg & 2)) {
                 if (NPX == 2 && !p.out_eo) {
@@ -336,8 +368,8 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
 #pragma unroll
                     for (int c = 0; c < CPP; ++c) {
                         uint4 h0, l0, h1, l1;
-                        split8(v + 8 * c, h0, l0);
-                        split8(v + PC + 8 * c, h1, l1);
+                        split8p(v + 4 * c, h0, l0);
+                        split8p(v + PC / 2 + 4 * c, h1, l1);
                         st_global_32B(orow + c * plane, h0, h1);
                         st_global_32B(orow + (CPP + c) * plane, l0, l1);
                     }
@@ -349,7 +381,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
 #pragma unroll
                         for (int c = 0; c < CPP; ++c) {
                             uint4 hi, lo;
-                            split8(v + g * PC + 8 * c, hi, lo);
+                            split8p(v + g * PC / 2 + 4 * c, hi, lo);
                             *reinterpret_cast<uint4*>(o + c * plane) = hi;
                             *reinterpret_cast<uint4*>(o + (CPP + c) * plane) = lo;
                         }
@@ -374,27 +406,37 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
         const int cpp0 = p.C0 >> 3;                            // chunks per part of a source (C1 == C0)
         const int rs16 = p.F_in * (p.C0 >> 2);                 // 16-byte units per source frame row
         const int NB = p.nabuf;
+        const float rcpP = 1.0f / (float)p.P, rcpTp = 1.0f / (float)Tp;
         int buf = 0, round = 0;        // ring position of phase g and the parity of its use count
         int g = 0;
         for (int it = 0; it < my_tiles; ++it) {
             const int tile = cta + it * ncta;
             const int q0 = tile * tile_pos - p.lead;
             if (it > 0) asm volatile("bar.sync 1, %0;" ::"n"(T3_LD_THREADS) : "memory");   // everyone is done with the old table
-            for (int e = lt; e < nit * ESTEP; e += T3_LD_THREADS) {
-                const int img = (e >= p.slots) ? 1 : 0;
-                const int slot = e - img * p.slots;
-                const int q = q0 + slot;
-                int o = -1;
-                if (e < nslot && q >= 0 && q < p.total_flat) {
-                    const int rho = q / p.P;
-                    const int x = q - rho * p.P;
-                    const int b = rho / Tp;
-                    const int t = (rho - b * Tp) - p.padrow;
-                    const int fi = p.img_mul[img] * x + p.img_add[img];
-                    if (t >= 0 && fi >= 0 && fi < p.F_in)
-                        o = (b * p.T + t) * rs16 + (p.src_eo ? (fi & 1) * (p.F_in >> 1) + (fi >> 1) : fi);
+            {
+                // (row, x) of slot 0 by two real divisions per tile; every entry then needs only small-number
+                // divisions (float reciprocal + fix-up): slot < 2^11, rows per tile < 2^11
+                const int rho0 = (q0 >= 0) ? q0 / p.P : -((-q0 + p.P - 1) / p.P);
+                const int x0 = q0 - rho0 * p.P;
+                const int b0 = (rho0 >= 0) ? rho0 / Tp : 0;
+                const int t0 = rho0 - b0 * Tp;                     // row inside clip b0 (negative before the first clip)
+                for (int e = lt; e < nit * ESTEP; e += T3_LD_THREADS) {
+                    const int img = (e >= p.slots) ? 1 : 0;
+                    const int slot = e - img * p.slots;
+                    const int xs = x0 + slot;
+                    const int drho = small_div(xs, p.P, rcpP);
+                    const int x = xs - drho * p.P;
+                    const int ts = t0 + drho;
+                    int o = -1;
+                    if (e < nslot && ts >= 0 && q0 + slot < p.total_flat) {
+                        const int db = small_div(ts, Tp, rcpTp);
+                        const int t = ts - db * Tp - p.padrow;
+                        const int fi = p.img_mul[img] * x + p.img_add[img];
+                        if (t >= 0 && fi >= 0 && fi < p.F_in)
+                            o = ((b0 + db) * p.T + t) * rs16 + (p.src_eo ? (fi & 1) * (p.F_in >> 1) + (fi >> 1) : fi);
+                    }
+                    slot_tbl[e] = o;
                 }
-                slot_tbl[e] = o;
             }
             asm volatile("bar.sync 1, %0;" ::"n"(T3_LD_THREADS) : "memory");
             // TMA mode: lane r describes the part of frame row (first row of the tile + r) that lies inside the image

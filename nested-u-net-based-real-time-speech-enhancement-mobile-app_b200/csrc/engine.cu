@@ -366,6 +366,7 @@ struct Engine {
     bool use_tc = true;     // NUNET_CONV=simt forces the FP32 SIMT units everywhere
     int tc3_fence_mode = 0;  // NUNET_TC3_FENCE
     int tc3_dbg = 0;         // NUNET_TC3_DBG (experiments)
+    int tc3_force_mt = 0;    // NUNET_TC3_MT (experiments)
     int tc3_tma = 0;         // NUNET_TC3_TMA=1 moves the row segments of stride-1 units (F_in >= 32) with bulk copies
     bool use_tc3 = true;    // NUNET_CONV=tc keeps the 3xTF32 kernel (fp32 activations) for the offline plan
     int tc_min_bins = 1;    // NUNET_TC_MIN_BINS: units with fewer conv-output bins stay on the SIMT kernel
@@ -780,7 +781,9 @@ struct Engine {
         size_t abuf2, abuf1;
         const int nb2 = geometry(2, slots2, plane2, abuf2), nb1 = geometry(1, slots1, plane1, abuf1);
         const bool ok = nb2 >= 2 || nb1 >= 2;
-        const bool two = nb2 >= 3 || (nb2 >= 2 && nb1 < 3);
+        bool two = nb2 >= 2;   // larger tiles beat a deeper ring (measured): per-tile overheads dominate
+        if (tc3_force_mt == 1 && nb1 >= 2) two = false;
+        if (tc3_force_mt == 2 && nb2 >= 2) two = true;
         p.mt = two ? 2 : 1;
         p.slots = two ? slots2 : slots1;
         p.plane_bytes = two ? plane2 : plane1;
@@ -1290,6 +1293,7 @@ int nunet_create(const nunet_config* cfg, const void* blob, size_t blob_bytes, n
         if (const char* c = getenv("NUNET_TC3_FENCE")) E.tc3_fence_mode = atoi(c);
         if (const char* c = getenv("NUNET_TC3_DBG")) E.tc3_dbg = atoi(c);
         if (const char* c = getenv("NUNET_TC3_TMA")) E.tc3_tma = atoi(c);
+        if (const char* c = getenv("NUNET_TC3_MT")) E.tc3_force_mt = atoi(c);
         E.blob.parse(blob, blob_bytes);
         E.pack_params();
         E.pool.upload();

@@ -38,10 +38,11 @@ __global__ void __launch_bounds__(128) input_layer_sh_kernel(const float* __rest
     const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (pix >= npix) return;
     const float x = __ldg(mag + pix);
-    float v[64];
+    float2 v2[32];
+    float* v = reinterpret_cast<float*>(v2);
 #pragma unroll
     for (int c = 0; c < 64; ++c) v[c] = fmaf(x, par[c], par[64 + c]);
-    ln_prelu_s<64>(v, par + 128, par + 192, __ldg(alpha));
+    ln_prelu_s<64>(v2, par + 128, par + 192, __ldg(alpha));
     const long long frame = pix / F;
     const int f = (int)(pix - frame * F);
     uint8_t* row = out + frame * ((long long)F * 256);
@@ -84,6 +85,7 @@ __global__ void __launch_bounds__(256) ctfa_ta_sh_kernel(const uint8_t* __restri
     const int c8 = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint8_t* row = x + (size_t)frame * F * 256;
     float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
     for (int f = lane; f < F; f += 32) {
         float v[8];
         sh16_load8(row, F, 64, f, c8, v);
