@@ -231,9 +231,19 @@ def main():
             k[1] += nbytes
         top_name, (top_ms, top_bytes) = max(by_kernel.items(), key=lambda kv: kv[1][0])
         achieved = top_bytes / (top_ms * 1e-3) / 1e9
+        # DRAM bytes of that launch from the committed ncu capture of the same command line (profiles/), if the
+        # capture was taken at this batch size
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r1_tc3_dram_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            u = tj["units"].get(top_name)
+            if u is not None and tj["frames"] == B * T:
+                traffic = u["dram_read_bytes"] + u["dram_write_bytes"]
         path_gbs = value / world * B_ALG_BYTES_PER_FRAME / 1e9
         roofline = {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes": top_bytes,
+                    "peak_source": peak_src,
                     "kernel_ms": top_ms, "kernel_share_of_step": top_ms / total_ms,
                     "path": {"achieved": path_gbs, "frac": path_gbs / peak,
                              "b_alg_bytes_per_frame": B_ALG_BYTES_PER_FRAME,
