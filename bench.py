@@ -102,6 +102,93 @@ def cpu_reference_leg(weights, n_samples: int, clips: int, steps: int, warmup: i
     return clips * T * steps / dt, dt / steps, cores, f"{clips} clips x {T} frames per step, offline forward, torch fp32 CPU"
 
 
+B_ALG_STREAM_BYTES_PER_FRAME = 5.897e6   # 4.256 MB + 1.641 MB history read + write per stream-frame
+
+
+def streaming_main(args, weights, rank, local_rank, world):
+    """configs[2]: S concurrent streams, frame-basis, history carried on the device (interpreter_proposed.py:200-366
+    for S streams at once).  One step = one hop of every stream."""
+    import torch
+    import torch.distributed as dist
+    from nunet_b200.engine import NunetEngine
+    from nunet_b200.synth import synth_clips
+    from nunet_b200.weights import pack_blob
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    blob = pack_blob(weights)
+    if world > 1:
+        from nunet_b200.sharding import broadcast_blob
+        dist.init_process_group("nccl", device_id=dev)
+        blob = broadcast_blob(blob if rank == 0 else None, src=0, device=dev)
+    S = args.streams
+    eng = NunetEngine(blob, max_streams=S, device=local_rank, ctfa_mode="frame_div32", dc_mode="edge")
+    nh = args.warmup + args.steps + 4
+    pool = synth_clips(min(S, 32), 256 * nh, first_clip=1000 * rank)
+    hops_h = torch.from_numpy(np.tile(pool, ((S + len(pool) - 1) // len(pool), 1))[:S]).reshape(S, nh, 256)
+    hops_h = hops_h.permute(1, 0, 2).contiguous().pin_memory()          # [hop][stream][256]
+    hops_d = hops_h.to(dev)
+    out_d = torch.empty((S, 256), device=dev)
+    out_h = torch.empty((S, 256)).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    eng.stream_reset()
+    W = max(args.warmup, 3)
+    for i in range(W):
+        eng.stream_step_wav(hops_d[i % nh], out_d)
+    launches = eng.last_launch_count
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        eng.stream_step_wav(hops_d[(W + i) % nh], out_d)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * S * args.steps / (ms * 1e-3)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        eng.stream_step_wav_host(hops_h[(W + i) % nh], out_h)
+    torch.cuda.synchronize(dev)
+    e2e = world * S * args.steps / max_over_ranks(time.perf_counter() - t0)
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        gbs = value / world * B_ALG_STREAM_BYTES_PER_FRAME / 1e9
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"configs[2]: streaming frame-basis, {S} concurrent streams per GPU with carried conv / LSTM "
+                                   "history, NUNet-TLS-LSTM, ctfa frame_div32 (one-frame graph)", "streams_per_gpu": S,
+                       "l2_policy": f"per-step working set {S * B_ALG_STREAM_BYTES_PER_FRAME / 1e9:.1f} GB exceeds the 126 MB L2"},
+            "rtf_per_stream": (ms / args.steps * 1e-3) / 0.016, "clocks": clocks,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": S * 256 * 4, "d2h_bytes_per_step": S * 256 * 4},
+            "gpu_launches": int(launches * args.steps),
+            "roofline": {"bound": "hbm", "kernel": "whole streaming step (FP32 SIMT units)", "achieved": gbs, "peak": peak,
+                         "unit": "GB/s", "frac": gbs / peak, "traffic": None, "peak_source": peak_src,
+                         "b_alg_bytes_per_frame": B_ALG_STREAM_BYTES_PER_FRAME},
+            "cpu_baseline": None,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -111,6 +198,10 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="clips per GPU per step")
     ap.add_argument("--seconds", type=float, default=4.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="offline", choices=["offline", "streaming"],
+                    help="offline = BASELINE configs[1] (default, the headline); streaming = configs[2]: --streams "
+                         "concurrent streams, one 256-sample hop per stream per step, carried conv/LSTM history")
+    ap.add_argument("--streams", type=int, default=1024)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -148,6 +239,8 @@ def main():
         return
 
     # ------------------------------------------------------------------ our arm
+    if args.config == "streaming":
+        return streaming_main(args, weights, rank, local_rank, world)
     import torch
     import torch.distributed as dist
     from nunet_b200.engine import NunetEngine
@@ -157,11 +250,10 @@ def main():
     dev = torch.device("cuda", local_rank)
     blob = pack_blob(weights)
     if world > 1:
+        from nunet_b200.sharding import broadcast_blob
         dist.init_process_group("nccl", device_id=dev)
         # the only collective of the path: rank 0's packed weights go to every GPU once (NVLink / NCCL)
-        t = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
-        dist.broadcast(t, src=0)
-        blob = bytes(t.cpu().numpy().tobytes())
+        blob = broadcast_blob(blob if rank == 0 else None, src=0, device=dev)
 
     B = args.batch
     eng = NunetEngine(blob, max_frames=B * T, device=local_rank, ctfa_mode="causal_avg32")
