@@ -87,6 +87,84 @@ def lstm_weights_from_h5(path: str) -> Dict[str, np.ndarray]:
     return out
 
 
+def _tflite_role_tensors(path: str):
+    """role -> list of constant tensors of a shipped .tflite whose name starts with the Keras layer name
+    (`<layer>/<sub-layer>/<op>`).  Returns (graph, {role: [Tensor]})."""
+    from .tflite_reader import read_tflite
+    g = read_tflite(path)
+    by_role: Dict[str, list] = {}
+    for t in g.tensors:
+        if t.data is None or t.data.size == 0 or t.dtype not in (np.float32, np.int8):
+            continue
+        first = t.name.split(";")[0]
+        if "/" not in first:
+            continue
+        by_role.setdefault(first.split("/")[0], []).append(t)
+    return g, by_role
+
+
+def _unit_from_tflite(role: str, tensors, out: Dict[str, np.ndarray]) -> None:
+    """Fill the `<role>/...` entries of a weight set from the constants attributed to that layer, converting
+    TFLite layouts to the Keras ones: conv [Cout,kh,kw,Cin] -> (kh,kw,Cin,Cout); transpose conv
+    [Cout,kh,kw,Cin] -> (kh,kw,Cout,Cin); FC [out,in] -> (in,out)."""
+    convs, biases = [], {}
+    for t in tensors:
+        sub = t.name.split(";")[0].split("/")[1]
+        leaf = t.name.split(";")[0].split("/", 2)[2] if t.name.split(";")[0].count("/") >= 2 else ""
+        w = t.dequantized()
+        if sub.startswith("layer_normalization"):
+            if leaf == "batchnorm/mul/ReadVariableOp":
+                out[f"{role}/gamma"] = w
+            elif leaf == "batchnorm/ReadVariableOp":
+                out[f"{role}/beta"] = w
+        elif sub.startswith("p_re_lu"):
+            out[f"{role}/alpha"] = w.reshape(1)
+        elif sub.startswith("lstm_cell"):
+            if w.ndim == 2 and w.shape == (84, 21):         # leaf names vary (MatMul_1, MatMul_11): go by shape
+                out[f"{role}/recurrent_kernel"] = np.ascontiguousarray(w.T)
+            elif w.ndim == 2:
+                out[f"{role}/kernel"] = np.ascontiguousarray(w.T)
+            elif leaf.startswith("BiasAdd"):
+                out[f"{role}/bias"] = w
+        elif sub == "Tensordot":                                # Dense applied to [T, 21]
+            out[f"{role}/kernel"] = np.ascontiguousarray(w.T)
+        elif sub == "BiasAdd":
+            out[f"{role}/bias"] = w
+        elif sub.startswith("conv2d_transpose"):
+            if w.ndim == 4:
+                out[f"{role}/kernel"] = np.ascontiguousarray(w.transpose(1, 2, 0, 3))
+            else:
+                out[f"{role}/bias"] = w
+        elif sub.startswith("conv") or sub == "Conv2D":
+            if w.ndim == 4:
+                convs.append((_suffix(sub), np.ascontiguousarray(w.transpose(1, 2, 3, 0))))
+            elif leaf.startswith("BiasAdd"):
+                biases[_suffix(sub)] = w
+    convs.sort(key=lambda c: c[0])
+    if role.endswith("_ta") or role.endswith("_fa"):
+        for i, (suf, k) in enumerate(convs):
+            out[f"{role}/kernel{i}"] = k.reshape(k.shape[-2:])
+            out[f"{role}/bias{i}"] = biases[suf]
+    elif convs:
+        suf, k = convs[0]
+        out[f"{role}/kernel"] = k
+        if suf in biases:
+            out[f"{role}/bias"] = biases[suf]
+
+
+def lstm_weights_from_tflite(path: str) -> Dict[str, np.ndarray]:
+    """Role-named float32 weight set of NUNet-TLS-LSTM from the shipped `nutls_lstm.tflite`: int8 tensors are
+    dequantised (q * scale, per output channel for conv, per tensor for FC).  Used to run the source restatement
+    and the flatbuffer executor with IDENTICAL weights."""
+    _g, by_role = _tflite_role_tensors(path)
+    out: Dict[str, np.ndarray] = {}
+    for role, tensors in by_role.items():
+        _unit_from_tflite("out_conv" if role == "conv2d" else role, tensors, out)
+    for un in UP_NAMES:                                         # no bias tensor in the graph when it is all zeros
+        out.setdefault(f"{un}/bias", np.zeros(128, np.float32))
+    return out
+
+
 def expected_lstm_shapes() -> Dict[str, tuple]:
     """Shape table of the LSTM variant, derived from the topology, used to validate a set."""
     s: Dict[str, tuple] = {}
@@ -183,6 +261,10 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_BLOB = os.path.join(_HERE, "data", "nutls_lstm.nunetw")
 REFERENCE_H5 = "/root/reference/dnn_model/log/saved_model/nutls_lstm.h5"
+# the same architecture with the weights of the reference's SHIPPED graph (int8 tensors dequantised): lets the engine
+# and the source restatement be compared with the flatbuffer executor on identical weights
+TFLITE_LSTM_BLOB = os.path.join(_HERE, "data", "nutls_lstm_tflite.nunetw")
+REFERENCE_TFLITE_LSTM = "/root/reference/dnn_model/tflite/nutls_lstm.tflite"
 
 
 def ensure_default_blob() -> str:
@@ -194,6 +276,24 @@ def ensure_default_blob() -> str:
         with open(DEFAULT_BLOB, "wb") as f:
             f.write(pack_blob(w))
     return DEFAULT_BLOB
+
+
+def ensure_tflite_lstm_blob() -> str:
+    if not os.path.exists(TFLITE_LSTM_BLOB) and os.path.exists(REFERENCE_TFLITE_LSTM):
+        w = lstm_weights_from_tflite(REFERENCE_TFLITE_LSTM)
+        validate(w, expected_lstm_shapes())
+        os.makedirs(os.path.dirname(TFLITE_LSTM_BLOB), exist_ok=True)
+        with open(TFLITE_LSTM_BLOB, "wb") as f:
+            f.write(pack_blob(w))
+    return TFLITE_LSTM_BLOB
+
+
+def load_tflite_lstm_weights() -> Dict[str, np.ndarray]:
+    path = ensure_tflite_lstm_blob()
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"{path} missing and {REFERENCE_TFLITE_LSTM} not available")
+    with open(path, "rb") as f:
+        return unpack_blob(f.read())[0]
 
 
 def load_default_weights() -> Dict[str, np.ndarray]:

@@ -26,3 +26,18 @@ def weights():
 @pytest.fixture(scope="session")
 def golden_io():
     return dict(np.load(os.path.join(GOLDEN, "oracle_io_lstm.npz")))
+
+
+@pytest.fixture(scope="session")
+def tflite_weights():
+    """Weights of the reference's shipped nutls_lstm.tflite (int8 tensors dequantised), role-named."""
+    from nunet_b200.weights import load_tflite_lstm_weights
+    try:
+        return load_tflite_lstm_weights()
+    except FileNotFoundError as e:
+        pytest.skip(str(e))
+
+
+@pytest.fixture(scope="session")
+def golden_o2():
+    return dict(np.load(os.path.join(GOLDEN, "o2_lstm.npz")))

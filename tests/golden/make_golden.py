@@ -6,6 +6,7 @@ Fixtures:
   state_shapes_lstm.json   history-tensor table of interpreter_proposed.py:36-198
   input_specs_lstm.json    TensorSpec names/shapes of converter_proposed.py:26-187
   wav_excerpt.npz          first 1.5 s (int16) of data/40hc020i_0.wav (noisy) and data/40hc020i.wav (clean)
+  o2_lstm.npz              outputs of the reference's shipped nutls_lstm.tflite executed by oracle/tflite_graph.py
   oracle_io_lstm.npz       oracle outputs with the reference .h5 weights on seeded inputs (regression pin +
                            expected values for the GPU parity tests)
 """
@@ -57,6 +58,34 @@ def wav_excerpt():
                         clean=np.round(clean[:n] * 32768).astype(np.int16), fs=fs)
 
 
+def graph_oracle_io():
+    """o2_lstm.npz: the reference's shipped nutls_lstm.tflite executed frame by frame (oracle/tflite_graph.py) on 48
+    frames of the reference's own noisy excerpt: input magnitudes, model_out, and three final history tensors."""
+    from oracle.nunet_oracle import Oracle, min_max_norm
+    from oracle.tflite_graph import TFLiteGraph, zero_feed
+    from oracle.wavio import read_wav
+    noisy, _ = read_wav(f"{REF}/dnn_model/data/40hc020i_0.wav")
+    noisy = min_max_norm(noisy).astype(np.float32)
+    T = 48
+    seg = noisy[8000:8000 + 512 + 256 * (T - 1)]
+    mags, _ = Oracle({}, ctfa_mode="frame_div32").stft(torch.from_numpy(seg)[None])
+    mag = mags[0, :, 1:].numpy().astype(np.float32)
+    g = TFLiteGraph(f"{REF}/dnn_model/tflite/nutls_lstm.tflite")
+    feed = zero_feed(g)
+    outs = []
+    with torch.no_grad():
+        for t in range(T):
+            feed["input"] = torch.from_numpy(mag[t].reshape(1, 1, 256, 1))
+            res = g.run(feed)
+            outs.append(res["model_out"].reshape(256).numpy().copy())
+            for k, val in res.items():
+                kin = k.replace("_cur", "_prev")
+                if k != "model_out" and kin in feed:
+                    feed[kin] = val
+    keep = {k: res[k].numpy() for k in ("msfe6_ee_cur1", "msfe4_dd2_cur3", "state_h", "msfe5_en_c")}
+    np.savez_compressed(f"{HERE}/o2_lstm.npz", mag=mag, model_out=np.stack(outs), **{f"state_{k}": v for k, v in keep.items()})
+
+
 def oracle_io():
     from nunet_b200.synth import synth_clips
     from nunet_b200.weights import lstm_weights_from_h5
@@ -78,4 +107,5 @@ if __name__ == "__main__":
     state_tables()
     wav_excerpt()
     oracle_io()
+    graph_oracle_io()
     print("fixtures written to", HERE)

@@ -254,3 +254,35 @@ def test_enhancement_quality_on_reference_excerpt(blob):
     y = y.cpu().numpy()[0]
     before, after = si_sdr(clean[:len(y)], x[0, :len(y)]), si_sdr(clean[:len(y)], y)
     assert after > before + 8.0, (before, after)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Parity with the reference's DEPLOYED graph: the shipped nutls_lstm.tflite executed by oracle/tflite_graph.py
+# (committed fixture tests/golden/o2_lstm.npz), engine loaded with the same (dequantised) weights.
+def test_streaming_engine_matches_shipped_tflite_graph(tflite_weights, golden_o2):
+    from nunet_b200.weights import pack_blob
+    mag = golden_o2["mag"]
+    eng = _engine(pack_blob(tflite_weights), max_streams=2, ctfa_mode="frame_div32")
+    eng.stream_reset()
+    outs = []
+    for t in range(mag.shape[0]):
+        m = torch.from_numpy(np.stack([mag[t], mag[t]])).cuda()       # two identical streams
+        outs.append(eng.stream_step_mag(m).cpu().numpy())
+    est = np.stack(outs)                                               # [T, 2, 256]
+    ref = golden_o2["model_out"]
+    assert ref.max() > 20.0
+    assert np.abs(est[:, 0] - ref).max() <= TOL_MAG
+    assert (est[:, 0] == est[:, 1]).all()
+    for k in ("msfe6_ee_cur1", "msfe4_dd2_cur3", "state_h", "msfe5_en_c"):
+        name = k.replace("_cur", "_") if "_cur" in k else k
+        got = eng.state_export(1, name)
+        assert np.abs(got - golden_o2[f"state_{k}"].reshape(-1)).max() <= TOL_MAG, k
+
+
+def test_offline_engine_matches_shipped_tflite_graph(tflite_weights, golden_o2):
+    """Zero history == zero padding: the offline tensor-core path in frame_div32 mode computes the deployed graph."""
+    from nunet_b200.weights import pack_blob
+    mag = torch.from_numpy(golden_o2["mag"])[None].contiguous().cuda()
+    eng = _engine(pack_blob(tflite_weights), max_frames=mag.shape[1], ctfa_mode="frame_div32")
+    est = eng.forward_mag(mag).cpu().numpy()[0]
+    assert np.abs(est - golden_o2["model_out"]).max() <= TOL_MAG
