@@ -30,6 +30,7 @@
 #include "framing.cuh"
 #include "misc_kernels.cuh"
 #include "sh16_kernels.cuh"
+#include "ddb_kernels.cuh"
 
 namespace nunet {
 
@@ -145,6 +146,11 @@ struct MlpLayer {
 struct LstmLayer {
     size_t wk, wr, wb, dk, db;
     int D;
+};
+struct DdbLayer {   // one dilated dense block: float offsets into the pool
+    int C = 0;
+    size_t w_in, b_in, a_in, w_out, b_out, a_out;
+    size_t w0[6], b0[6], w1[6], b1[6], gamma[6], beta[6], alpha[6];
 };
 struct VecLayer {   // input_layer / out_conv
     size_t w, b, gamma, beta, alpha;
@@ -346,6 +352,7 @@ struct Engine {
     std::map<std::string, ConvLayer> convs;
     std::map<std::string, MlpLayer> mlps;
     std::map<std::string, LstmLayer> lstms;
+    std::map<std::string, DdbLayer> ddbs;
     VecLayer in_layer{}, out_layer{};
     size_t tw_off = 0, win_off = 0, win_stream_off = 0, inv_win_off = 0;
 
@@ -504,10 +511,34 @@ struct Engine {
         lstms[lstm] = l;
     }
 
+    // role = "<block>_ddb" or "ddb": in / 1..6 / out (weights.py: ddb_weights_from_tflite)
+    void add_ddb(const std::string& role, int C) {
+        const int h = C / 2;
+        DdbLayer d;
+        d.C = C;
+        d.w_in = add_arr(role + "_in/kernel", {2, 3, C, h});
+        d.b_in = add_arr(role + "_in/bias", {h});
+        d.a_in = add_arr(role + "_in/alpha", {1});
+        for (int k = 1; k <= 6; ++k) {
+            const std::string r = role + "_" + std::to_string(k);
+            d.w0[k - 1] = add_arr(r + "/kernel0", {2, 3, k, h});
+            d.b0[k - 1] = add_arr(r + "/bias0", {h});
+            d.w1[k - 1] = add_arr(r + "/kernel1", {h, h});
+            d.b1[k - 1] = add_arr(r + "/bias1", {h});
+            d.gamma[k - 1] = add_arr(r + "/gamma", {h});
+            d.beta[k - 1] = add_arr(r + "/beta", {h});
+            d.alpha[k - 1] = add_arr(r + "/alpha", {1});
+        }
+        d.w_out = add_arr(role + "_out/kernel", {2, 3, h, C});
+        d.b_out = add_arr(role + "_out/bias", {C});
+        d.a_out = add_arr(role + "_out/alpha", {1});
+        ddbs[role] = d;
+    }
+    bool is_ddb() const { return cfg.variant == NUNET_VARIANT_DDB; }
+
     void pack_params() {
-        if (blob.variant != NUNET_VARIANT_LSTM || cfg.variant != NUNET_VARIANT_LSTM)
-            fail(NUNET_EINVAL, "this build implements the NUNet-TLS-LSTM variant only (blob variant %d, cfg %d)",
-                 blob.variant, cfg.variant);
+        if (blob.variant != cfg.variant || (cfg.variant != NUNET_VARIANT_LSTM && cfg.variant != NUNET_VARIANT_DDB))
+            fail(NUNET_EINVAL, "weight blob variant %d does not match the requested variant %d", blob.variant, cfg.variant);
         in_layer.w = add_arr("input_layer/kernel", {1, 1, 1, 64});
         in_layer.b = add_arr("input_layer/bias", {64});
         in_layer.gamma = add_arr("input_layer/gamma", {64});
@@ -528,7 +559,8 @@ struct Engine {
                     else { CA = (k == 1) ? 64 : 32; CB = CA; }
                     add_conv(blk + "_conv" + std::to_string(k), CA, CB, 32, 2, 3, 1, 2, EPI_LN);
                 }
-                add_lstm(blk + "_lstm", blk + "_dense", (F0 >> n) * 32);
+                if (is_ddb()) add_ddb(blk + "_ddb", 32);
+                else add_lstm(blk + "_lstm", blk + "_dense", (F0 >> n) * 32);
                 for (int k = 1; k <= n; ++k) {
                     const bool last = (k == n);
                     add_conv(blk + "_spconv" + std::to_string(k), 32, 32, last ? 128 : 64, 2, 3, 1, 1,
@@ -538,7 +570,8 @@ struct Engine {
                 add_mlp(blk + "_fa");
                 if (side == 0) add_conv(DOWN_NAMES[i], 64, 0, 64, 1, 3, 0, 2, EPI_BIAS);
             }
-        add_lstm("lstm", "dense", 256);
+        if (is_ddb()) add_ddb("ddb", 64);
+        else add_lstm("lstm", "dense", 256);
 
         // framing tables (tf.signal.hann_window periodic; inverse_stft_window_fn(256); interpreter_proposed.py:21-26)
         std::vector<float> tw(512), win(512), wins(512), inv(512);
@@ -924,6 +957,51 @@ struct Engine {
         return o;
     }
 
+    // Dilated dense block bottleneck (models/nunet_tls.py:383-410), offline plans only.
+    Ten* op_ddb(Plan& P, const std::string& role, Ten* x, const std::string& out_name, bool persistent) {
+        if (P.streaming) fail(NUNET_EINVAL, "the dilated-dense variant has no streaming plan yet (offline only)");
+        const DdbLayer L = ddbs.at(role);
+        const int C = x->C, h = C / 2, F = x->F;
+        if (C != L.C) fail(NUNET_EINVAL, "plan: %s width", role.c_str());
+        Ten* mid[7];
+        for (int i = 0; i < 7; ++i) mid[i] = P.make("", F, h, false, false);
+        Ten* o = P.make(out_name, F, C, persistent);
+        o->sh = P.sh16;
+        Plan* pp = &P;
+        const bool sh = P.sh16;
+        P.ops.push_back([=](Engine& E, const Run& r) {
+            E.cur_op = out_name;
+            const long long frames = (long long)r.B * r.T;
+            const long long nin = frames * F * h, nout = frames * F * C;
+            float* m[7];
+            for (int i = 0; i < 7; ++i) m[i] = pp->cur(mid[i], 0);
+            const void* xin = pp->cur(x, r.parity);
+            if (sh) ddb_in_kernel<true><<<(int)((nin + 127) / 128), 128, 0, r.st>>>(xin, E.pool.at(L.w_in), E.pool.at(L.b_in), E.pool.at(L.a_in), m[0], frames, r.T, F, C);
+            else ddb_in_kernel<false><<<(int)((nin + 127) / 128), 128, 0, r.st>>>(xin, E.pool.at(L.w_in), E.pool.at(L.b_in), E.pool.at(L.a_in), m[0], frames, r.T, F, C);
+            E.check_launch("ddb_in", frames * 4.0 * F * (C + h));
+            DdbOuts src{};
+            for (int i = 0; i < 6; ++i) src.o[i] = m[i];
+            for (int k = 1; k <= 6; ++k) {
+                const int d = 1 << (k - 1);
+                const int blocks = (int)((nin + 127) / 128);
+                if (h == 16)
+                    ddb_layer_kernel<16><<<blocks, 128, 0, r.st>>>(src, k, d, E.pool.at(L.w0[k - 1]), E.pool.at(L.b0[k - 1]), E.pool.at(L.w1[k - 1]),
+                                                                  E.pool.at(L.b1[k - 1]), E.pool.at(L.gamma[k - 1]), E.pool.at(L.beta[k - 1]),
+                                                                  E.pool.at(L.alpha[k - 1]), m[k], frames, r.T, F);
+                else
+                    ddb_layer_kernel<32><<<blocks, 128, 0, r.st>>>(src, k, d, E.pool.at(L.w0[k - 1]), E.pool.at(L.b0[k - 1]), E.pool.at(L.w1[k - 1]),
+                                                                  E.pool.at(L.b1[k - 1]), E.pool.at(L.gamma[k - 1]), E.pool.at(L.beta[k - 1]),
+                                                                  E.pool.at(L.alpha[k - 1]), m[k], frames, r.T, F);
+                E.check_launch("ddb_layer", frames * 4.0 * F * h * (k + 1));
+            }
+            void* yo = pp->cur(o, r.parity);
+            if (sh) ddb_out_kernel<true><<<(int)((nout + 127) / 128), 128, 0, r.st>>>(m[6], E.pool.at(L.w_out), E.pool.at(L.b_out), E.pool.at(L.a_out), yo, frames, r.T, F, C);
+            else ddb_out_kernel<false><<<(int)((nout + 127) / 128), 128, 0, r.st>>>(m[6], E.pool.at(L.w_out), E.pool.at(L.b_out), E.pool.at(L.a_out), yo, frames, r.T, F, C);
+            E.check_launch("ddb_out", frames * 4.0 * F * (C + h));
+        });
+        return o;
+    }
+
     // One nested sub-U-Net (MSFE): returns ctfa(de_1) + en_in; fills des_out[k-1] = de_k (k = 1..n, F0 >> (k-1) bins)
     Ten* op_msfe(Plan& P, const std::string& blk, int n, Ten* en_in, Ten* const* skips, Ten** des_out,
                  bool des_persistent, bool out_persistent, bool out_eo) {
@@ -943,7 +1021,7 @@ struct Engine {
             cur = op_conv(P, blk + "_conv" + std::to_string(k), cur, sk, blk + "_conv" + std::to_string(k), false);
             ens.push_back(cur);
         }
-        Ten* bb = op_lstm(P, blk + "_lstm", cur, blk + "_bb", blk, false);
+        Ten* bb = is_ddb() ? op_ddb(P, blk + "_ddb", cur, blk + "_bb", false) : op_lstm(P, blk + "_lstm", cur, blk + "_bb", blk, false);
         cur = bb;
         std::vector<Ten*> des;
         for (int k = 1; k <= n; ++k) {
@@ -1044,7 +1122,7 @@ struct Engine {
             enc_out[i] = x;
             if (recycle) P.release(m);
         }
-        Ten* y = op_lstm(P, "lstm", x, "bb_main", "state", true);
+        Ten* y = is_ddb() ? op_ddb(P, "ddb", x, "bb_main", true) : op_lstm(P, "lstm", x, "bb_main", "state", true);
         for (int i = 0; i < 6; ++i) {
             const std::string blk = DEC_NAMES[i];
             const int j = 5 - i;

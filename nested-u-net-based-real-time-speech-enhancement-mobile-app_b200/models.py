@@ -14,15 +14,18 @@ import numpy as np
 import torch
 
 from .engine import NunetEngine, num_frames
-from .weights import expected_lstm_shapes, lstm_weights_from_h5, pack_blob, validate
+from ._lib import NUNET_VARIANT_DDB, NUNET_VARIANT_LSTM
+from .weights import (VARIANT_DDB, VARIANT_LSTM, ddb_weights_from_tflite, expected_ddb_shapes, expected_lstm_shapes,
+                      lstm_weights_from_h5, lstm_weights_from_tflite, pack_blob, validate)
 
 
 class _Model:
     """What `build_model()` returns: waveform [B, N] -> enhanced waveform [B, (T-1)*256+512]."""
 
-    def __init__(self, opt, ctfa_mode: str = "causal_avg32"):
+    def __init__(self, opt, ctfa_mode: str = "causal_avg32", variant: int = NUNET_VARIANT_LSTM):
         self.opt = opt
         self.ctfa_mode = ctfa_mode
+        self.variant = variant
         self._weights: Optional[Dict[str, np.ndarray]] = None
         self._blob: Optional[bytes] = None
         self._engine: Optional[NunetEngine] = None
@@ -30,10 +33,20 @@ class _Model:
 
     # Keras API subset ---------------------------------------------------------------------------
     def load_weights(self, path_or_set):
-        """`.h5` path written by Keras save_weights (train_interface.py:99-100) or a role-named weight set."""
-        w = lstm_weights_from_h5(path_or_set) if isinstance(path_or_set, str) else dict(path_or_set)
-        validate(w, expected_lstm_shapes())
-        self._weights, self._blob, self._engine = w, pack_blob(w), None
+        """`.h5` path written by Keras save_weights (train_interface.py:99-100), a shipped `.tflite` (int8 tensors
+        are dequantised; the only weight source of the dilated-dense variant), or a role-named weight set."""
+        ddb = self.variant == NUNET_VARIANT_DDB
+        if isinstance(path_or_set, str):
+            if path_or_set.endswith(".tflite"):
+                w = ddb_weights_from_tflite(path_or_set) if ddb else lstm_weights_from_tflite(path_or_set)
+            elif ddb:
+                raise ValueError("the dilated-dense variant ships no .h5 checkpoint: load nutls.tflite or a weight set")
+            else:
+                w = lstm_weights_from_h5(path_or_set)
+        else:
+            w = dict(path_or_set)
+        validate(w, expected_ddb_shapes() if ddb else expected_lstm_shapes())
+        self._weights, self._blob, self._engine = w, pack_blob(w, VARIANT_DDB if ddb else VARIANT_LSTM), None
         return self
 
     def _get_engine(self, frames: int) -> NunetEngine:
@@ -42,7 +55,8 @@ class _Model:
         if self._engine is None or self._engine.max_frames < frames:
             if self._engine is not None:
                 self._engine.close()
-            self._engine = NunetEngine(self._blob, max_frames=frames, device=self.device, ctfa_mode=self.ctfa_mode)
+            self._engine = NunetEngine(self._blob, max_frames=frames, device=self.device, ctfa_mode=self.ctfa_mode,
+                                       variant=self.variant)
         return self._engine
 
     def __call__(self, x, training: bool = False):
@@ -106,3 +120,24 @@ class NUTLS_LSTM:
 
     def tflite_model(self) -> _FrameModel:
         return _FrameModel(self.opt)
+
+
+class NUTLS:
+    """The NUNet-TLS baseline with dilated-dense bottlenecks (`dnn_model/models/nunet_tls.py:13`, build_model :1007).
+    Offline surface only: the one-frame stateful form of this variant (`tflite_model`, converter_nunet_tls.py) is not
+    built yet."""
+
+    def __init__(self, opt):
+        self.in_ch, self.mid_ch, self.out_ch = 1, 32, 64
+        self.win_len, self.fft_len, self.hop_len = opt.win_len, opt.fft_len, opt.hop_len
+        if (self.win_len, self.fft_len, self.hop_len) != (512, 512, 256):
+            raise ValueError("the kernels are specialised for win_len = fft_len = 512, hop_len = 256")
+        self.opt = opt
+        self.model = None
+
+    def build_model(self) -> _Model:
+        self.model = _Model(self.opt, variant=NUNET_VARIANT_DDB)
+        return self.model
+
+    def tflite_model(self):
+        raise NotImplementedError("streaming form of the dilated-dense variant: next round (DESIGN.md 7)")

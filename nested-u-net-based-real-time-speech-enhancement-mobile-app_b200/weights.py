@@ -165,6 +165,107 @@ def lstm_weights_from_tflite(path: str) -> Dict[str, np.ndarray]:
     return out
 
 
+DDB_DILATIONS = (1, 2, 4, 8, 16, 32)
+
+
+def ddb_roles():
+    """(role prefix, channels C) of the 13 dilated-dense bottlenecks in network order (nunet_tls.py:383-410, 678-700)."""
+    out = [(f"{name}_ddb", 32) for name, _f0, _n in ENC_BLOCKS]
+    out.append(("ddb", 64))
+    out += [(f"{name}_ddb", 32) for name, _f0, _n in DEC_BLOCKS]
+    return out
+
+
+def ddb_weights_from_tflite(path: str) -> Dict[str, np.ndarray]:
+    """Role-named float32 weight set of the NUNet-TLS baseline (dilated-dense bottleneck) from the shipped
+    `nutls.tflite`, its ONLY weight source (SURVEY 3A.5).  Per DDB layer k: `kernel0/bias0` = the grouped dilated
+    (2,3) conv in Keras layout (2,3,k,h), `kernel1/bias1` = the 1x1 conv (h,h), `gamma/beta/alpha`.
+    The grouped kernels are anonymous tensors (`Conv2DNN`) in the flatbuffer and are attributed through the graph:
+    by the conv's own bias tensor (dilation 1) or by the bias ADD that follows BATCH_TO_SPACE_ND (dilation >= 2,
+    lowered to SPACE_TO_BATCH / CONV / BATCH_TO_SPACE).  The three MSFE4 encoder down-sampling convs share one weight
+    tensor in the shipped file (SURVEY 3A.4 #5) and are aliased here."""
+    g, by_role = _tflite_role_tensors(path)
+    out: Dict[str, np.ndarray] = {}
+    ddb_re = re.compile(r"^(.*ddb)_(\d)$")
+    for role, tensors in by_role.items():
+        if role.startswith("Conv2D"):
+            continue
+        m = ddb_re.match(role)
+        if not m:
+            _unit_from_tflite("out_conv" if role == "conv2d" else role, tensors, out)
+            continue
+        biases = []
+        for t in tensors:
+            first = t.name.split(";")[0]
+            sub = first.split("/")[1]
+            leaf = first.split("/", 2)[2] if first.count("/") >= 2 else ""
+            w = t.dequantized()
+            if sub.startswith("layer_normalization"):
+                if leaf == "batchnorm/mul/ReadVariableOp":
+                    out[f"{role}/gamma"] = w
+                elif leaf == "batchnorm/ReadVariableOp":
+                    out[f"{role}/beta"] = w
+            elif sub.startswith("p_re_lu"):
+                out[f"{role}/alpha"] = w.reshape(1)
+            elif sub.startswith("conv2d") and w.ndim == 4:
+                out[f"{role}/kernel1"] = np.ascontiguousarray(w.transpose(1, 2, 3, 0)).reshape(w.shape[3], w.shape[0])
+            elif sub.startswith("conv2d") and leaf.startswith("BiasAdd"):
+                biases.append((_suffix(sub), w))
+        biases.sort(key=lambda b: b[0])
+        out[f"{role}/bias0"], out[f"{role}/bias1"] = biases[0][1], biases[1][1]
+    # anonymous grouped-conv kernels
+    producer = {}
+    consumers: Dict[int, list] = {}
+    for op in g.operators:
+        for o in op.outputs:
+            producer[o] = op
+        for i in op.inputs:
+            if i >= 0:
+                consumers.setdefault(i, []).append(op)
+
+    def role_of(tname: str):
+        first = tname.split(";")[0]
+        return first.split("/")[0] if "/" in first and ddb_re.match(first.split("/")[0]) else None
+
+    for op in g.operators:
+        if op.op != "CONV_2D" or not g.tensors[op.inputs[1]].name.startswith("Conv2D"):
+            continue
+        role = role_of(g.tensors[op.inputs[2]].name) if len(op.inputs) > 2 else None
+        if role is None:      # dilated lowering: CONV_2D -> BATCH_TO_SPACE_ND -> ADD(bias)
+            nxt = consumers[op.outputs[0]][0]
+            assert nxt.op == "BATCH_TO_SPACE_ND", nxt.op
+            add = consumers[nxt.outputs[0]][0]
+            assert add.op == "ADD", add.op
+            for i in add.inputs:
+                role = role or role_of(g.tensors[i].name)
+        assert role is not None, g.tensors[op.inputs[1]].name
+        w = g.tensors[op.inputs[1]].dequantized()                 # [h, 2, 3, k]
+        out[f"{role}/kernel0"] = np.ascontiguousarray(w.transpose(1, 2, 3, 0))
+    for alias in ("msfe4_down_sampling2", "msfe4_down_sampling3"):
+        for var in ("kernel", "bias"):
+            out.setdefault(f"{alias}/{var}", out[f"msfe4_down_sampling/{var}"].copy())
+    for un in UP_NAMES:
+        out.setdefault(f"{un}/bias", np.zeros(128, np.float32))
+    return out
+
+
+def expected_ddb_shapes() -> Dict[str, tuple]:
+    """Shape table of the dilated-dense variant: the LSTM table with every LSTM + Dense replaced by a DDB."""
+    s = {k: v for k, v in expected_lstm_shapes().items()
+         if not (k.split("/")[0].endswith("_lstm") or k.split("/")[0].endswith("_dense") or k.split("/")[0] in ("lstm", "dense"))}
+    for role, C in ddb_roles():
+        h = C // 2
+        s[f"{role}_in/kernel"], s[f"{role}_in/bias"], s[f"{role}_in/alpha"] = (2, 3, C, h), (h,), (1,)
+        for k in range(1, 7):
+            r = f"{role}_{k}"
+            s[f"{r}/kernel0"], s[f"{r}/bias0"] = (2, 3, k, h), (h,)
+            s[f"{r}/kernel1"], s[f"{r}/bias1"] = (h, h), (h,)
+            s[f"{r}/gamma"] = s[f"{r}/beta"] = (h,)
+            s[f"{r}/alpha"] = (1,)
+        s[f"{role}_out/kernel"], s[f"{role}_out/bias"], s[f"{role}_out/alpha"] = (2, 3, h, C), (C,), (1,)
+    return s
+
+
 def expected_lstm_shapes() -> Dict[str, tuple]:
     """Shape table of the LSTM variant, derived from the topology (SURVEY §3A.3), used to validate a set."""
     s: Dict[str, tuple] = {}
@@ -278,6 +379,32 @@ def ensure_default_blob() -> str:
     return DEFAULT_BLOB
 
 
+DDB_BLOB = os.path.join(_HERE, "data", "nutls_ddb.nunetw")
+REFERENCE_TFLITE_DDB = "/root/reference/dnn_model/tflite/nutls.tflite"
+
+
+def ensure_ddb_blob() -> str:
+    """The dilated-dense variant's only weights: the shipped nutls.tflite, dequantised."""
+    if not os.path.exists(DDB_BLOB) and os.path.exists(REFERENCE_TFLITE_DDB):
+        w = ddb_weights_from_tflite(REFERENCE_TFLITE_DDB)
+        validate(w, expected_ddb_shapes())
+        os.makedirs(os.path.dirname(DDB_BLOB), exist_ok=True)
+        with open(DDB_BLOB, "wb") as f:
+            f.write(pack_blob(w, VARIANT_DDB))
+    return DDB_BLOB
+
+
+def load_ddb_weights() -> Dict[str, np.ndarray]:
+    path = ensure_ddb_blob()
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"{path} missing and {REFERENCE_TFLITE_DDB} not available")
+    with open(path, "rb") as f:
+        w, variant = unpack_blob(f.read())
+    if variant != VARIANT_DDB:
+        raise ValueError("not a dilated-dense blob")
+    return w
+
+
 def ensure_tflite_lstm_blob() -> str:
     if not os.path.exists(TFLITE_LSTM_BLOB) and os.path.exists(REFERENCE_TFLITE_LSTM):
         w = lstm_weights_from_tflite(REFERENCE_TFLITE_LSTM)
@@ -306,6 +433,25 @@ def load_default_weights() -> Dict[str, np.ndarray]:
     if variant != VARIANT_LSTM:
         raise ValueError("default blob is not the LSTM variant")
     return w
+
+
+def random_ddb_weights(seed: int = 0) -> Dict[str, np.ndarray]:
+    """Seeded random-init weight set of the dilated-dense variant (plumbing / parity tests with O(1) activations)."""
+    rng = np.random.default_rng(seed)
+    out: Dict[str, np.ndarray] = {}
+    for k, shp in expected_ddb_shapes().items():
+        var = k.split("/")[1]
+        if var == "gamma":
+            a = 1.0 + 0.1 * rng.standard_normal(shp)
+        elif var == "alpha":
+            a = np.full(shp, 0.25)
+        elif var.startswith("bias") or var == "beta":
+            a = 0.05 * rng.standard_normal(shp)
+        else:
+            fan_in = int(np.prod(shp[:-1]))
+            a = rng.standard_normal(shp) / np.sqrt(max(fan_in, 1))
+        out[k] = a.astype(np.float32)
+    return out
 
 
 def random_lstm_weights(seed: int = 0) -> Dict[str, np.ndarray]:

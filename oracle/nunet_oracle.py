@@ -57,10 +57,14 @@ def state_prefixes(block: str) -> Tuple[str, str, str]:
 class Oracle:
     """Float restatement of NUNet-TLS-LSTM.  `weights` is a role-named set (nunet_b200/weights.py)."""
 
-    def __init__(self, weights: Dict[str, np.ndarray], dtype=torch.float32, ctfa_mode: str = "causal_avg32"):
-        assert ctfa_mode in ("causal_avg32", "frame_div32")
+    def __init__(self, weights: Dict[str, np.ndarray], dtype=torch.float32, ctfa_mode: str = "causal_avg32",
+                 variant: str = "lstm"):
+        """variant 'lstm' = NUNet-TLS-LSTM (models/proposed.py); 'ddb' = the NUNet-TLS baseline whose bottlenecks
+        are dilated dense blocks (models/nunet_tls.py) -- everything else is shared."""
+        assert ctfa_mode in ("causal_avg32", "frame_div32") and variant in ("lstm", "ddb")
         self.dt = dtype
         self.ctfa_mode = ctfa_mode
+        self.variant = variant
         self.w = {k: torch.from_numpy(np.asarray(v, dtype=np.float32)).to(dtype) for k, v in weights.items()}
 
     # ------------------------------------------------------------------ Keras layer semantics
@@ -155,6 +159,41 @@ class Oracle:
         y = hs @ self.w[f"{dense_name}/kernel"] + self.w[f"{dense_name}/bias"]
         return y.reshape(b, t, f, c), (h, cst)
 
+    def ddb(self, x, role: str, st_in=None, st_out=None):
+        """Dilated dense block (nunet_tls.py:190-272; use :383-410, main :678-700; one-frame form with explicit
+        history converter_nunet_tls.py:373-411).  `in`: causal (2,3) conv C -> C/2 + PReLU; layers k = 1..6 with
+        dilation d = 2^(k-1) in time AND frequency: grouped conv (groups = C/2, group g reads channels [g k, (g+1) k)
+        of cat[out_{k-1}, .., out_0]) -> 1x1 conv -> LayerNorm -> PReLU; `out`: causal (2,3) conv C/2 -> C + PReLU.
+        History: `in`/`out` keep their last input row, layer k the last d rows of its concatenated input."""
+        def prev(sfx):
+            return None if st_in is None else st_in[f"{role}_prev{sfx}"]
+
+        def keep(sfx, full, rows):
+            if st_out is not None:
+                st_out[f"{role}_cur{sfx}"] = full[:, -rows:]
+
+        def prelu(y, name):
+            return torch.where(y >= 0, y, self.w[f"{name}/alpha"] * y)
+
+        full = self._with_history(x, prev("_in"))
+        keep("_in", full, 1)
+        outs = [prelu(self._conv2d(F.pad(full, (0, 0, 1, 1)), f"{role}_in"), f"{role}_in")]
+        for k in range(1, 7):
+            d = 2 ** (k - 1)
+            name = f"{role}_{k}"
+            inp = torch.cat(outs[::-1], dim=3)                       # newest first: out_{k-1}, ..., out_0
+            p = prev(str(k))
+            full = F.pad(inp, (0, 0, 0, 0, d, 0)) if p is None else torch.cat([p, inp], dim=1)
+            keep(str(k), full, d)
+            z = F.pad(full, (0, 0, d, d)).permute(0, 3, 1, 2)        # ZeroPadding2D((d,0),(d,d)) / freq part
+            kg = self.w[f"{name}/kernel0"].permute(3, 2, 0, 1)       # (2,3,k,h) -> (h, k, 2, 3)
+            z = F.conv2d(z, kg, self.w[f"{name}/bias0"], dilation=(d, d), groups=kg.shape[0]).permute(0, 2, 3, 1)
+            z = z @ self.w[f"{name}/kernel1"] + self.w[f"{name}/bias1"]
+            outs.append(self._ln_prelu(z, name))
+        full = self._with_history(outs[6], prev("_out"))
+        keep("_out", full, 1)
+        return prelu(self._conv2d(F.pad(full, (0, 0, 1, 1)), f"{role}_out"), f"{role}_out")
+
     # ------------------------------------------------------------------ the network
     def _msfe(self, block: str, depth: int, en_in, skips2, st_in, st_out, ctfa_hist, taps=None):
         """One nested sub-U-Net.  `skips2` = the paired encoder block's spconv outputs
@@ -177,10 +216,13 @@ class Oracle:
             ens.append(cur)
             if taps is not None:
                 taps[f"{block}_conv{k}"] = cur
-        lstm_state = None if st_in is None else (st_in[f"{pl}_h"], st_in[f"{pl}_c"])
-        bb, (h, c) = self.lstm_dense(cur, f"{block}_lstm", f"{block}_dense", lstm_state)
-        if st_out is not None:
-            st_out[f"{pl}_h"], st_out[f"{pl}_c"] = h, c
+        if self.variant == "ddb":
+            bb = self.ddb(cur, f"{block}_ddb", st_in, st_out)
+        else:
+            lstm_state = None if st_in is None else (st_in[f"{pl}_h"], st_in[f"{pl}_c"])
+            bb, (h, c) = self.lstm_dense(cur, f"{block}_lstm", f"{block}_dense", lstm_state)
+            if st_out is not None:
+                st_out[f"{pl}_h"], st_out[f"{pl}_c"] = h, c
         if taps is not None:
             taps[f"{block}_bb"] = bb
         des = []
@@ -218,10 +260,13 @@ class Oracle:
             enc_out.append(x)
             if taps is not None:
                 taps[dn] = x
-        main_state = None if st_in is None else (st_in["state_h"], st_in["state_c"])
-        y, (h, c) = self.lstm_dense(x, "lstm", "dense", main_state)
-        if st_out is not None:
-            st_out["state_h"], st_out["state_c"] = h, c
+        if self.variant == "ddb":
+            y = self.ddb(x, "ddb", st_in, st_out)
+        else:
+            main_state = None if st_in is None else (st_in["state_h"], st_in["state_c"])
+            y, (h, c) = self.lstm_dense(x, "lstm", "dense", main_state)
+            if st_out is not None:
+                st_out["state_h"], st_out["state_c"] = h, c
         if taps is not None:
             taps["bb_main"] = y
         for i, ((block, depth), un) in enumerate(zip(DEC_BLOCKS, UP_NAMES)):

@@ -41,3 +41,18 @@ def tflite_weights():
 @pytest.fixture(scope="session")
 def golden_o2():
     return dict(np.load(os.path.join(GOLDEN, "o2_lstm.npz")))
+
+
+@pytest.fixture(scope="session")
+def ddb_weights():
+    """Weights of the reference's shipped nutls.tflite (dilated-dense baseline), dequantised, role-named."""
+    from nunet_b200.weights import load_ddb_weights
+    try:
+        return load_ddb_weights()
+    except FileNotFoundError as e:
+        pytest.skip(str(e))
+
+
+@pytest.fixture(scope="session")
+def golden_o2_ddb():
+    return dict(np.load(os.path.join(GOLDEN, "o2_ddb.npz")))

@@ -7,6 +7,7 @@ Fixtures:
   input_specs_lstm.json    TensorSpec names/shapes of converter_proposed.py:26-187
   wav_excerpt.npz          first 1.5 s (int16) of data/40hc020i_0.wav (noisy) and data/40hc020i.wav (clean)
   o2_lstm.npz              outputs of the reference's shipped nutls_lstm.tflite executed by oracle/tflite_graph.py
+  o2_ddb.npz               the same for nutls.tflite (dilated-dense baseline)
   oracle_io_lstm.npz       oracle outputs with the reference .h5 weights on seeded inputs (regression pin +
                            expected values for the GPU parity tests)
 """
@@ -86,6 +87,22 @@ def graph_oracle_io():
     np.savez_compressed(f"{HERE}/o2_lstm.npz", mag=mag, model_out=np.stack(outs), **{f"state_{k}": v for k, v in keep.items()})
 
 
+def graph_oracle_ddb_io():
+    """o2_ddb.npz: the shipped nutls.tflite (dilated-dense baseline) executed frame by frame on 72 frames (covers the
+    32-frame history of the deepest dilation)."""
+    from oracle.nunet_oracle import Oracle, min_max_norm
+    from oracle.tflite_graph import TFLiteGraph, stream_frames
+    from oracle.wavio import read_wav
+    noisy, _ = read_wav(f"{REF}/dnn_model/data/40hc020i_0.wav")
+    noisy = min_max_norm(noisy).astype(np.float32)
+    T = 72
+    seg = noisy[8000:8000 + 512 + 256 * (T - 1)]
+    mags, _ = Oracle({}, ctfa_mode="frame_div32").stft(torch.from_numpy(seg)[None])
+    mag = mags[0, :, 1:].numpy().astype(np.float32)
+    est = stream_frames(TFLiteGraph(f"{REF}/dnn_model/tflite/nutls.tflite"), mag)
+    np.savez_compressed(f"{HERE}/o2_ddb.npz", mag=mag, model_out=est)
+
+
 def oracle_io():
     from nunet_b200.synth import synth_clips
     from nunet_b200.weights import lstm_weights_from_h5
@@ -108,4 +125,5 @@ if __name__ == "__main__":
     wav_excerpt()
     oracle_io()
     graph_oracle_io()
+    graph_oracle_ddb_io()
     print("fixtures written to", HERE)

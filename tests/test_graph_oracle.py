@@ -82,3 +82,45 @@ def test_graph_executor_matches_committed_fixture(golden_o2):
     g = TFLiteGraph(f"{REF_TFLITE}/nutls_lstm.tflite")
     est = stream_frames(g, golden_o2["mag"][:6])
     assert np.abs(est - golden_o2["model_out"][:6]).max() <= 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------
+# dilated-dense baseline (models/nunet_tls.py, shipped nutls.tflite)
+def test_ddb_restatement_equals_shipped_graph(ddb_weights, golden_o2_ddb):
+    """Group / concat channel order, time taps t-d & t, frequency taps f-d, f, f+d, history = last d rows, and the
+    shared down-sampling weight of the shipped file (SURVEY 3A.4 #5): 72 frames cover the d = 32 layer."""
+    from oracle.nunet_oracle import Oracle
+    o = Oracle(ddb_weights, ctfa_mode="frame_div32", variant="ddb")
+    mag = torch.from_numpy(golden_o2_ddb["mag"])
+    with torch.no_grad():
+        est = o.net(mag[None, :, :, None]).squeeze().numpy()
+    ref = golden_o2_ddb["model_out"]
+    assert np.abs(ref).max() > 1.0
+    assert np.abs(est - ref).max() <= 1e-4, np.abs(est - ref).max()
+
+
+def test_ddb_streaming_restatement_equals_offline(ddb_weights, golden_o2_ddb):
+    """One-frame form with the reference's history tensors (`*_ddb_prevK`, converter_nunet_tls.py:373-411)."""
+    from oracle.nunet_oracle import Oracle
+    o = Oracle(ddb_weights, ctfa_mode="frame_div32", variant="ddb")
+    mag = torch.from_numpy(golden_o2_ddb["mag"][:40])
+    with torch.no_grad():
+        ref = o.net(mag[None, :, :, None]).squeeze()
+        st, outs = None, []
+        for t in range(mag.shape[0]):
+            nxt = {}
+            if st is None:      # zero history of the right shapes: run once with st_out only
+                o.net(mag[None, t:t + 1, :, None], st_out=nxt)
+                st = {k.replace("_cur", "_prev"): torch.zeros_like(v) for k, v in nxt.items()}
+                nxt = {}
+            outs.append(o.net(mag[None, t:t + 1, :, None], st_in=st, st_out=nxt).reshape(256))
+            st = {k.replace("_cur", "_prev"): v for k, v in nxt.items()}
+    assert (torch.stack(outs) - ref).abs().max() <= 1e-4
+
+
+def test_ddb_weight_set_structure(ddb_weights):
+    from nunet_b200.weights import expected_ddb_shapes, validate
+    validate(ddb_weights, expected_ddb_shapes())
+    assert sum(v.size for v in ddb_weights.values()) == 2830462
+    k = ddb_weights["msfe4_down_sampling/kernel"]
+    assert (ddb_weights["msfe4_down_sampling2/kernel"] == k).all() and (ddb_weights["msfe4_down_sampling3/kernel"] == k).all()
