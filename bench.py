@@ -82,14 +82,14 @@ class ClockSampler:
                 "power_w_max": max(float(r[2]) for r in rows), "reasons": reasons}
 
 
-def cpu_reference_leg(weights, n_samples: int, clips: int, steps: int, warmup: int):
+def cpu_reference_leg(weights, n_samples: int, clips: int, steps: int, warmup: int, variant: str = "lstm"):
     """The oracle's offline forward (the reference's `model(noisy)`, test_interface.py:58) on host cores."""
     import torch
     from nunet_b200.synth import synth_clips
     from oracle.nunet_oracle import Oracle          # allowed here: the CPU baseline / reference arm
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    o = Oracle(weights, ctfa_mode="causal_avg32")
+    o = Oracle(weights, ctfa_mode="causal_avg32", variant=variant)
     wav = torch.from_numpy(synth_clips(clips, n_samples))
     T = 1 + (n_samples - 512) // 256
     with torch.no_grad():
@@ -202,6 +202,8 @@ def main():
                     help="offline = BASELINE configs[1] (default, the headline); streaming = configs[2]: --streams "
                          "concurrent streams, one 256-sample hop per stream per step, carried conv/LSTM history")
     ap.add_argument("--streams", type=int, default=1024)
+    ap.add_argument("--variant", default="lstm", choices=["lstm", "ddb"],
+                    help="lstm = NUNet-TLS-LSTM (headline); ddb = configs[3], the dilated-dense baseline, offline only")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -214,13 +216,27 @@ def main():
               "clips_per_gpu": args.batch, "frames_per_clip": T, "weights": None,
               "l2_policy": "working set (inputs 65 MB + >30 GB activations per pass) far exceeds the 126 MB L2"}
 
-    from nunet_b200.weights import load_default_weights, pack_blob, random_lstm_weights
-    try:
-        weights = load_default_weights()
-        config["weights"] = "trained nutls_lstm.h5 (reference checkpoint)"
-    except FileNotFoundError:
-        weights = random_lstm_weights(0)
-        config["weights"] = "RANDOM-INIT (trained checkpoint blob missing on this box)"
+    from nunet_b200.weights import (load_ddb_weights, load_default_weights, pack_blob, random_ddb_weights,
+                                    random_lstm_weights)
+    ddb = args.variant == "ddb"
+    if ddb:
+        if args.config != "offline" or args.impl != "ours":
+            raise SystemExit("--variant ddb: offline config, our arm only")
+        config["workload"] = (f"configs[3]: offline batch={args.batch} x {args.seconds:g} s @16 kHz clips per GPU, NUNet-TLS "
+                              f"dilated-dense bottleneck variant, T={T} frames/clip, ctfa causal_avg32")
+        try:
+            weights = load_ddb_weights()
+            config["weights"] = "shipped nutls.tflite, int8 tensors dequantised (the variant's only checkpoint)"
+        except FileNotFoundError:
+            weights = random_ddb_weights(0)
+            config["weights"] = "RANDOM-INIT (nutls.tflite blob missing on this box)"
+    else:
+        try:
+            weights = load_default_weights()
+            config["weights"] = "trained nutls_lstm.h5 (reference checkpoint)"
+        except FileNotFoundError:
+            weights = random_lstm_weights(0)
+            config["weights"] = "RANDOM-INIT (trained checkpoint blob missing on this box)"
 
     # ------------------------------------------------------------------ reference arm: CPU oracle only
     if args.impl == "reference":
@@ -248,7 +264,7 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    blob = pack_blob(weights)
+    blob = pack_blob(weights, 1 if ddb else 0)
     if world > 1:
         from nunet_b200.sharding import broadcast_blob
         dist.init_process_group("nccl", device_id=dev)
@@ -256,7 +272,9 @@ def main():
         blob = broadcast_blob(blob if rank == 0 else None, src=0, device=dev)
 
     B = args.batch
-    eng = NunetEngine(blob, max_frames=B * T, device=local_rank, ctfa_mode="causal_avg32")
+    eng = NunetEngine(blob, max_frames=B * T, device=local_rank, ctfa_mode="causal_avg32", variant=1 if ddb else 0)
+    b_alg = 4.358e6 if ddb else B_ALG_BYTES_PER_FRAME
+    flop = 149.0e6 if ddb else FLOP_PER_FRAME
     # synthetic clips: a pool of 32 distinct clips tiled to the batch (generation is host-side numpy)
     pool = synth_clips(min(B, 32), n_samples, first_clip=1000 * rank)
     wav_h = torch.from_numpy(np.tile(pool, ((B + len(pool) - 1) // len(pool), 1))[:B]).contiguous().pin_memory()
@@ -332,14 +350,14 @@ def main():
             u = tj["units"].get(top_name)
             if u is not None and tj["frames"] == B * T:
                 traffic = u["dram_read_bytes"] + u["dram_write_bytes"]
-        path_gbs = value / world * B_ALG_BYTES_PER_FRAME / 1e9
+        path_gbs = value / world * b_alg / 1e9
         roofline = {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes": top_bytes,
                     "peak_source": peak_src,
                     "kernel_ms": top_ms, "kernel_share_of_step": top_ms / total_ms,
                     "path": {"achieved": path_gbs, "frac": path_gbs / peak,
-                             "b_alg_bytes_per_frame": B_ALG_BYTES_PER_FRAME,
-                             "fp32_tflops": value / world * FLOP_PER_FRAME / 1e12},
+                             "b_alg_bytes_per_frame": b_alg,
+                             "fp32_tflops": value / world * flop / 1e12},
                     "top5": sorted(((n, round(v[0], 3)) for n, v in by_kernel.items()), key=lambda x: -x[1])[:5]}
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         with open(os.path.join(ROOT, "gpurun_out", "bench_kernel_profile.json"), "w") as f:
@@ -347,7 +365,7 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
-        val, sec, cores, sample = cpu_reference_leg(weights, n_samples, 2, 2, 1)
+        val, sec, cores, sample = cpu_reference_leg(weights, n_samples, 2, 2, 1, variant=args.variant)
         cpu_baseline = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
 
     if rank == 0:
