@@ -33,31 +33,53 @@ __device__ __forceinline__ void act_store(void* base, long long frame, int F, in
     }
 }
 
-// `in`: x [frame][F][C] -> out0 [frame][F][h], causal (2,3) conv + bias + PReLU.  One thread per (pixel, co).
+// Where "the same unit, `back` steps earlier" lives.  Offline: unit = frame b*T+t of a dense [frame][F][h] tensor, the
+// earlier value is `back` frames before (zero when that leaves the clip).  Streaming (converter_nunet_tls.py:373-411:
+// layer k keeps the last d rows of its input): unit = stream, every intermediate tensor is a per-stream ring of
+// DDB_RING steps [stream][DDB_RING][F][h], `slot` = current step; rings start as zeros = the reference's zero history.
+constexpr int DDB_RING = 64;   // > the deepest look-back (32) so that writing step s never clobbers step s - 32
+struct DdbGeom {
+    int streaming;
+    int slot;      // streaming: current step & (DDB_RING - 1)
+    int T;         // offline: frames per clip
+};
+__device__ __forceinline__ bool ddb_back_ok(const DdbGeom& g, long long unit, int back) {
+    return g.streaming || (int)(unit % g.T) - back >= 0;
+}
+// element offset (in floats) of (unit, back, bin ff) in an intermediate tensor with F bins x H channels
+__device__ __forceinline__ long long ddb_off(const DdbGeom& g, long long unit, int back, int F, int H, int ff) {
+    if (g.streaming) return ((unit * DDB_RING + ((g.slot - back) & (DDB_RING - 1))) * F + ff) * (long long)H;
+    return ((unit - back) * F + ff) * (long long)H;
+}
+
+// `in`: x [unit][F][C] -> out0, causal (2,3) conv + bias + PReLU.  One thread per (pixel, co).  The previous row of x is
+// the same tensor one frame earlier (offline) or the other parity's buffer `x_prev` (streaming).
 template <bool SH>
-__global__ void __launch_bounds__(128) ddb_in_kernel(const void* __restrict__ x, const float* __restrict__ w /*[2][3][C][h]*/,
-                                                    const float* __restrict__ b, const float* __restrict__ alpha,
-                                                    float* __restrict__ out0, long long frames, int T, int F, int C) {
+__global__ void __launch_bounds__(128) ddb_in_kernel(const void* __restrict__ x, const void* __restrict__ x_prev,
+                                                    const float* __restrict__ w /*[2][3][C][h]*/, const float* __restrict__ b,
+                                                    const float* __restrict__ alpha, float* __restrict__ out0, long long units,
+                                                    DdbGeom g, int F, int C) {
     const int h = C >> 1;
     const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long pix = gt / h;
     const int co = (int)(gt - pix * h);
-    if (pix >= frames * F) return;
-    const long long frame = pix / F;
-    const int f = (int)(pix - frame * F);
-    const int t = (int)(frame % T);
+    if (pix >= units * F) return;
+    const long long unit = pix / F;
+    const int f = (int)(pix - unit * F);
     float acc = __ldg(b + co);
     for (int kt = 0; kt < 2; ++kt) {
-        if (t - 1 + kt < 0) continue;
+        if (kt == 0 && !ddb_back_ok(g, unit, 1)) continue;
+        const void* src = (kt == 0 && g.streaming) ? x_prev : x;
+        const long long u = (kt == 0 && !g.streaming) ? unit - 1 : unit;
         for (int kf = 0; kf < 3; ++kf) {
             const int ff = f - 1 + kf;
             if (ff < 0 || ff >= F) continue;
             const float* wk = w + (size_t)((kt * 3 + kf) * C) * h + co;
-            for (int ci = 0; ci < C; ++ci) acc = fmaf(act_load<SH>(x, frame - 1 + kt, F, C, ff, ci), __ldg(wk + (size_t)ci * h), acc);
+            for (int ci = 0; ci < C; ++ci) acc = fmaf(act_load<SH>(src, u, F, C, ff, ci), __ldg(wk + (size_t)ci * h), acc);
         }
     }
     const float a = __ldg(alpha);
-    out0[pix * h + co] = acc >= 0.f ? acc : a * acc;
+    out0[ddb_off(g, unit, 0, F, h, f) + co] = acc >= 0.f ? acc : a * acc;
 }
 
 struct DdbOuts {
@@ -70,23 +92,22 @@ __global__ void __launch_bounds__(128) ddb_layer_kernel(DdbOuts src, int k, int 
                                                        const float* __restrict__ b0, const float* __restrict__ w1 /*[H][H]*/,
                                                        const float* __restrict__ b1, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, const float* __restrict__ alpha,
-                                                       float* __restrict__ outk, long long frames, int T, int F) {
+                                                       float* __restrict__ outk, int outk_is_ring, long long units, DdbGeom geo, int F) {
     const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long pix = gt / H;
     const int g = (int)(gt - pix * H);
-    const bool ok = pix < frames * F;
-    if (!ok) pix = frames * F - 1;            // keep the lane alive for the shuffles
-    const long long frame = pix / F;
-    const int f = (int)(pix - frame * F);
-    const int t = (int)(frame % T);
+    const bool ok = pix < units * F;
+    if (!ok) pix = units * F - 1;            // keep the lane alive for the shuffles
+    const long long unit = pix / F;
+    const int f = (int)(pix - unit * F);
     float z = __ldg(b0 + g);
     for (int kt = 0; kt < 2; ++kt) {
         const int back = d * (1 - kt);
-        if (t - back < 0) continue;
+        if (!ddb_back_ok(geo, unit, back)) continue;
         for (int kf = 0; kf < 3; ++kf) {
             const int ff = f + (kf - 1) * d;
             if (ff < 0 || ff >= F) continue;
-            const long long p2 = ((frame - back) * F + ff) * H;
+            const long long p2 = ddb_off(geo, unit, back, F, H, ff);
             for (int j = 0; j < k; ++j) {
                 const int c = g * k + j;                 // channel of cat[out_{k-1}, .., out_0]
                 const int m = c / H, ch = c - m * H;
@@ -108,29 +129,33 @@ __global__ void __launch_bounds__(128) ddb_layer_kernel(DdbOuts src, int k, int 
     const float inv = rsqrtf(q * (1.0f / H) + LN_EPS) * __ldg(gamma + g);
     const float r = fmaf(y, inv, __ldg(beta + g) - mean * inv);
     const float a = __ldg(alpha);
-    if (ok) outk[pix * H + g] = r >= 0.f ? r : a * r;
+    // out_1..out_5 are rings when streaming; out_6 is a plain (ping-ponged) tensor
+    const long long oo = outk_is_ring ? ddb_off(geo, unit, 0, F, H, f) : pix * H;
+    if (ok) outk[oo + g] = r >= 0.f ? r : a * r;
 }
 
 // `out`: out6 [frame][F][h] -> y [frame][F][C] (activation tensor), causal (2,3) conv + bias + PReLU.
 template <bool SH>
-__global__ void __launch_bounds__(128) ddb_out_kernel(const float* __restrict__ o6, const float* __restrict__ w /*[2][3][h][C]*/,
-                                                     const float* __restrict__ b, const float* __restrict__ alpha,
-                                                     void* __restrict__ y, long long frames, int T, int F, int C) {
+__global__ void __launch_bounds__(128) ddb_out_kernel(const float* __restrict__ o6, const float* __restrict__ o6_prev,
+                                                     const float* __restrict__ w /*[2][3][h][C]*/, const float* __restrict__ b,
+                                                     const float* __restrict__ alpha, void* __restrict__ y, long long units,
+                                                     DdbGeom g, int F, int C) {
     const int h = C >> 1;
     const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long pix = gt / C;
     const int co = (int)(gt - pix * C);
-    if (pix >= frames * F) return;
+    if (pix >= units * F) return;
     const long long frame = pix / F;
     const int f = (int)(pix - frame * F);
-    const int t = (int)(frame % T);
     float acc = __ldg(b + co);
     for (int kt = 0; kt < 2; ++kt) {
-        if (t - 1 + kt < 0) continue;
+        if (kt == 0 && !ddb_back_ok(g, frame, 1)) continue;
+        const float* base = (kt == 0 && g.streaming) ? o6_prev : o6;
+        const long long u = (kt == 0 && !g.streaming) ? frame - 1 : frame;
         for (int kf = 0; kf < 3; ++kf) {
             const int ff = f - 1 + kf;
             if (ff < 0 || ff >= F) continue;
-            const float* src = o6 + ((frame - 1 + kt) * F + ff) * h;
+            const float* src = base + (u * F + ff) * h;
             const float* wk = w + (size_t)((kt * 3 + kf) * h) * C + co;
             for (int ci = 0; ci < h; ++ci) acc = fmaf(__ldg(src + ci), __ldg(wk + (size_t)ci * C), acc);
         }

@@ -248,6 +248,7 @@ struct Run {   // arguments of one forward / step call
     float* est_out = nullptr;        // [B*T][est_stride], written at +est_off
     int est_stride = 256, est_off = 0;
     int ring_pos = 0;
+    int step = 0;                    // streaming: absolute step counter (DDB rings)
 };
 
 struct Engine;
@@ -272,6 +273,10 @@ struct Plan {
         Ten* a = nullptr;
         Ten* b = nullptr;
         bool is_lstm = false;    // a = the [21] h or c vector
+        // DDB layer k (converter_nunet_tls.py:373-411): the last d rows of cat[out_{k-1}, .., out_0], gathered from
+        // the per-stream rings of out_0 .. out_{k-1}
+        int ddb_k = 0, ddb_d = 0;
+        Ten* rings[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     };
     std::vector<StateRef> states;
     std::vector<Ten*> rings;
@@ -957,47 +962,69 @@ struct Engine {
         return o;
     }
 
-    // Dilated dense block bottleneck (models/nunet_tls.py:383-410), offline plans only.
+    // Dilated dense block bottleneck (models/nunet_tls.py:383-410; one-frame form converter_nunet_tls.py:373-411).
+    // Offline: seven dense fp32 intermediates [frame][F][h].  Streaming: out_0..out_5 are per-stream rings of DDB_RING
+    // steps (layer k looks d = 2^(k-1) steps back), out_6 and the block input are ping-ponged like every activation.
     Ten* op_ddb(Plan& P, const std::string& role, Ten* x, const std::string& out_name, bool persistent) {
-        if (P.streaming) fail(NUNET_EINVAL, "the dilated-dense variant has no streaming plan yet (offline only)");
         const DdbLayer L = ddbs.at(role);
         const int C = x->C, h = C / 2, F = x->F;
         if (C != L.C) fail(NUNET_EINVAL, "plan: %s width", role.c_str());
         Ten* mid[7];
-        for (int i = 0; i < 7; ++i) mid[i] = P.make("", F, h, false, false);
+        for (int i = 0; i < 6; ++i) mid[i] = P.streaming ? P.make("", F * DDB_RING, h, true, false) : P.make("", F, h, false, false);
+        mid[6] = P.make("", F, h, P.streaming, true);
         Ten* o = P.make(out_name, F, C, persistent);
         o->sh = P.sh16;
+        if (P.streaming) {
+            Plan::StateRef si, so;
+            si.name = role + "_in"; si.a = x;
+            P.states.push_back(si);
+            for (int k = 1; k <= 6; ++k) {
+                Plan::StateRef s;
+                s.name = role + "_" + std::to_string(k);
+                s.ddb_k = k; s.ddb_d = 1 << (k - 1);
+                for (int j = 0; j < k; ++j) s.rings[j] = mid[j];
+                s.a = mid[0];
+                P.states.push_back(s);
+            }
+            so.name = role + "_out"; so.a = mid[6];
+            P.states.push_back(so);
+        }
         Plan* pp = &P;
         const bool sh = P.sh16;
         P.ops.push_back([=](Engine& E, const Run& r) {
             E.cur_op = out_name;
-            const long long frames = (long long)r.B * r.T;
-            const long long nin = frames * F * h, nout = frames * F * C;
+            const long long units = (long long)r.B * r.T;
+            const long long nin = units * F * h, nout = units * F * C;
+            DdbGeom g{pp->streaming ? 1 : 0, r.step & (DDB_RING - 1), r.T};
             float* m[7];
-            for (int i = 0; i < 7; ++i) m[i] = pp->cur(mid[i], 0);
+            for (int i = 0; i < 6; ++i) m[i] = pp->cur(mid[i], 0);
+            m[6] = pp->cur(mid[6], r.parity);
             const void* xin = pp->cur(x, r.parity);
-            if (sh) ddb_in_kernel<true><<<(int)((nin + 127) / 128), 128, 0, r.st>>>(xin, E.pool.at(L.w_in), E.pool.at(L.b_in), E.pool.at(L.a_in), m[0], frames, r.T, F, C);
-            else ddb_in_kernel<false><<<(int)((nin + 127) / 128), 128, 0, r.st>>>(xin, E.pool.at(L.w_in), E.pool.at(L.b_in), E.pool.at(L.a_in), m[0], frames, r.T, F, C);
-            E.check_launch("ddb_in", frames * 4.0 * F * (C + h));
+            const void* xprev = pp->prev(x, r.parity);
+            if (sh) ddb_in_kernel<true><<<(int)((nin + 127) / 128), 128, 0, r.st>>>(xin, xprev, E.pool.at(L.w_in), E.pool.at(L.b_in), E.pool.at(L.a_in), m[0], units, g, F, C);
+            else ddb_in_kernel<false><<<(int)((nin + 127) / 128), 128, 0, r.st>>>(xin, xprev, E.pool.at(L.w_in), E.pool.at(L.b_in), E.pool.at(L.a_in), m[0], units, g, F, C);
+            E.check_launch("ddb_in", units * 4.0 * F * (C + h));
             DdbOuts src{};
             for (int i = 0; i < 6; ++i) src.o[i] = m[i];
             for (int k = 1; k <= 6; ++k) {
                 const int d = 1 << (k - 1);
                 const int blocks = (int)((nin + 127) / 128);
+                const int ring_out = (pp->streaming && k < 6) ? 1 : 0;
                 if (h == 16)
                     ddb_layer_kernel<16><<<blocks, 128, 0, r.st>>>(src, k, d, E.pool.at(L.w0[k - 1]), E.pool.at(L.b0[k - 1]), E.pool.at(L.w1[k - 1]),
                                                                   E.pool.at(L.b1[k - 1]), E.pool.at(L.gamma[k - 1]), E.pool.at(L.beta[k - 1]),
-                                                                  E.pool.at(L.alpha[k - 1]), m[k], frames, r.T, F);
+                                                                  E.pool.at(L.alpha[k - 1]), m[k], ring_out, units, g, F);
                 else
                     ddb_layer_kernel<32><<<blocks, 128, 0, r.st>>>(src, k, d, E.pool.at(L.w0[k - 1]), E.pool.at(L.b0[k - 1]), E.pool.at(L.w1[k - 1]),
                                                                   E.pool.at(L.b1[k - 1]), E.pool.at(L.gamma[k - 1]), E.pool.at(L.beta[k - 1]),
-                                                                  E.pool.at(L.alpha[k - 1]), m[k], frames, r.T, F);
-                E.check_launch("ddb_layer", frames * 4.0 * F * h * (k + 1));
+                                                                  E.pool.at(L.alpha[k - 1]), m[k], ring_out, units, g, F);
+                E.check_launch("ddb_layer", units * 4.0 * F * h * (k + 1));
             }
             void* yo = pp->cur(o, r.parity);
-            if (sh) ddb_out_kernel<true><<<(int)((nout + 127) / 128), 128, 0, r.st>>>(m[6], E.pool.at(L.w_out), E.pool.at(L.b_out), E.pool.at(L.a_out), yo, frames, r.T, F, C);
-            else ddb_out_kernel<false><<<(int)((nout + 127) / 128), 128, 0, r.st>>>(m[6], E.pool.at(L.w_out), E.pool.at(L.b_out), E.pool.at(L.a_out), yo, frames, r.T, F, C);
-            E.check_launch("ddb_out", frames * 4.0 * F * (C + h));
+            const float* o6prev = pp->prev(mid[6], r.parity);
+            if (sh) ddb_out_kernel<true><<<(int)((nout + 127) / 128), 128, 0, r.st>>>(m[6], o6prev, E.pool.at(L.w_out), E.pool.at(L.b_out), E.pool.at(L.a_out), yo, units, g, F, C);
+            else ddb_out_kernel<false><<<(int)((nout + 127) / 128), 128, 0, r.st>>>(m[6], o6prev, E.pool.at(L.w_out), E.pool.at(L.b_out), E.pool.at(L.a_out), yo, units, g, F, C);
+            E.check_launch("ddb_out", units * 4.0 * F * (C + h));
         });
         return o;
     }
@@ -1228,6 +1255,7 @@ struct Engine {
         r.B = S; r.T = 1; r.st = st; r.mag_in = mag; r.est_out = out; r.est_stride = 256; r.est_off = 0;
         r.parity = stream_parity ^ 1;
         r.ring_pos = stream_steps & (CTFA_WINDOW - 1);
+        r.step = stream_steps;
         run_plan(stream, r);
         stream_parity ^= 1;
         ++stream_steps;
@@ -1280,6 +1308,7 @@ struct Engine {
     }
     int state_numel(const Plan::StateRef& s) const {
         if (s.is_lstm) return LSTM_UNITS;
+        if (s.ddb_k) return s.ddb_d * (s.a->F / DDB_RING) * s.a->C * s.ddb_k;
         return s.a->F * (s.a->C + (s.b ? s.b->C : 0));
     }
     void state_xfer(int sid, const std::string& name, float* buf, bool to_host) {
@@ -1294,6 +1323,19 @@ struct Engine {
         };
         if (s->is_lstm) {
             xfer(stream.cur(s->a, 0) + (size_t)sid * LSTM_UNITS, buf, LSTM_UNITS, LSTM_UNITS, 1);
+            return;
+        }
+        if (s->ddb_k) {
+            // reference tensor [d rows (oldest first)][F][k*h], channels = cat[out_{k-1}, .., out_0]; row r is step
+            // last - (d - 1 - r), the last finished step sits in slot (stream_steps - 1)
+            const int k = s->ddb_k, d = s->ddb_d, h = s->a->C, F = s->a->F / DDB_RING;
+            for (int r = 0; r < d; ++r) {
+                const int slot = (stream_steps - 1 - (d - 1 - r)) & (DDB_RING - 1);
+                for (int m = 0; m < k; ++m) {
+                    float* ring = stream.cur(s->rings[k - 1 - m], 0) + ((size_t)sid * DDB_RING + slot) * F * h;
+                    xfer(ring, buf + (size_t)r * F * k * h + (size_t)m * h, h, (size_t)k * h, F);
+                }
+            }
             return;
         }
         const int CA = s->a->C, CB = s->b ? s->b->C : 0, F = s->a->F;

@@ -21,14 +21,21 @@ import numpy as np
 import torch
 
 from .engine import NunetEngine
-from .state_table import STATE_SHAPES
-from .weights import expected_lstm_shapes, lstm_weights_from_h5, pack_blob, validate
+from ._lib import NUNET_VARIANT_DDB, NUNET_VARIANT_LSTM
+from .state_table import STATE_SHAPES, STATE_SHAPES_DDB
+from .weights import (VARIANT_DDB, ddb_weights_from_tflite, expected_ddb_shapes, expected_lstm_shapes, lstm_weights_from_h5,
+                      lstm_weights_from_tflite, pack_blob, validate)
 
 SIGNATURE_KEYS = ("nutls_lstm_sm", "nutls_lstm")   # shipped file / converter script
+SIGNATURE_KEYS_DDB = ("nutls",)                      # interpreter_nunet_tls.py:543-549
 
 
 def _engine_to_ref(name: str, which: str) -> str:
-    """engine state name 'msfe4_ee2_3' -> 'msfe4_ee2_prev3' / 'msfe4_ee2_cur3'; LSTM names are unchanged."""
+    """engine state name 'msfe4_ee2_3' -> 'msfe4_ee2_prev3' / 'msfe4_ee2_cur3', 'msfe3_en_ddb_in' ->
+    'msfe3_en_ddb_prev_in'; LSTM names are unchanged."""
+    m = re.fullmatch(r"(.*ddb)_(in|out)", name)
+    if m:
+        return f"{m.group(1)}_{which}_{m.group(2)}"
     m = re.fullmatch(r"(.+)_(\d+)", name)
     if m and not name.endswith(("_h", "_c")):
         return f"{m.group(1)}_{which}{m.group(2)}"
@@ -36,7 +43,9 @@ def _engine_to_ref(name: str, which: str) -> str:
 
 
 class SignatureRunner:
-    def __init__(self, engine: NunetEngine):
+    def __init__(self, engine: NunetEngine, shapes: Optional[Dict[str, tuple]] = None):
+        STATE_SHAPES = shapes if shapes is not None else globals()["STATE_SHAPES"]
+        self._shapes = STATE_SHAPES
         self._e = engine
         self._names: List[str] = engine.state_names()
         self._last_out: Dict[str, np.ndarray] = {}
@@ -75,46 +84,57 @@ class SignatureRunner:
         out: Dict[str, np.ndarray] = {}
         for n in self._names:
             ref = _engine_to_ref(n, "cur")
-            out[ref] = e.state_export(0, n).reshape(STATE_SHAPES[ref])
+            out[ref] = e.state_export(0, n).reshape(self._shapes[ref])
         out["model_out"] = y.cpu().numpy().reshape(1, 1, 256, 1)
         self._last_out = out
         return out
 
 
 class Interpreter:
-    """`tf.lite.Interpreter` stand-in for the NUNet-TLS-LSTM graph.  `model_path` may be the reference `.h5`
-    float checkpoint (or a role-named weight set via `weights=`)."""
+    """`tf.lite.Interpreter` stand-in.  `model_path` may be the reference `.h5` float checkpoint or a shipped
+    `.tflite` (int8 tensors dequantised); `variant="ddb"` (or a path ending in `nutls.tflite`) selects the dilated-dense
+    baseline with signature key 'nutls' (interpreter_nunet_tls.py:543-549); a role-named weight set goes in `weights=`."""
 
     def __init__(self, model_path: Optional[str] = None, weights: Optional[dict] = None, device: int = 0,
-                 num_threads: Optional[int] = None):
+                 num_threads: Optional[int] = None, variant: Optional[str] = None):
+        if variant is None:
+            variant = "ddb" if (model_path or "").endswith("nutls.tflite") else "lstm"
+        self._ddb = variant == "ddb"
         if weights is None:
             if model_path is None:
                 raise ValueError("model_path or weights required")
             if model_path.endswith(".tflite"):
-                from .tflite_reader import lstm_weights_from_tflite
-                weights = lstm_weights_from_tflite(model_path)
+                weights = ddb_weights_from_tflite(model_path) if self._ddb else lstm_weights_from_tflite(model_path)
+            elif self._ddb:
+                raise ValueError("the dilated-dense variant ships no .h5 checkpoint")
             else:
                 weights = lstm_weights_from_h5(model_path)
-        validate(weights, expected_lstm_shapes())
-        self._blob = pack_blob(weights)
+        validate(weights, expected_ddb_shapes() if self._ddb else expected_lstm_shapes())
+        self._blob = pack_blob(weights, VARIANT_DDB if self._ddb else 0)
         self._device = device
         self._engine: Optional[NunetEngine] = None
+        self._keys = SIGNATURE_KEYS_DDB if self._ddb else SIGNATURE_KEYS
 
     def allocate_tensors(self):
         if self._engine is None:
-            self._engine = NunetEngine(self._blob, max_streams=1, device=self._device, dc_mode="edge")
+            self._engine = NunetEngine(self._blob, max_streams=1, device=self._device, dc_mode="edge",
+                                       variant=NUNET_VARIANT_DDB if self._ddb else NUNET_VARIANT_LSTM)
             self._engine.stream_reset()
+
+    def _runner(self) -> SignatureRunner:
+        return SignatureRunner(self._engine, STATE_SHAPES_DDB if self._ddb else STATE_SHAPES)
 
     def get_signature_list(self) -> dict:
         self.allocate_tensors()
-        r = SignatureRunner(self._engine)
-        return {SIGNATURE_KEYS[0]: {"inputs": r.input_names(), "outputs": r.output_names()}}
+        r = self._runner()
+        return {self._keys[0]: {"inputs": r.input_names(), "outputs": r.output_names()}}
 
-    def get_signature_runner(self, key: str = SIGNATURE_KEYS[0]) -> SignatureRunner:
-        if key not in SIGNATURE_KEYS:
-            raise ValueError(f"unknown signature key {key!r}; available: {SIGNATURE_KEYS[0]}")
+    def get_signature_runner(self, key: Optional[str] = None) -> SignatureRunner:
+        key = self._keys[0] if key is None else key
+        if key not in self._keys:
+            raise ValueError(f"unknown signature key {key!r}; available: {self._keys[0]}")
         self.allocate_tensors()
-        return SignatureRunner(self._engine)
+        return self._runner()
 
     @property
     def engine(self) -> NunetEngine:

@@ -85,16 +85,24 @@ class _Model:
 class _FrameModel:
     """What `tflite_model()` returns: [1,1,256,1] -> [1,1,256,1] with zero history (proposed.py:639-1151)."""
 
-    def __init__(self, opt):
+    def __init__(self, opt, variant: int = NUNET_VARIANT_LSTM):
         self.opt = opt
         self._blob = None
+        self.variant = variant
         self.device = int(getattr(opt, "device", 0))
 
     def load_weights(self, path_or_set):
-        w = lstm_weights_from_h5(path_or_set) if isinstance(path_or_set, str) else dict(path_or_set)
-        validate(w, expected_lstm_shapes())
-        self._blob = pack_blob(w)
-        self._engine = NunetEngine(self._blob, max_streams=1, device=self.device)
+        ddb = self.variant == NUNET_VARIANT_DDB
+        if isinstance(path_or_set, str):
+            if path_or_set.endswith(".tflite"):
+                w = ddb_weights_from_tflite(path_or_set) if ddb else lstm_weights_from_tflite(path_or_set)
+            else:
+                w = lstm_weights_from_h5(path_or_set)
+        else:
+            w = dict(path_or_set)
+        validate(w, expected_ddb_shapes() if ddb else expected_lstm_shapes())
+        self._blob = pack_blob(w, VARIANT_DDB if ddb else VARIANT_LSTM)
+        self._engine = NunetEngine(self._blob, max_streams=1, device=self.device, variant=self.variant)
         return self
 
     def __call__(self, x, training: bool = False):
@@ -123,9 +131,8 @@ class NUTLS_LSTM:
 
 
 class NUTLS:
-    """The NUNet-TLS baseline with dilated-dense bottlenecks (`dnn_model/models/nunet_tls.py:13`, build_model :1007).
-    Offline surface only: the one-frame stateful form of this variant (`tflite_model`, converter_nunet_tls.py) is not
-    built yet."""
+    """The NUNet-TLS baseline with dilated-dense bottlenecks (`dnn_model/models/nunet_tls.py:13`, build_model :1007,
+    tflite_model :1019)."""
 
     def __init__(self, opt):
         self.in_ch, self.mid_ch, self.out_ch = 1, 32, 64
@@ -139,5 +146,5 @@ class NUTLS:
         self.model = _Model(self.opt, variant=NUNET_VARIANT_DDB)
         return self.model
 
-    def tflite_model(self):
-        raise NotImplementedError("streaming form of the dilated-dense variant: next round (DESIGN.md 7)")
+    def tflite_model(self) -> _FrameModel:
+        return _FrameModel(self.opt, variant=NUNET_VARIANT_DDB)

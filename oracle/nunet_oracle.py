@@ -299,7 +299,7 @@ class Oracle:
 
     # ------------------------------------------------------------------ streaming surface
     def zero_state(self, batch: int = 1) -> Dict[str, torch.Tensor]:
-        return {k: torch.zeros((batch,) + s[1:], dtype=self.dt) for k, s in state_shapes().items()}
+        return {k: torch.zeros((batch,) + s[1:], dtype=self.dt) for k, s in state_shapes(self.variant).items()}
 
     def frame_step(self, inputs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         """The signature function `nutls_lstm` (converter_proposed.py:188-867): `input` + 104 `*_prevK`
@@ -383,10 +383,18 @@ def inverse_stft(spec: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def state_shapes() -> Dict[str, tuple]:
+def state_shapes(variant: str = "lstm") -> Dict[str, tuple]:
     """name -> shape of every `*_curK`/LSTM state (batch 1), derived from the topology; the test suite checks
-    it against the tables in interpreter_proposed.py:36-198."""
+    it against the tables in interpreter_proposed.py:36-198.  variant 'ddb': the 208 tensors of
+    interpreter_nunet_tls.py:36-289 (LSTM states replaced by the dilated-dense histories)."""
     s: Dict[str, tuple] = {}
+
+    def ddb(role, fb, c):
+        s[f"{role}_cur_in"] = (1, 1, fb, c)
+        for k in range(1, 7):
+            s[f"{role}_cur{k}"] = (1, 1 << (k - 1), fb, k * c // 2)
+        s[f"{role}_cur_out"] = (1, 1, fb, c // 2)
+
     f0s = {"msfe6": 256, "msfe5": 128, "msfe4_en": 64, "msfe4_en2": 32, "msfe4_en3": 16, "msfe3": 8,
            "msfe4_de": 16, "msfe4_de2": 32, "msfe4_de3": 64}
     for blocks, side in ((ENC_BLOCKS, "en"), (DEC_BLOCKS, "de")):
@@ -402,8 +410,14 @@ def state_shapes() -> Dict[str, tuple]:
                     cin = 128 if k == 1 else 64
                 s[f"{pc}_cur{k}"] = (1, 1, f, cin)
                 s[f"{ps}_cur{k}"] = (1, 1, (f0 >> depth) << (k - 1), 64)
-            s[f"{pl}_h"] = s[f"{pl}_c"] = (1, UNITS)
-    s["state_h"] = s["state_c"] = (1, UNITS)
+            if variant == "ddb":
+                ddb(f"{block}_ddb", f0 >> depth, 32)
+            else:
+                s[f"{pl}_h"] = s[f"{pl}_c"] = (1, UNITS)
+    if variant == "ddb":
+        ddb("ddb", 4, 64)
+    else:
+        s["state_h"] = s["state_c"] = (1, UNITS)
     return s
 
 

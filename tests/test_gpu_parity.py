@@ -331,5 +331,88 @@ def test_ddb_models_surface(ddb_weights, golden_o2_ddb):
     from nunet_b200.synth import synth_clips
     y = model(synth_clips(1, 512 + 256 * 9), training=False)
     assert y.shape == (1, 9 * 256 + 512) and np.isfinite(y).all()
-    with pytest.raises(NotImplementedError):
-        m.tflite_model()
+    fm = m.tflite_model().load_weights(ddb_weights)
+    out = fm(np.full((1, 1, 256, 1), 3.0, np.float32))
+    assert out.shape == (1, 1, 256, 1) and np.isfinite(out).all()
+
+
+def test_ddb_streaming_engine_matches_shipped_tflite_graph(ddb_weights, golden_o2_ddb):
+    """One-frame stateful form of the dilated-dense baseline (converter_nunet_tls.py:292-1526) vs the shipped
+    nutls.tflite executed frame by frame: 72 steps exercise the 32-step look-back of the deepest layer."""
+    from nunet_b200._lib import NUNET_VARIANT_DDB
+    from nunet_b200.weights import VARIANT_DDB, pack_blob
+    mag = golden_o2_ddb["mag"]
+    eng = _engine(pack_blob(ddb_weights, VARIANT_DDB), max_streams=2, ctfa_mode="frame_div32", variant=NUNET_VARIANT_DDB)
+    eng.stream_reset()
+    outs = []
+    for t in range(mag.shape[0]):
+        outs.append(eng.stream_step_mag(torch.from_numpy(np.stack([mag[t], mag[t]])).cuda()).cpu().numpy())
+    est = np.stack(outs)
+    ref = golden_o2_ddb["model_out"]
+    assert np.abs(est[:, 0] - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max()), np.abs(est[:, 0] - ref).max()
+    assert (est[:, 0] == est[:, 1]).all()
+
+
+def test_ddb_streaming_state_contract_random_weights():
+    """40 steps of S = 3 streams vs the oracle's one-frame graph with carried history; then every one of the 208
+    reference-named history tensors (interpreter_nunet_tls.py:36-289) is exported and compared, and a foreign history
+    is imported into one stream."""
+    from nunet_b200._lib import NUNET_VARIANT_DDB
+    from nunet_b200.interpreter import _engine_to_ref
+    from nunet_b200.synth import synth_clips
+    from nunet_b200.weights import VARIANT_DDB, pack_blob, random_ddb_weights
+    from oracle.nunet_oracle import Oracle
+    w = random_ddb_weights(5)
+    S, T = 3, 40
+    o = Oracle(w, ctfa_mode="frame_div32", variant="ddb")
+    mags, _ = o.stft(torch.from_numpy(synth_clips(S, 512 + 256 * (T - 1), first_clip=21)))
+    mag = mags[:, :, 1:].contiguous()
+    eng = _engine(pack_blob(w, VARIANT_DDB), max_streams=S, ctfa_mode="frame_div32", variant=NUNET_VARIANT_DDB)
+    eng.stream_reset()
+    state = o.zero_state(S)
+    worst, peak = 0.0, 0.0
+    for t in range(T):
+        feed = {"input": mag[:, t].reshape(S, 1, 256, 1)}
+        feed.update({k.replace("_cur", "_prev"): v for k, v in state.items()})
+        with torch.no_grad():
+            res = o.frame_step(feed)
+        ref = res.pop("model_out").reshape(S, 256)
+        state = res
+        out = eng.stream_step_mag(mag[:, t].contiguous().cuda()).cpu()
+        worst = max(worst, float((out - ref).abs().max()))
+        peak = max(peak, float(ref.abs().max()))
+    scale = max(1.0, peak / 48.0)
+    assert worst <= TOL_MAG * scale, (worst, peak)
+    names = eng.state_names()
+    assert len(names) == 208
+    for n in names:
+        ref = state[_engine_to_ref(n, "cur")]
+        for s_ in (0, S - 1):
+            got = eng.state_export(s_, n)
+            assert np.abs(got - ref[s_].reshape(-1).numpy()).max() <= TOL_MAG * scale, n
+    # import: stream 0's history into stream 1, then both must produce the same next frame
+    for n in names:
+        eng.state_import(1, n, eng.state_export(0, n))
+    nxt = torch.stack([mag[0, T - 1], mag[0, T - 1], mag[2, T - 1]]).contiguous().cuda()
+    y = eng.stream_step_mag(nxt).cpu().numpy()
+    assert np.abs(y[0] - y[1]).max() <= 1e-5 * scale
+
+
+def test_ddb_signature_runner_contract(ddb_weights, golden_o2_ddb):
+    """Interpreter(...).get_signature_runner('nutls') with 209 keyword tensors (interpreter_nunet_tls.py:543-549)."""
+    from nunet_b200.interpreter import Interpreter
+    it = Interpreter(weights=ddb_weights, variant="ddb")
+    it.allocate_tensors()
+    sig = it.get_signature_list()
+    assert list(sig) == ["nutls"] and len(sig["nutls"]["inputs"]) == 209 and len(sig["nutls"]["outputs"]) == 209
+    run = it.get_signature_runner("nutls")
+    with pytest.raises(ValueError):
+        it.get_signature_runner("nutls_lstm_sm")
+    from nunet_b200.state_table import STATE_SHAPES_DDB
+    state = {k.replace("_cur", "_prev"): np.zeros(s, np.float32) for k, s in STATE_SHAPES_DDB.items()}
+    mag = golden_o2_ddb["mag"]
+    for t in range(3):
+        out = run(input=mag[t].reshape(1, 1, 256, 1), **state)
+        assert np.abs(out["model_out"].reshape(256) - golden_o2_ddb["model_out"][t]).max() <= 1e-4 * 2
+        state = {k.replace("_cur", "_prev"): v for k, v in out.items() if k != "model_out"}
+    assert out["ddb_cur6"].shape == (1, 32, 4, 192) and out["msfe3_en_ddb_cur_in"].shape == (1, 1, 1, 32)
