@@ -180,7 +180,7 @@ def streaming_main(args, weights, rank, local_rank, world):
             "rtf_per_stream": (ms / args.steps * 1e-3) / 0.016, "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": S * 256 * 4, "d2h_bytes_per_step": S * 256 * 4},
             "gpu_launches": int(launches * args.steps),
-            "roofline": {"bound": "hbm", "kernel": "whole streaming step (FP32 SIMT units)", "achieved": gbs, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "whole streaming step (conv_tc3 units with the history row as a second source)", "achieved": gbs, "peak": peak,
                          "unit": "GB/s", "frac": gbs / peak, "traffic": None, "peak_source": peak_src,
                          "b_alg_bytes_per_frame": B_ALG_STREAM_BYTES_PER_FRAME},
             "cpu_baseline": None,

@@ -58,6 +58,7 @@ constexpr int T3_LD_THREADS = 32 * T3_LD_WARPS;
 constexpr int T3_THREADS = 32 * (T3_EPI_WARPS + T3_LD_WARPS + 1);
 constexpr int T3_MAXNB = 8;         // image ring depth
 constexpr int T3_TBL = 1024;        // slot table entries (nimg*slots <= 1024)
+constexpr int T3_PREV_FLAG = 1 << 30;   // slot-table entry: read the history tensor (streaming) instead of the source
 constexpr int T3_PAR_OFF = 256;     // bias / gamma / beta staged as floats: 3 x 64
 constexpr int T3_TBL_OFF = 1024;
 constexpr int T3_FIXED_BYTES = T3_TBL_OFF + T3_TBL * 4;
@@ -65,6 +66,8 @@ constexpr int T3_FIXED_BYTES = T3_TBL_OFF + T3_TBL * 4;
 struct Tc3Params {
     const uint8_t* src0;   // sh16 [frames][F_in][C0]
     const uint8_t* src1;   // sh16 [frames][F_in][C1] or null (C1 == C0 when present)
+    const uint8_t* prev0;  // streaming: history row of src0 per unit [B][F_in][C0] (the other parity's buffer), else null
+    const uint8_t* prev1;
     const uint8_t* wpk;    // [nhalf][phase][tap][chunk 2][hi N | lo N][8 halves]
     const float* bias;     // [nhalf * N], packed-column order
     const float* gamma;    // [PC] LayerNorm scale / offset by output channel
@@ -432,8 +435,11 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
                         const int db = small_div(ts, Tp, rcpTp);
                         const int t = ts - db * Tp - p.padrow;
                         const int fi = p.img_mul[img] * x + p.img_add[img];
-                        if (t >= 0 && fi >= 0 && fi < p.F_in)
-                            o = ((b0 + db) * p.T + t) * rs16 + (p.src_eo ? (fi & 1) * (p.F_in >> 1) + (fi >> 1) : fi);
+                        if (fi >= 0 && fi < p.F_in) {
+                            const int pos = p.src_eo ? (fi & 1) * (p.F_in >> 1) + (fi >> 1) : fi;
+                            if (t >= 0) o = ((b0 + db) * p.T + t) * rs16 + pos;
+                            else if (p.prev0 != nullptr) o = ((b0 + db) * rs16 + pos) | T3_PREV_FLAG;   // carried history row
+                        }
                     }
                     slot_tbl[e] = o;
                 }
@@ -462,7 +468,9 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
                 const bool first = c0 < p.C0;
                 const uint8_t* src = first ? p.src0 : p.src1;
                 const int cc = first ? c0 : c0 - p.C0;
-                const uint8_t* pb = src + (long long)((part * cpp0 + (cc >> 3) + chunk) * p.F_in) * 16;   // source plane
+                const long long plane_off = (long long)((part * cpp0 + (cc >> 3) + chunk) * p.F_in) * 16;
+                const uint8_t* pb = src + plane_off;                                                          // source plane
+                const uint8_t* pbp = (first ? p.prev0 : p.prev1) + plane_off;                                 // history plane
                 uint32_t d = dst0 + (uint32_t)buf * abuf_bytes;
                 const int* tb = slot_tbl + e0;
                 if (p.tma) {
@@ -483,7 +491,8 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
 #pragma unroll 4
                     for (int k = 0; k < nit; ++k) {
                         const int o = tb[k * ESTEP];
-                        cp_async16_s(d, pb + (long long)(o < 0 ? 0 : o) * 16, (o >= 0) ? 16 : 0);
+                        const uint8_t* base = (o & T3_PREV_FLAG) && o >= 0 ? pbp : pb;
+                        cp_async16_s(d, base + (long long)(o < 0 ? 0 : (o & (T3_PREV_FLAG - 1))) * 16, (o >= 0) ? 16 : 0);
                         d += ESTEP * 16;
                     }
                     // completion is signalled by the copy engine itself: a_full[buf] collects one arrival per loader

@@ -378,6 +378,7 @@ struct Engine {
     bool use_tc = true;     // NUNET_CONV=simt forces the FP32 SIMT units everywhere
     int tc3_fence_mode = 0;  // NUNET_TC3_FENCE
     int tc3_dbg = 0;         // NUNET_TC3_DBG (experiments)
+    bool stream_tc3 = true;  // NUNET_STREAM_CONV=simt keeps the streaming plan on the FP32 SIMT units
     int tc3_force_mt = 0;    // NUNET_TC3_MT (experiments)
     int tc3_tma = 0;         // NUNET_TC3_TMA=1 moves the row segments of stride-1 units (F_in >= 32) with bulk copies
     bool use_tc3 = true;    // NUNET_CONV=tc keeps the 3xTF32 kernel (fp32 activations) for the offline plan
@@ -746,9 +747,12 @@ struct Engine {
     }
 
     // Split-half tensor-core path (offline plans with sh16 tensors): every conv unit of the topology is eligible.
-    void launch_conv_tc3(const ConvLayer& L, const float* a_cur, const float* b_cur, float* out, int B, int T, int F_in,
-                         bool src_eo, bool out_eo, cudaStream_t st) {
+    void launch_conv_tc3(const ConvLayer& L, const float* a_cur, const float* b_cur, const float* a_prev, const float* b_prev,
+                         float* out, int B, int T, int F_in, bool src_eo, bool out_eo, cudaStream_t st) {
         Tc3Params p{};
+        if (a_prev && T != 1) fail(NUNET_EINVAL, "conv_tc3: a carried history row needs T = 1");
+        p.prev0 = (L.KT == 2) ? reinterpret_cast<const uint8_t*>(a_prev) : nullptr;
+        p.prev1 = (L.KT == 2) ? reinterpret_cast<const uint8_t*>(b_prev) : nullptr;
         p.src_eo = src_eo ? 1 : 0;
         p.out_eo = out_eo ? 1 : 0;
         p.src0 = reinterpret_cast<const uint8_t*>(a_cur);
@@ -795,7 +799,7 @@ struct Engine {
         }
         int maxoff = 0;
         for (int i = 0; i < p.ntaps; ++i) maxoff = std::max(maxoff, p.tap_off[i]);
-        p.tma = (tc3_tma && p.nimg == 1 && F_in >= 32 && !src_eo) ? 1 : 0;
+        p.tma = (tc3_tma && p.nimg == 1 && F_in >= 32 && !src_eo && !p.prev0) ? 1 : 0;
         p.nphase = (L.CA + L.CB) / T3_KCH;
         p.nhalf = L.nhalf3;
         p.w_half_bytes = p.nphase * p.ntaps * L.N3 * 64;
@@ -903,8 +907,8 @@ struct Engine {
         P.ops.push_back([=](Engine& E, const Run& r) {
             E.cur_op = out_name;
             if (pp->sh16) {
-                E.launch_conv_tc3(L, pp->cur(a, r.parity), b ? pp->cur(b, r.parity) : nullptr, pp->cur(o, r.parity), r.B, r.T,
-                                  F_in, src_eo, dst_eo, r.st);
+                E.launch_conv_tc3(L, pp->cur(a, r.parity), b ? pp->cur(b, r.parity) : nullptr, pp->prev(a, r.parity),
+                                  b ? pp->prev(b, r.parity) : nullptr, pp->cur(o, r.parity), r.B, r.T, F_in, src_eo, dst_eo, r.st);
                 return;
             }
             E.launch_conv(L, pp->cur(a, r.parity), pp->prev(a, r.parity), b ? pp->cur(b, r.parity) : nullptr,
@@ -1175,7 +1179,7 @@ struct Engine {
 
     void alloc_plan(Plan& P, int cap, bool streaming) {
         P.streaming = streaming;
-        P.sh16 = !streaming && use_tc && use_tc3;
+        P.sh16 = use_tc && use_tc3 && (!streaming || stream_tc3);
         P.cap = cap;
         build_plan(P);
         if (streaming) {
@@ -1339,8 +1343,35 @@ struct Engine {
             return;
         }
         const int CA = s->a->C, CB = s->b ? s->b->C : 0, F = s->a->F;
-        xfer(stream.cur(s->a, stream_parity) + (size_t)sid * s->a->numel(), buf, CA, CA + CB, F);
-        if (s->b) xfer(stream.cur(s->b, stream_parity) + (size_t)sid * s->b->numel(), buf + CA, CB, CA + CB, F);
+        auto one = [&](const Ten* tn, int coff) {
+            float* dev = stream.cur(tn, stream_parity) + (size_t)sid * tn->numel();
+            const int C = tn->C;
+            if (!tn->sh) {
+                xfer(dev, buf + coff, C, CA + CB, F);
+                return;
+            }
+            // sh16 frame row: planar [hi|lo][chunk][position][8 halves], positions natural or [even | odd]
+            std::vector<__half> row((size_t)2 * F * C);
+            if (!to_host) CUDA_OK(cudaMemcpy(row.data(), dev, (size_t)4 * F * C, cudaMemcpyDeviceToHost));   // keep nothing stale
+            if (to_host) CUDA_OK(cudaMemcpy(row.data(), dev, (size_t)4 * F * C, cudaMemcpyDeviceToHost));
+            for (int f = 0; f < F; ++f)
+                for (int c = 0; c < C; ++c) {
+                    const int pos = tn->eo ? (f & 1) * (F >> 1) + (f >> 1) : f;
+                    const size_t hi = ((size_t)(c >> 3) * F + pos) * 8 + (c & 7);
+                    const size_t lo = ((size_t)((C >> 3) + (c >> 3)) * F + pos) * 8 + (c & 7);
+                    float& v = buf[(size_t)f * (CA + CB) + coff + c];
+                    if (to_host) {
+                        v = __half2float(row[hi]) + __half2float(row[lo]);
+                    } else {
+                        const __half h = __float2half_rn(v);
+                        row[hi] = h;
+                        row[lo] = __float2half_rn(v - __half2float(h));
+                    }
+                }
+            if (!to_host) CUDA_OK(cudaMemcpy(dev, row.data(), (size_t)4 * F * C, cudaMemcpyHostToDevice));
+        };
+        one(s->a, 0);
+        if (s->b) one(s->b, CA);
     }
 };
 
@@ -1414,6 +1445,7 @@ int nunet_create(const nunet_config* cfg, const void* blob, size_t blob_bytes, n
         if (const char* c = getenv("NUNET_TC3_DBG")) E.tc3_dbg = atoi(c);
         if (const char* c = getenv("NUNET_TC3_TMA")) E.tc3_tma = atoi(c);
         if (const char* c = getenv("NUNET_TC3_MT")) E.tc3_force_mt = atoi(c);
+        if (const char* c = getenv("NUNET_STREAM_CONV")) E.stream_tc3 = strcmp(c, "simt") != 0;
         E.blob.parse(blob, blob_bytes);
         E.pack_params();
         E.pool.upload();
