@@ -52,34 +52,102 @@ __device__ __forceinline__ long long ddb_off(const DdbGeom& g, long long unit, i
     return ((unit - back) * F + ff) * (long long)H;
 }
 
-// `in`: x [unit][F][C] -> out0, causal (2,3) conv + bias + PReLU.  One thread per (pixel, co).  The previous row of x is
-// the same tensor one frame earlier (offline) or the other parity's buffer `x_prev` (streaming).
-template <bool SH>
-__global__ void __launch_bounds__(128) ddb_in_kernel(const void* __restrict__ x, const void* __restrict__ x_prev,
-                                                    const float* __restrict__ w /*[2][3][C][h]*/, const float* __restrict__ b,
-                                                    const float* __restrict__ alpha, float* __restrict__ out0, long long units,
-                                                    DdbGeom g, int F, int C) {
-    const int h = C >> 1;
-    const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long pix = gt / h;
-    const int co = (int)(gt - pix * h);
-    if (pix >= units * F) return;
-    const long long unit = pix / F;
-    const int f = (int)(pix - unit * F);
-    float acc = __ldg(b + co);
-    for (int kt = 0; kt < 2; ++kt) {
-        if (kt == 0 && !ddb_back_ok(g, unit, 1)) continue;
-        const void* src = (kt == 0 && g.streaming) ? x_prev : x;
-        const long long u = (kt == 0 && !g.streaming) ? unit - 1 : unit;
-        for (int kf = 0; kf < 3; ++kf) {
-            const int ff = f - 1 + kf;
-            if (ff < 0 || ff >= F) continue;
-            const float* wk = w + (size_t)((kt * 3 + kf) * C) * h + co;
-            for (int ci = 0; ci < C; ++ci) acc = fmaf(act_load<SH>(src, u, F, C, ff, ci), __ldg(wk + (size_t)ci * h), acc);
+// Causal (2,3) convolution + bias + PReLU at small F -- the `in` (C -> C/2, activation tensor -> intermediate) and
+// `out` (C/2 -> C, intermediate -> activation tensor) layers of the block.  Register-blocked FP32: a CTA of 128
+// threads owns 32 pixels x COUT channels; the weights [6][CIN][COUT] and the input patch [6][CIN][32 pixels] are staged
+// in shared memory once, then every thread accumulates 4 pixels x (COUT/16) channels with one 16-byte and one
+// 8/16-byte shared load per 4*(COUT/16) FMAs.  The previous row is the same tensor one unit earlier (offline) or the
+// other parity's buffer `x_prev` (streaming).  IN_ACT / OUT_ACT: the tensor on that side is a plan activation tensor
+// (sh16 planar when SH, else fp32 [unit][F][C]); otherwise it is an fp32 intermediate addressed through DdbGeom.
+template <int CIN, int COUT, bool IN_ACT, bool OUT_ACT, bool SH>
+__global__ void __launch_bounds__(128) ddb_conv23_kernel(const void* __restrict__ x, const void* __restrict__ x_prev,
+                                                        const float* __restrict__ w /*[2][3][CIN][COUT]*/,
+                                                        const float* __restrict__ b, const float* __restrict__ alpha,
+                                                        void* __restrict__ y, long long units, DdbGeom g, int F) {
+    constexpr int PX = 32, CPT = COUT / 16;          // pixels per CTA, channels per thread
+    extern __shared__ __align__(16) float sm[];
+    float* ws = sm;                                  // [6][CIN][COUT]
+    float* xs = sm + 6 * CIN * COUT;                 // [6][CIN][PX]
+    const long long pix0 = (long long)blockIdx.x * PX;
+    const long long npix = units * F;
+    for (int i = threadIdx.x; i < 6 * CIN * COUT / 4; i += 128)
+        reinterpret_cast<float4*>(ws)[i] = __ldg(reinterpret_cast<const float4*>(w) + i);
+    // input patch: item = (pixel, tap, 8-channel chunk)
+    for (int i = threadIdx.x; i < PX * 6 * (CIN / 8); i += 128) {
+        const int px = i % PX, rest = i / PX;
+        const int c8 = rest % (CIN / 8), tap = rest / (CIN / 8);
+        const int kt = tap / 3, kf = tap - kt * 3;
+        const long long pix = pix0 + px;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (pix < npix) {
+            const long long unit = pix / F;
+            const int f = (int)(pix - unit * F), ff = f - 1 + kf;
+            if (ff >= 0 && ff < F && (kt == 1 || ddb_back_ok(g, unit, 1))) {
+                if (IN_ACT) {
+                    const void* src = (kt == 0 && g.streaming) ? x_prev : x;
+                    const long long u = (kt == 0 && !g.streaming) ? unit - 1 : unit;
+                    if (SH) {
+                        sh16_load8(reinterpret_cast<const uint8_t*>(src) + u * ((long long)F * CIN * 4), F, CIN, ff, c8, v);
+                    } else {
+                        const float4* p4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + (u * F + ff) * (long long)CIN + c8 * 8);
+                        const float4 a0 = __ldg(p4), a1 = __ldg(p4 + 1);
+                        v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+                    }
+                } else {   // intermediate: plain tensor, previous row = other parity (streaming) or previous unit
+                    const float* src = reinterpret_cast<const float*>((kt == 0 && g.streaming) ? x_prev : x);
+                    const long long u = (kt == 0 && !g.streaming) ? unit - 1 : unit;
+                    const float4* p4 = reinterpret_cast<const float4*>(src + (u * F + ff) * (long long)CIN + c8 * 8);
+                    const float4 a0 = __ldg(p4), a1 = __ldg(p4 + 1);
+                    v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+                }
+            }
         }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) xs[(tap * CIN + c8 * 8 + e) * PX + px] = v[e];
+    }
+    __syncthreads();
+    const int cg = threadIdx.x & 15, pg = threadIdx.x >> 4;     // channels cg*CPT.., pixels pg*4..
+    float acc[4][CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+        const float bv = __ldg(b + cg * CPT + j);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i][j] = bv;
+    }
+#pragma unroll 4
+    for (int k = 0; k < 6 * CIN; ++k) {
+        const float4 xv = *reinterpret_cast<const float4*>(xs + k * PX + pg * 4);
+        float wv[CPT];
+        if (CPT == 4) {
+            const float4 t = *reinterpret_cast<const float4*>(ws + k * COUT + cg * 4);
+            wv[0] = t.x; wv[1] = t.y; wv[2] = t.z; wv[3] = t.w;
+        } else if (CPT == 2) {
+            const float2 t = *reinterpret_cast<const float2*>(ws + k * COUT + cg * 2);
+            wv[0] = t.x; wv[1] = t.y;
+        } else {
+            wv[0] = ws[k * COUT + cg];
+        }
+        const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) acc[i][j] = fmaf(xa[i], wv[j], acc[i][j]);
     }
     const float a = __ldg(alpha);
-    out0[ddb_off(g, unit, 0, F, h, f) + co] = acc >= 0.f ? acc : a * acc;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long pix = pix0 + pg * 4 + i;
+        if (pix >= npix) continue;
+        const long long unit = pix / F;
+        const int f = (int)(pix - unit * F);
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            const float r = acc[i][j] >= 0.f ? acc[i][j] : a * acc[i][j];
+            const int co = cg * CPT + j;
+            if (OUT_ACT) act_store<SH>(y, unit, F, COUT, f, co, r);
+            else reinterpret_cast<float*>(y)[ddb_off(g, unit, 0, F, COUT, f) + co] = r;
+        }
+    }
 }
 
 struct DdbOuts {
@@ -132,36 +200,6 @@ __global__ void __launch_bounds__(128) ddb_layer_kernel(DdbOuts src, int k, int 
     // out_1..out_5 are rings when streaming; out_6 is a plain (ping-ponged) tensor
     const long long oo = outk_is_ring ? ddb_off(geo, unit, 0, F, H, f) : pix * H;
     if (ok) outk[oo + g] = r >= 0.f ? r : a * r;
-}
-
-// `out`: out6 [frame][F][h] -> y [frame][F][C] (activation tensor), causal (2,3) conv + bias + PReLU.
-template <bool SH>
-__global__ void __launch_bounds__(128) ddb_out_kernel(const float* __restrict__ o6, const float* __restrict__ o6_prev,
-                                                     const float* __restrict__ w /*[2][3][h][C]*/, const float* __restrict__ b,
-                                                     const float* __restrict__ alpha, void* __restrict__ y, long long units,
-                                                     DdbGeom g, int F, int C) {
-    const int h = C >> 1;
-    const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long pix = gt / C;
-    const int co = (int)(gt - pix * C);
-    if (pix >= units * F) return;
-    const long long frame = pix / F;
-    const int f = (int)(pix - frame * F);
-    float acc = __ldg(b + co);
-    for (int kt = 0; kt < 2; ++kt) {
-        if (kt == 0 && !ddb_back_ok(g, frame, 1)) continue;
-        const float* base = (kt == 0 && g.streaming) ? o6_prev : o6;
-        const long long u = (kt == 0 && !g.streaming) ? frame - 1 : frame;
-        for (int kf = 0; kf < 3; ++kf) {
-            const int ff = f - 1 + kf;
-            if (ff < 0 || ff >= F) continue;
-            const float* src = base + (u * F + ff) * h;
-            const float* wk = w + (size_t)((kt * 3 + kf) * h) * C + co;
-            for (int ci = 0; ci < h; ++ci) acc = fmaf(__ldg(src + ci), __ldg(wk + (size_t)ci * C), acc);
-        }
-    }
-    const float a = __ldg(alpha);
-    act_store<SH>(y, frame, F, C, f, co, acc >= 0.f ? acc : a * acc);
 }
 
 }  // namespace nunet

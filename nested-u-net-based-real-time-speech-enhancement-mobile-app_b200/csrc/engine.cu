@@ -1005,8 +1005,16 @@ struct Engine {
             m[6] = pp->cur(mid[6], r.parity);
             const void* xin = pp->cur(x, r.parity);
             const void* xprev = pp->prev(x, r.parity);
-            if (sh) ddb_in_kernel<true><<<(int)((nin + 127) / 128), 128, 0, r.st>>>(xin, xprev, E.pool.at(L.w_in), E.pool.at(L.b_in), E.pool.at(L.a_in), m[0], units, g, F, C);
-            else ddb_in_kernel<false><<<(int)((nin + 127) / 128), 128, 0, r.st>>>(xin, xprev, E.pool.at(L.w_in), E.pool.at(L.b_in), E.pool.at(L.a_in), m[0], units, g, F, C);
+            {
+                const int blocks = (int)((units * F + 31) / 32);
+                const size_t smem = (size_t)(6 * C * h + 6 * C * 32) * sizeof(float);
+                auto go = [&](auto kfn) {
+                    CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+                    kfn<<<blocks, 128, smem, r.st>>>(xin, xprev, E.pool.at(L.w_in), E.pool.at(L.b_in), E.pool.at(L.a_in), m[0], units, g, F);
+                };
+                if (C == 64) { if (sh) go(ddb_conv23_kernel<64, 32, true, false, true>); else go(ddb_conv23_kernel<64, 32, true, false, false>); }
+                else { if (sh) go(ddb_conv23_kernel<32, 16, true, false, true>); else go(ddb_conv23_kernel<32, 16, true, false, false>); }
+            }
             E.check_launch("ddb_in", units * 4.0 * F * (C + h));
             DdbOuts src{};
             for (int i = 0; i < 6; ++i) src.o[i] = m[i];
@@ -1026,8 +1034,16 @@ struct Engine {
             }
             void* yo = pp->cur(o, r.parity);
             const float* o6prev = pp->prev(mid[6], r.parity);
-            if (sh) ddb_out_kernel<true><<<(int)((nout + 127) / 128), 128, 0, r.st>>>(m[6], o6prev, E.pool.at(L.w_out), E.pool.at(L.b_out), E.pool.at(L.a_out), yo, units, g, F, C);
-            else ddb_out_kernel<false><<<(int)((nout + 127) / 128), 128, 0, r.st>>>(m[6], o6prev, E.pool.at(L.w_out), E.pool.at(L.b_out), E.pool.at(L.a_out), yo, units, g, F, C);
+            {
+                const int blocks = (int)((units * F + 31) / 32);
+                const size_t smem = (size_t)(6 * h * C + 6 * h * 32) * sizeof(float);
+                auto go = [&](auto kfn) {
+                    CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+                    kfn<<<blocks, 128, smem, r.st>>>(m[6], o6prev, E.pool.at(L.w_out), E.pool.at(L.b_out), E.pool.at(L.a_out), yo, units, g, F);
+                };
+                if (C == 64) { if (sh) go(ddb_conv23_kernel<32, 64, false, true, true>); else go(ddb_conv23_kernel<32, 64, false, true, false>); }
+                else { if (sh) go(ddb_conv23_kernel<16, 32, false, true, true>); else go(ddb_conv23_kernel<16, 32, false, true, false>); }
+            }
             E.check_launch("ddb_out", units * 4.0 * F * (C + h));
         });
         return o;
