@@ -94,6 +94,7 @@ struct Tc3Params {
     int w_half_bytes;      // nphase * ntaps * N * 64
     int fence_mode;        // experiments only: 2 = skip the consumer-side fence.proxy.async
     int src_eo, out_eo;    // bins of the sources / of the output are stored [even | odd] inside each plane
+    int cluster;           // 1: launched as 2-CTA clusters (the two halves of a 128-channel unit): bulk copies are multicast
     int tma;               // 1: stride-1 single-image unit with F_in >= 32: row segments move with bulk copies (TMA)
     int dbg;               // experiments only: 1 = no loads, 2 = no stores, 4 = no MMAs, 8 = no LN/split math
 };
@@ -122,6 +123,21 @@ __device__ __forceinline__ int small_div(int n, int d, float rcp) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_mc(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ uint32_t elect_one() {
     uint32_t pred;
@@ -271,6 +287,9 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
     uint8_t* abuf0 = wsm + p.w_half_bytes;
     const uint32_t abuf_bytes = 4u * (uint32_t)p.plane_bytes;
 
+    // Programmatic dependent launch: let the next kernel of the stream start its prologue (barrier / TMEM set-up,
+    // weight load -- none of which depends on this kernel's output) on SMs that this grid has already left.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int MMA_WARP = T3_EPI_WARPS + T3_LD_WARPS;
     constexpr uint32_t ACC_COLS = 2 * T3_MT * 2 * N;   // 2 buffers x 2 tiles x (N + N) columns
@@ -280,7 +299,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
     if (threadIdx.x == 0) {
         for (int i = 0; i < T3_MAXNB; ++i) {
             mbar_init(&a_full[i], T3_LD_THREADS);
-            mbar_init(&a_empty[i], 1);
+            mbar_init(&a_empty[i], p.cluster ? 2 : 1);     // cluster: both CTAs' MMAs must be done before either refills
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&acc_full[i], 1);
@@ -301,6 +320,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (p.cluster) cluster_sync_all();     // the partner's barriers exist before anything is multicast to them
     const uint32_t tmem_base = *tmem_ptr_s;
 
     const int Tp = p.T + p.padrow;
@@ -315,6 +335,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
         const int eg = warp >> 2, wq = warp & 3;
         const int row = wq * 32 + lane;   // TMEM lane == tile row
         const float alpha = LN ? __ldg(p.alpha) : 0.f;
+        asm volatile("griddepcontrol.wait;" ::: "memory");   // the previous kernel may still read what we overwrite
         constexpr int NPX = N / PC;            // output pixels per conv pixel made by this CTA
         constexpr int CPP = PC / 8;            // 16-byte chunks per part of an output pixel
         const int npx = NPX * p.nhalf;         // output bins per conv bin
@@ -410,6 +431,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
         const int rs16 = p.F_in * (p.C0 >> 2);                 // 16-byte units per source frame row
         const int NB = p.nabuf;
         const float rcpP = 1.0f / (float)p.P, rcpTp = 1.0f / (float)Tp;
+        asm volatile("griddepcontrol.wait;" ::: "memory");   // our sources are the previous kernels' outputs
         int buf = 0, round = 0;        // ring position of phase g and the parity of its use count
         int g = 0;
         for (int it = 0; it < my_tiles; ++it) {
@@ -482,8 +504,11 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
                     fence_proxy_async();
                     if (seg_n > 0 && !(p.dbg & 1)) {
                         mbar_expect_tx(&a_full[buf], (uint32_t)seg_n * 16);
-                        bulk_g2s(abuf0 + (size_t)buf * abuf_bytes + (size_t)lw * p.plane_bytes + (size_t)seg_dst * 16,
-                                 pb + (long long)seg_src * 16, (uint32_t)seg_n * 16, &a_full[buf]);
+                        uint8_t* dstp = abuf0 + (size_t)buf * abuf_bytes + (size_t)lw * p.plane_bytes + (size_t)seg_dst * 16;
+                        if (!p.cluster)
+                            bulk_g2s(dstp, pb + (long long)seg_src * 16, (uint32_t)seg_n * 16, &a_full[buf]);
+                        else if (part == half)      // CTA 0 fetches the hi planes, CTA 1 the lo planes, for both CTAs
+                            bulk_g2s_mc(dstp, pb + (long long)seg_src * 16, (uint32_t)seg_n * 16, &a_full[buf], (uint16_t)3);
                     }
                     mbar_arrive(&a_full[buf]);
                 } else {
@@ -566,7 +591,8 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
                             wlow += N * 4;   // next (phase, tap) stage: N * 64 bytes
                         }
                     }
-                    tc_commit(&a_empty[buf]);
+                    if (p.cluster) tc_commit_mc(&a_empty[buf], (uint16_t)3);
+                    else tc_commit(&a_empty[buf]);
                 }
                 __syncwarp();
                 if (++buf == p.nabuf) {
@@ -582,6 +608,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
     // ------------------------------------------------------------------ teardown
     tc_fence_before();
     __syncthreads();
+    if (p.cluster) cluster_sync_all();     // nobody leaves while the partner can still write to / arrive on this CTA
     if (warp == MMA_WARP) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }

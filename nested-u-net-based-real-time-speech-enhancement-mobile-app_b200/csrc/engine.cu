@@ -378,9 +378,12 @@ struct Engine {
     bool use_tc = true;     // NUNET_CONV=simt forces the FP32 SIMT units everywhere
     int tc3_fence_mode = 0;  // NUNET_TC3_FENCE
     int tc3_dbg = 0;         // NUNET_TC3_DBG (experiments)
+    bool tc3_pdl = true;     // NUNET_TC3_PDL=0: plain stream order between consecutive conv kernels
     bool stream_tc3 = true;  // NUNET_STREAM_CONV=simt keeps the streaming plan on the FP32 SIMT units
     int tc3_force_mt = 0;    // NUNET_TC3_MT (experiments)
-    int tc3_tma = 0;         // NUNET_TC3_TMA=1 moves the row segments of stride-1 units (F_in >= 32) with bulk copies
+    int tc3_tma = 1;         // NUNET_TC3_TMA=0 keeps every unit on the cp.async loaders (default: bulk copies for stride-1 units, F_in >= 32)
+    int tc3_cluster = 0;     // NUNET_TC3_CLUSTER=1: the two CTAs of a 128-channel unit form a cluster and multicast their bulk copies
+                             // (one L2 read feeds both); measured neutral on B200, kept as an option
     bool use_tc3 = true;    // NUNET_CONV=tc keeps the 3xTF32 kernel (fp32 activations) for the offline plan
     int tc_min_bins = 1;    // NUNET_TC_MIN_BINS: units with fewer conv-output bins stay on the SIMT kernel
     // per-launch profiling (bench.py roofline leg): one CUDA event after every launch on the launching stream
@@ -741,7 +744,34 @@ struct Engine {
             CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             attr_set = true;
         }
-        kfn<<<grid, T3_THREADS, smem, st>>>(p);
+        cudaLaunchConfig_t lc{};
+        lc.gridDim = dim3((unsigned)grid);
+        lc.blockDim = dim3(T3_THREADS);
+        lc.dynamicSmemBytes = smem;
+        lc.stream = st;
+        cudaLaunchAttribute at[2];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = tc3_pdl ? 1 : 0;
+        lc.attrs = at;
+        lc.numAttrs = 1;
+        if (p.cluster) {
+            at[1].id = cudaLaunchAttributeClusterDimension;
+            at[1].val.clusterDim.x = 2;
+            at[1].val.clusterDim.y = 1;
+            at[1].val.clusterDim.z = 1;
+            lc.numAttrs = 2;
+        }
+        if (p.cluster) {
+            // a persistent grid must be co-resident: clamp to the number of 2-CTA clusters the device can hold at once
+            static int max_clusters = -1;
+            if (max_clusters < 0) {
+                int n = 0;
+                if (cudaOccupancyMaxActiveClusters(&n, kfn, &lc) != cudaSuccess || n <= 0) n = num_sms / 2 - 2;
+                max_clusters = n;
+            }
+            if ((int)lc.gridDim.x > 2 * max_clusters) lc.gridDim = dim3((unsigned)(2 * max_clusters));
+        }
+        CUDA_OK(cudaLaunchKernelEx(&lc, kfn, p));
         const double frames = (double)p.B * p.T;
         check_launch("conv_tc3", frames * 4.0 * ((double)p.F_in * (p.C0 + p.C1) + (double)p.F_conv * N * p.nhalf));
     }
@@ -800,6 +830,7 @@ struct Engine {
         int maxoff = 0;
         for (int i = 0; i < p.ntaps; ++i) maxoff = std::max(maxoff, p.tap_off[i]);
         p.tma = (tc3_tma && p.nimg == 1 && F_in >= 32 && !src_eo && !p.prev0) ? 1 : 0;
+        p.cluster = (p.tma && L.nhalf3 == 2 && tc3_cluster) ? 1 : 0;
         p.nphase = (L.CA + L.CB) / T3_KCH;
         p.nhalf = L.nhalf3;
         p.w_half_bytes = p.nphase * p.ntaps * L.N3 * 64;
@@ -1460,8 +1491,10 @@ int nunet_create(const nunet_config* cfg, const void* blob, size_t blob_bytes, n
         if (const char* c = getenv("NUNET_TC3_FENCE")) E.tc3_fence_mode = atoi(c);
         if (const char* c = getenv("NUNET_TC3_DBG")) E.tc3_dbg = atoi(c);
         if (const char* c = getenv("NUNET_TC3_TMA")) E.tc3_tma = atoi(c);
+        if (const char* c = getenv("NUNET_TC3_CLUSTER")) E.tc3_cluster = atoi(c);
         if (const char* c = getenv("NUNET_TC3_MT")) E.tc3_force_mt = atoi(c);
         if (const char* c = getenv("NUNET_STREAM_CONV")) E.stream_tc3 = strcmp(c, "simt") != 0;
+        if (const char* c = getenv("NUNET_TC3_PDL")) E.tc3_pdl = atoi(c) != 0;
         E.blob.parse(blob, blob_bytes);
         E.pack_params();
         E.pool.upload();
