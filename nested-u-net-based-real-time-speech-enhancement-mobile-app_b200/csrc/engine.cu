@@ -1082,7 +1082,7 @@ struct Engine {
 
     // One nested sub-U-Net (MSFE): returns ctfa(de_1) + en_in; fills des_out[k-1] = de_k (k = 1..n, F0 >> (k-1) bins)
     Ten* op_msfe(Plan& P, const std::string& blk, int n, Ten* en_in, Ten* const* skips, Ten** des_out,
-                 bool des_persistent, bool out_persistent, bool out_eo) {
+                 bool des_persistent, bool out_persistent, bool out_eo, bool fuse_out_conv = false) {
         std::string pc, ps;
         state_prefixes(blk, pc, ps);
         std::vector<Ten*> ens;
@@ -1149,6 +1149,16 @@ struct Engine {
                                                      ring ? pp->cur(ring, 0) : nullptr, r.ring_pos);
             E.check_launch("ctfa_gate", frames * 4.0 * (64 + 64));
             const long long n4 = (long long)frames * F0 * 16;
+            if (pp->sh16 && fuse_out_conv) {
+                // last decoder block: the 64 -> 1 out_conv is applied on the fly, the block output is never written
+                const long long npix = (long long)frames * F0;
+                gate_residual_out_conv_sh_kernel<<<(int)((npix + 127) / 128), 128, 0, r.st>>>(
+                    reinterpret_cast<const uint8_t*>(pp->cur(x, r.parity)), reinterpret_cast<const uint8_t*>(pp->cur(en_in, r.parity)),
+                    pp->cur(gate, 0), E.pool.at(E.out_layer.w), E.pool.at(E.out_layer.b), r.est_out, npix, F0, in_eo, r.est_stride,
+                    r.est_off);
+                E.check_launch("gate_residual_out_conv", frames * 4.0 * (3.0 * F0 * 64 + 64) + npix * 4.0 * 65);
+                return;
+            }
             if (pp->sh16) {
                 const long long n8 = n4 / 2;
                 const int blocks8 = (int)std::min<long long>((n8 + 255) / 256, 148LL * 16);
@@ -1206,9 +1216,13 @@ struct Engine {
             const int j = 5 - i;
             const size_t m = P.mark();
             Ten* en_in = op_conv(P, blk + "_in", y, enc_out[j], blk + "_in", false, /*out_eo=*/true);
-            y = op_msfe(P, blk, DEC_N[i], en_in, enc_des[j], nullptr, false, true, /*out_eo=*/false);
+            // the last block's gate + residual also applies out_conv (sh16 plans; kept apart when every tensor is retained
+            // for tools/layer_report.py)
+            const bool fuse = (i == 5) && P.sh16 && !getenv("NUNET_NO_RECYCLE");
+            y = op_msfe(P, blk, DEC_N[i], en_in, enc_des[j], nullptr, false, true, /*out_eo=*/false, fuse);
             if (recycle) P.release(m);
         }
+        if (!(P.sh16 && !getenv("NUNET_NO_RECYCLE")))
         P.ops.push_back([=](Engine& E, const Run& r) {
             E.cur_op = "out_conv";
             const long long npix = (long long)r.B * r.T * 256;

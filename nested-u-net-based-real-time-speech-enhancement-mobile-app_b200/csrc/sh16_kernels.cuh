@@ -140,6 +140,45 @@ __global__ void __launch_bounds__(256) gate_residual_sh_kernel(const uint8_t* __
     }
 }
 
+// Last decoder block: out_conv (Conv2D 1x1, 64 -> 1, models/proposed.py:615) applied to x * gate + res without ever
+// writing the 64-channel block output.  One thread per bin; lanes = consecutive bins, so every 16-byte load of a warp
+// is contiguous.  x and res share the [even | odd] order (in_eo); the estimate goes to bin order.
+__global__ void __launch_bounds__(128) gate_residual_out_conv_sh_kernel(const uint8_t* __restrict__ x, const uint8_t* __restrict__ res,
+                                                                       const float* __restrict__ gate, const float* __restrict__ w,
+                                                                       const float* __restrict__ b, float* __restrict__ out,
+                                                                       long long npix, int F, int in_eo, int out_stride, int out_off) {
+    __shared__ float ws[64];
+    if (threadIdx.x < 64) ws[threadIdx.x] = __ldg(w + threadIdx.x);
+    __syncthreads();
+    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= npix) return;
+    const long long frame = pix / F;
+    const int po = (int)(pix - frame * F);                       // storage position (coalesced loads)
+    const int f = in_eo ? ((po < (F >> 1)) ? 2 * po : 2 * (po - (F >> 1)) + 1) : po;
+    const long long rowoff = frame * ((long long)F * 256);
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int c8 = 0; c8 < 8; ++c8) {
+        float xv[8], rv[8];
+        sh16_load8(x + rowoff, F, 64, po, c8, xv);
+        sh16_load8(res + rowoff, F, 64, po, c8, rv);
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + frame * 64 + c8 * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + frame * 64 + c8 * 8) + 1);
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+            // the 64-channel value is rounded through the sh16 split exactly like the unfused path stores it
+            float y0 = fmaf(xv[e], gg[e], rv[e]), y1 = fmaf(xv[e + 1], gg[e + 1], rv[e + 1]);
+            const __half2 hh = __floats2half2_rn(y0, y1);
+            const float2 hf = __half22float2(hh);
+            const float2 lf = __half22float2(__floats2half2_rn(y0 - hf.x, y1 - hf.y));
+            s0 = fmaf(hf.x + lf.x, ws[c8 * 8 + e], s0);
+            s1 = fmaf(hf.y + lf.y, ws[c8 * 8 + e + 1], s1);
+        }
+    }
+    out[frame * out_stride + out_off + f] = (s0 + s1) + __ldg(b);
+}
+
 // half index of element (f, c) of part `part` inside a planar frame row [F][C]
 __device__ __forceinline__ int sh16_half_index(int F, int C, int part, int f, int c) {
     return (((part * (C >> 3) + (c >> 3)) * F + f) << 3) + (c & 7);
@@ -155,17 +194,16 @@ __global__ void __launch_bounds__(128) dense_rows_sh_kernel(const void* __restri
     const long long r0 = (long long)blockIdx.x * DENSE_RB;
     const int nr = (int)min((long long)DENSE_RB, rows - r0);
     if (IN_SH) {
-        const __half* X = reinterpret_cast<const __half*>(Xv);
-        const int F = K / C;
-        for (int i = threadIdx.x; i < DENSE_RB * K; i += blockDim.x) {
-            const int r = i / K, k = i - r * K;
-            const int f = k / C, c = k - f * C;
-            float v = 0.0f;
-            if (r < nr) {
-                const __half* row = X + (r0 + r) * (long long)K * 2;
-                v = __half2float(row[sh16_half_index(F, C, 0, f, c)]) + __half2float(row[sh16_half_index(F, C, 1, f, c)]);
-            }
-            xs[i] = v;
+        const uint8_t* X = reinterpret_cast<const uint8_t*>(Xv);
+        const int F = K / C, K8 = K >> 3, C8 = C >> 3;
+        for (int i = threadIdx.x; i < DENSE_RB * K8; i += blockDim.x) {      // item = 8 channels of one bin
+            const int r = i / K8, k8 = i - r * K8;
+            const int f = k8 / C8, c8 = k8 - f * C8;
+            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (r < nr) sh16_load8(X + (r0 + r) * (long long)K * 4, F, C, f, c8, v);
+            float4* dst = reinterpret_cast<float4*>(xs + r * K + f * C + c8 * 8);
+            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
         }
     } else {
         const float* X = reinterpret_cast<const float*>(Xv);
