@@ -1,6 +1,6 @@
 """One offline forward at a chosen batch, for ncu captures (`ncu -k regex:conv_tc3 ... python tools/ncu_target.py B`).
 Not a benchmark: numbers printed under a profiler are never bench values.  Also writes the launch-name list of the
-forward (gpurun_out/launch_names.json) so that ncu's per-launch rows can be joined with the engine's unit names."""
+forward (gpurun_out/launch_names_b<B>.json) so that ncu's per-launch rows can be joined with the engine's unit names."""
 import json
 import os
 import sys
@@ -24,5 +24,5 @@ eng.forward_wav_into(wav, out)
 torch.cuda.synchronize()
 names = [(n, b) for n, _ms, b in eng.profile_entries()]
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump({"batch": B, "frames": B * T, "launches": names}, open(os.path.join(ROOT, "gpurun_out", "launch_names.json"), "w"))
+json.dump({"batch": B, "frames": B * T, "launches": names}, open(os.path.join(ROOT, "gpurun_out", f"launch_names_b{B}.json"), "w"))
 print("done", eng.last_launch_count)

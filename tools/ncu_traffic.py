@@ -1,6 +1,6 @@
 """Join an ncu metrics CSV (dram__bytes_read.sum, dram__bytes_write.sum, gpu__time_duration.sum per launch, captured
-around tools/ncu_target.py) with gpurun_out/launch_names.json -> per-unit DRAM traffic table.
-usage: python tools/ncu_traffic.py gpurun_out/traffic.csv gpurun_out/launch_names.json profiles/out.json"""
+around tools/ncu_target.py) with gpurun_out/launch_names_b<B>.json -> per-unit DRAM traffic table.
+usage: python tools/ncu_traffic.py gpurun_out/traffic.csv gpurun_out/launch_names_b<B>.json profiles/out.json"""
 import csv
 import json
 import sys
