@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
     const int half = (int)blockIdx.x % p.nhalf;
     if (threadIdx.x == 0) {
         for (int i = 0; i < T3_MAXNB; ++i) {
-            mbar_init(&a_full[i], T3_LD_THREADS);
+            mbar_init(&a_full[i], p.tma ? T3_LD_WARPS : T3_LD_THREADS);   // TMA: one arrival per loader warp (+ tx bytes)
             mbar_init(&a_empty[i], p.cluster ? 2 : 1);     // cluster: both CTAs' MMAs must be done before either refills
         }
         for (int i = 0; i < 2; ++i) {
@@ -467,9 +467,13 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
                 }
             }
             asm volatile("bar.sync 1, %0;" ::"n"(T3_LD_THREADS) : "memory");
-            // TMA mode: lane r describes the part of frame row (first row of the tile + r) that lies inside the image
+            // TMA mode: lane r describes the part of frame row (first row of the tile + r) that lies inside the image,
+            // and remembers which of its table entries are pads (bit k <-> entry lane + 32 k) so that the per-buffer
+            // zero fill touches only those
             int seg_dst = 0, seg_src = 0, seg_n = 0;
+            uint32_t padmask = 0;
             if (p.tma) {
+                for (int k = 0; k < nit; ++k) padmask |= (slot_tbl[e0 + k * ESTEP] < 0) ? (1u << k) : 0u;
                 const int rho0 = (q0 >= 0) ? q0 / p.P : -((-q0 + p.P - 1) / p.P);
                 const int rho = rho0 + lane;
                 const int qs = rho * p.P;                           // flat position of x = 0 of this row
@@ -497,11 +501,13 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
                 const int* tb = slot_tbl + e0;
                 if (p.tma) {
                     // zero the pad slots of this plane (generic proxy), then hand the row segments to the copy engine
-                    for (int k = 0; k < nit; ++k) {
-                        if (tb[k * ESTEP] < 0) asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(d), "r"(0) : "memory");
-                        d += ESTEP * 16;
+                    if (padmask) {
+                        for (uint32_t m = padmask; m; m &= m - 1) {
+                            const int k = __ffs(m) - 1;
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(d + (uint32_t)k * (ESTEP * 16)), "r"(0) : "memory");
+                        }
+                        fence_proxy_async();
                     }
-                    fence_proxy_async();
                     if (seg_n > 0 && !(p.dbg & 1)) {
                         mbar_expect_tx(&a_full[buf], (uint32_t)seg_n * 16);
                         uint8_t* dstp = abuf0 + (size_t)buf * abuf_bytes + (size_t)lw * p.plane_bytes + (size_t)seg_dst * 16;
@@ -510,7 +516,8 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
                         else if (part == half)      // CTA 0 fetches the hi planes, CTA 1 the lo planes, for both CTAs
                             bulk_g2s_mc(dstp, pb + (long long)seg_src * 16, (uint32_t)seg_n * 16, &a_full[buf], (uint16_t)3);
                     }
-                    mbar_arrive(&a_full[buf]);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&a_full[buf]);
                 } else {
                     if (!(p.dbg & 1))
 #pragma unroll 4
