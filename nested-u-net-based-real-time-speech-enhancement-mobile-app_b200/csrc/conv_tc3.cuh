@@ -474,17 +474,25 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
             uint32_t padmask = 0;
             if (p.tma) {
                 for (int k = 0; k < nit; ++k) padmask |= (slot_tbl[e0 + k * ESTEP] < 0) ? (1u << k) : 0u;
+                // two-image (stride-2) units: lanes 0-15 describe image 0, lanes 16-31 image 1 (<= 16 rows per tile);
+                // their sources are stored [even | odd], so each image's bins are consecutive storage positions
+                const int img = (p.nimg == 2) ? (lane >> 4) : 0;
+                const int r = (p.nimg == 2) ? (lane & 15) : lane;
+                const int mul = p.img_mul[img], add = p.img_add[img];
                 const int rho0 = (q0 >= 0) ? q0 / p.P : -((-q0 + p.P - 1) / p.P);
-                const int rho = rho0 + lane;
+                const int rho = rho0 + r;
                 const int qs = rho * p.P;                           // flat position of x = 0 of this row
-                int xa = max(q0 - qs, -p.img_add[0]);               // first x with a real source bin
-                int xb = min(q0 + p.slots - qs, p.F_in - p.img_add[0]);
-                xb = min(xb, p.P);
+                const int x_first = (mul == 1) ? -add : ((add < 0) ? (1 - add) / 2 : 0);       // first x with a real source bin
+                const int x_end = (mul == 1) ? p.F_in - add : (p.F_in - add + 1) / 2;          // first x past the last bin
+                int xa = max(q0 - qs, x_first);
+                int xb = min(min(q0 + p.slots - qs, x_end), p.P);
                 const int b = (rho >= 0) ? rho / Tp : 0;
                 const int t = rho - b * Tp - p.padrow;
                 if (rho >= 0 && (long long)qs < (long long)p.total_flat && t >= 0 && xb > xa) {
-                    seg_dst = qs + xa - q0;
-                    seg_src = (b * p.T + t) * rs16 + xa + p.img_add[0];
+                    const int fi = mul * xa + add;
+                    const int pos = p.src_eo ? (fi & 1) * (p.F_in >> 1) + (fi >> 1) : fi;
+                    seg_dst = img * p.slots + qs + xa - q0;
+                    seg_src = (b * p.T + t) * rs16 + pos;
                     seg_n = xb - xa;
                 }
             }

@@ -829,7 +829,9 @@ struct Engine {
         }
         int maxoff = 0;
         for (int i = 0; i < p.ntaps; ++i) maxoff = std::max(maxoff, p.tap_off[i]);
-        p.tma = (tc3_tma && p.nimg == 1 && F_in >= 32 && !src_eo && !p.prev0) ? 1 : 0;
+        // bulk-copy (TMA) row segments need contiguous source bins: stride-1 units over bin-ordered sources, stride-2 units
+        // over [even | odd] sources; <= 32 (16 per image) frame rows per tile
+        p.tma = (tc3_tma && !p.prev0 && ((p.nimg == 1 && !src_eo && F_in >= 32) || (p.nimg == 2 && src_eo && p.F_conv >= 32))) ? 1 : 0;
         p.cluster = (p.tma && L.nhalf3 == 2 && tc3_cluster) ? 1 : 0;
         p.nphase = (L.CA + L.CB) / T3_KCH;
         p.nhalf = L.nhalf3;
