@@ -382,6 +382,7 @@ struct Engine {
     bool stream_tc3 = true;  // NUNET_STREAM_CONV=simt keeps the streaming plan on the FP32 SIMT units
     int tc3_force_mt = 0;    // NUNET_TC3_MT (experiments)
     int tc3_tma = 1;         // NUNET_TC3_TMA=0 keeps every unit on the cp.async loaders (default: bulk copies for stride-1 units, F_in >= 32)
+    int tc3_tma_minf = 32;   // NUNET_TC3_TMA_MINF (experiments): smallest F_in of a stride-1 unit that uses bulk copies
     int tc3_cluster = 0;     // NUNET_TC3_CLUSTER=1: the two CTAs of a 128-channel unit form a cluster and multicast their bulk copies
                              // (one L2 read feeds both); measured neutral on B200, kept as an option
     bool use_tc3 = true;    // NUNET_CONV=tc keeps the 3xTF32 kernel (fp32 activations) for the offline plan
@@ -831,7 +832,7 @@ struct Engine {
         for (int i = 0; i < p.ntaps; ++i) maxoff = std::max(maxoff, p.tap_off[i]);
         // bulk-copy (TMA) row segments need contiguous source bins: stride-1 units over bin-ordered sources, stride-2 units
         // over [even | odd] sources; <= 32 (16 per image) frame rows per tile
-        p.tma = (tc3_tma && !p.prev0 && ((p.nimg == 1 && !src_eo && F_in >= 32) || (p.nimg == 2 && src_eo && p.F_conv >= 32))) ? 1 : 0;
+        p.tma = (tc3_tma && !p.prev0 && ((p.nimg == 1 && !src_eo && F_in >= tc3_tma_minf) || (p.nimg == 2 && src_eo && p.F_conv >= 32))) ? 1 : 0;
         p.cluster = (p.tma && L.nhalf3 == 2 && tc3_cluster) ? 1 : 0;
         p.nphase = (L.CA + L.CB) / T3_KCH;
         p.nhalf = L.nhalf3;
@@ -1141,8 +1142,8 @@ struct Engine {
             E.cur_op = blk;
             const int frames = r.B * r.T;
             if (pp->sh16)
-                ctfa_ta_sh_kernel<<<frames, 256, 0, r.st>>>(reinterpret_cast<const uint8_t*>(pp->cur(x, r.parity)), E.mlpw(mta),
-                                                           pp->cur(ta, 0), F0);
+                ctfa_ta_sh_kernel<<<(frames + CTFA_FPB - 1) / CTFA_FPB, 256, 0, r.st>>>(
+                    reinterpret_cast<const uint8_t*>(pp->cur(x, r.parity)), E.mlpw(mta), pp->cur(ta, 0), F0, (long long)frames);
             else
                 ctfa_ta_kernel<<<frames, 256, 0, r.st>>>(pp->cur(x, r.parity), E.mlpw(mta), pp->cur(ta, 0), F0);
             E.check_launch("ctfa_ta", frames * 4.0 * (F0 * 64 + 64));
@@ -1508,6 +1509,7 @@ int nunet_create(const nunet_config* cfg, const void* blob, size_t blob_bytes, n
         if (const char* c = getenv("NUNET_TC3_DBG")) E.tc3_dbg = atoi(c);
         if (const char* c = getenv("NUNET_TC3_TMA")) E.tc3_tma = atoi(c);
         if (const char* c = getenv("NUNET_TC3_CLUSTER")) E.tc3_cluster = atoi(c);
+        if (const char* c = getenv("NUNET_TC3_TMA_MINF")) E.tc3_tma_minf = std::max(8, atoi(c));
         if (const char* c = getenv("NUNET_TC3_MT")) E.tc3_force_mt = atoi(c);
         if (const char* c = getenv("NUNET_STREAM_CONV")) E.stream_tc3 = strcmp(c, "simt") != 0;
         if (const char* c = getenv("NUNET_TC3_PDL")) E.tc3_pdl = atoi(c) != 0;

@@ -76,37 +76,72 @@ __global__ void __launch_bounds__(128) out_conv_sh_kernel(const uint8_t* __restr
     out[frame * out_stride + out_off + f] = (s0 + s1) + __ldg(b);
 }
 
-// CTFA stage 1 (models/proposed.py:125): TA[frame, c] = MLP(mean_f x[frame, f, c]).  One CTA per frame:
-// warp w sums chunk w (8 channels) over the bins, lanes striding f.
-__global__ void __launch_bounds__(256) ctfa_ta_sh_kernel(const uint8_t* __restrict__ x, MlpW ta, float* __restrict__ ta_out, int F) {
-    __shared__ float mean_s[64];
-    __shared__ float h_s[16];
-    const int frame = blockIdx.x;
-    const int c8 = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint8_t* row = x + (size_t)frame * F * 256;
-    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-    for (int f = lane; f < F; f += 32) {
-        float v[8];
-        sh16_load8(row, F, 64, f, c8, v);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) s[e] += v[e];
+// The two-layer MLP of a CTFA attention (64 -> 16 relu -> 64 sigmoid) for CTFA_FPB frames at once, weights staged in
+// shared memory by the caller: thread (fr = tid / 64, c = tid % 64).  v_s [CTFA_FPB][64] input, h_s [CTFA_FPB][16] scratch.
+constexpr int CTFA_FPB = 4;   // frames per CTA (256 threads)
+struct MlpSmem {
+    float k0[64 * 16], b0[16], k1[16 * 64], b1[64];
+};
+__device__ __forceinline__ void mlp_stage(MlpSmem& m, const MlpW& w) {
+    for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) {
+        m.k0[i] = __ldg(w.k0 + i);
+        m.k1[i] = __ldg(w.k1 + i);
     }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-#pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) s[e] += __shfl_xor_sync(0xffffffffu, s[e], m);
-    }
-    if (lane == 0) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) mean_s[c8 * 8 + e] = s[e] / (float)F;
+    if (threadIdx.x < 16) m.b0[threadIdx.x] = __ldg(w.b0 + threadIdx.x);
+    if (threadIdx.x < 64) m.b1[threadIdx.x] = __ldg(w.b1 + threadIdx.x);
+}
+// call with all 256 threads after a __syncthreads() that made v_s and the staged weights visible
+__device__ __forceinline__ float mlp_apply(const MlpSmem& m, const float (*v_s)[64], float (*h_s)[16]) {
+    const int fr = threadIdx.x >> 6, c = threadIdx.x & 63;
+    if (c < 16) {
+        float a = m.b0[c];
+#pragma unroll 16
+        for (int k = 0; k < 64; ++k) a = fmaf(v_s[fr][k], m.k0[k * 16 + c], a);
+        h_s[fr][c] = fmaxf(a, 0.0f);
     }
     __syncthreads();
-    if (threadIdx.x < 64) {
-        const int c = threadIdx.x;
-        const float t = ctfa_mlp(mean_s, h_s, ta, c, 1);
-        ta_out[(size_t)frame * 64 + c] = t;
+    float o = m.b1[c];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o = fmaf(h_s[fr][j], m.k1[j * 64 + c], o);
+    return sigmoidf_(o);
+}
+
+// CTFA stage 1 (models/proposed.py:125): TA[frame, c] = MLP(mean_f x[frame, f, c]).  One CTA per CTFA_FPB frames:
+// warp w sums chunk w (8 channels) over the bins of each frame, lanes striding f; then all 256 threads run the MLP.
+__global__ void __launch_bounds__(256) ctfa_ta_sh_kernel(const uint8_t* __restrict__ x, MlpW ta, float* __restrict__ ta_out, int F,
+                                                        long long frames) {
+    __shared__ MlpSmem w_s;
+    __shared__ float mean_s[CTFA_FPB][64];
+    __shared__ float h_s[CTFA_FPB][16];
+    mlp_stage(w_s, ta);
+    const long long frame0 = (long long)blockIdx.x * CTFA_FPB;
+    const int c8 = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int fr = 0; fr < CTFA_FPB; ++fr) {
+        float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (frame0 + fr < frames) {
+            const uint8_t* row = x + (size_t)(frame0 + fr) * F * 256;
+#pragma unroll 4
+            for (int f = lane; f < F; f += 32) {
+                float v[8];
+                sh16_load8(row, F, 64, f, c8, v);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) s[e] += v[e];
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) s[e] += __shfl_xor_sync(0xffffffffu, s[e], m);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) mean_s[fr][c8 * 8 + e] = s[e] / (float)F;
+        }
     }
+    __syncthreads();
+    const float t = mlp_apply(w_s, mean_s, h_s);
+    const long long frame = frame0 + (threadIdx.x >> 6);
+    if (frame < frames) ta_out[frame * 64 + (threadIdx.x & 63)] = t;
 }
 
 // storage position of bin f inside a plane: natural order, or [even bins | odd bins]
