@@ -96,6 +96,7 @@ struct Tc3Params {
     int src_eo, out_eo;    // bins of the sources / of the output are stored [even | odd] inside each plane
     int cluster;           // 1: launched as 2-CTA clusters (the two halves of a 128-channel unit): bulk copies are multicast
     int tma;               // 1: stride-1 single-image unit with F_in >= 32: row segments move with bulk copies (TMA)
+    unsigned long long* timing;   // experiments: CTA 0 writes per-role cycle counters here (null = off)
     int dbg;               // experiments only: 1 = no loads, 2 = no stores, 4 = no MMAs, 8 = no LN/split math
 };
 
@@ -341,13 +342,18 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
         const int npx = NPX * p.nhalf;         // output bins per conv bin
         const long long out_rs = (long long)p.F_out * (PC * 4);   // bytes per output frame row
         const long long plane = (long long)p.F_out * 16;          // bytes per output plane
+        long long t_wait = 0, t_ld = 0;                           // per-role cycle counters (Tc3Params::timing)
+        const long long t_begin = clock64();
         for (int it = 0; it < my_tiles; ++it) {
             const int mt = (p.mt == 2) ? eg : 0;
             if (p.mt == 1 && (it & 1) != eg) continue;
             const int tile = cta + it * ncta;
             const int ab = it & 1;
+            const long long tq0 = clock64();
             mbar_wait_relaxed(&acc_full[ab], (it >> 1) & 1);
             tc_fence_after();
+            const long long tq1 = clock64();
+            t_wait += tq1 - tq0;
             const int q = tile * tile_pos + mt * 128 + row;
             const int rho = q / p.P;
             const int x = q - rho * p.P;
@@ -373,6 +379,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
             // the accumulator is in registers: hand the TMEM buffer back to the MMA warp right away
             tc_fence_before();
             mbar_arrive(&acc_empty[ab]);
+            t_ld += clock64() - tq1;
             {
                 const float2 sc = make_float2(p.wscale_inv, p.wscale_inv);
 #pragma unroll
@@ -413,6 +420,11 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
                 }
             }
         }
+        if (p.timing && blockIdx.x == 0 && threadIdx.x == 0) {
+            p.timing[4] = (unsigned long long)t_wait;
+            p.timing[5] = (unsigned long long)t_ld;
+            p.timing[6] = (unsigned long long)(clock64() - t_begin);
+        }
     } else if (warp < MMA_WARP) {
         // ================================================================= loaders
         // Loader warp w owns plane w = (part hi|lo, chunk) of every buffer; its lanes walk the table entries
@@ -431,12 +443,15 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
         const int rs16 = p.F_in * (p.C0 >> 2);                 // 16-byte units per source frame row
         const int NB = p.nabuf;
         const float rcpP = 1.0f / (float)p.P, rcpTp = 1.0f / (float)Tp;
+        long long tl_table = 0, tl_wait = 0, tl_fence = 0, tl_issue = 0;   // per-role cycle counters (Tc3Params::timing)
+        const long long tl_begin = clock64();
         asm volatile("griddepcontrol.wait;" ::: "memory");   // our sources are the previous kernels' outputs
         int buf = 0, round = 0;        // ring position of phase g and the parity of its use count
         int g = 0;
         for (int it = 0; it < my_tiles; ++it) {
             const int tile = cta + it * ncta;
             const int q0 = tile * tile_pos - p.lead;
+            const long long tl0 = clock64();
             if (it > 0) asm volatile("bar.sync 1, %0;" ::"n"(T3_LD_THREADS) : "memory");   // everyone is done with the old table
             {
                 // (row, x) of slot 0 by two real divisions per tile; every entry then needs only small-number
@@ -496,8 +511,11 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
                     seg_n = xb - xa;
                 }
             }
+            tl_table += clock64() - tl0;
             for (int ph = 0; ph < p.nphase; ++ph, ++g) {
+                const long long tl1 = clock64();
                 if (g >= NB) mbar_wait_relaxed(&a_empty[buf], round ^ 1);
+                tl_wait += clock64() - tl1;
                 const int c0 = ph * T3_KCH;
                 const bool first = c0 < p.C0;
                 const uint8_t* src = first ? p.src0 : p.src1;
@@ -509,6 +527,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
                 const int* tb = slot_tbl + e0;
                 if (p.tma) {
                     // zero the pad slots of this plane (generic proxy), then hand the row segments to the copy engine
+                    const long long tf0 = clock64();
                     if (padmask) {
                         for (uint32_t m = padmask; m; m &= m - 1) {
                             const int k = __ffs(m) - 1;
@@ -516,6 +535,8 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
                         }
                         fence_proxy_async();
                     }
+                    const long long tf1 = clock64();
+                    tl_fence += tf1 - tf0;
                     if (seg_n > 0 && !(p.dbg & 1)) {
                         mbar_expect_tx(&a_full[buf], (uint32_t)seg_n * 16);
                         uint8_t* dstp = abuf0 + (size_t)buf * abuf_bytes + (size_t)lw * p.plane_bytes + (size_t)seg_dst * 16;
@@ -524,6 +545,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
                         else if (part == half)      // CTA 0 fetches the hi planes, CTA 1 the lo planes, for both CTAs
                             bulk_g2s_mc(dstp, pb + (long long)seg_src * 16, (uint32_t)seg_n * 16, &a_full[buf], (uint16_t)3);
                     }
+                    tl_issue += clock64() - tf1;
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&a_full[buf]);
                 } else {
@@ -547,6 +569,13 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
             }
         }
         cp_async_wait<0>();
+        if (p.timing && blockIdx.x == 0 && lt == 0) {
+            p.timing[7] = (unsigned long long)tl_wait;
+            p.timing[8] = (unsigned long long)tl_table;
+            p.timing[9] = (unsigned long long)(clock64() - tl_begin);
+            p.timing[10] = (unsigned long long)tl_fence;
+            p.timing[11] = (unsigned long long)tl_issue;
+        }
     } else {
         // ================================================================= MMA issuer (+ one-off weight load)
         // The whole warp stays converged (waits are warp-wide); one elected lane issues, so the tcgen05
@@ -578,16 +607,22 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
         for (int tap = 0; tap < T3_MAXTAPS; ++tap)
             tapd[tap] = (tap < p.ntaps) ? (uint32_t)(p.tap_img[tap] * p.slots + p.tap_off[tap]) : 0u;
         int buf = 0, round = 0;
+        long long tm_full = 0, tm_acc = 0;                         // per-role cycle counters (Tc3Params::timing)
+        const long long tm_begin = clock64();
         for (int it = 0; it < my_tiles; ++it) {
             const int accb = it & 1;
+            const long long tm0 = clock64();
             if (it >= 2) mbar_wait(&acc_empty[accb], ((it >> 1) - 1) & 1);
             tc_fence_after();
+            tm_acc += clock64() - tm0;
             uint32_t wlow = db_low0;
             const uint32_t d0 = tmem_base + (uint32_t)(accb * p.mt * 2 * N);
             for (int ph = 0; ph < p.nphase; ++ph) {
+                const long long tm1 = clock64();
                 mbar_wait(&a_full[buf], round);
                 if (p.fence_mode != 2) fence_proxy_async();   // cp.async wrote through the generic proxy, the MMA reads through the async proxy
                 tc_fence_after();
+                tm_full += clock64() - tm1;
                 if (leader) {
                     const uint32_t alow = da_low0 + (uint32_t)buf * abuf16;
 #pragma unroll
@@ -617,6 +652,12 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
             }
             if (leader) tc_commit(&acc_full[accb]);
             __syncwarp();
+        }
+        if (p.timing && blockIdx.x == 0 && lane == 0) {
+            p.timing[0] = (unsigned long long)(clock64() - tm_begin);
+            p.timing[1] = (unsigned long long)tm_full;
+            p.timing[2] = (unsigned long long)tm_acc;
+            p.timing[3] = (unsigned long long)my_tiles;
         }
     }
 

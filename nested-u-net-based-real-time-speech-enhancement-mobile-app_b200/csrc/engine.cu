@@ -378,6 +378,7 @@ struct Engine {
     bool use_tc = true;     // NUNET_CONV=simt forces the FP32 SIMT units everywhere
     int tc3_fence_mode = 0;  // NUNET_TC3_FENCE
     int tc3_dbg = 0;         // NUNET_TC3_DBG (experiments)
+    unsigned long long* tc3_timing_buf = nullptr;   // NUNET_TC3_TIMING=1 (experiments): per-role cycle counters of CTA 0
     bool tc3_pdl = true;     // NUNET_TC3_PDL=0: plain stream order between consecutive conv kernels
     bool stream_tc3 = true;  // NUNET_STREAM_CONV=simt keeps the streaming plan on the FP32 SIMT units
     int tc3_force_mt = 0;    // NUNET_TC3_MT (experiments)
@@ -773,6 +774,16 @@ struct Engine {
             if ((int)lc.gridDim.x > 2 * max_clusters) lc.gridDim = dim3((unsigned)(2 * max_clusters));
         }
         CUDA_OK(cudaLaunchKernelEx(&lc, kfn, p));
+        if (tc3_timing_buf) {   // experiments: per-role cycles of CTA 0, per tile (serialises the stream)
+            unsigned long long h[12];
+            CUDA_OK(cudaStreamSynchronize(st));
+            CUDA_OK(cudaMemcpy(h, tc3_timing_buf, sizeof h, cudaMemcpyDeviceToHost));
+            const double tl = (double)std::max<unsigned long long>(h[3], 1);
+            fprintf(stderr, "TC3TIMING %-22s tiles %5llu phases %d tma %d | mma total %6.0f wait_data %6.0f wait_acc %5.0f | epilogue total %6.0f wait %6.0f tmem_ld %5.0f | "
+                            "loader total %6.0f wait_buf %6.0f table %5.0f zero+fence %5.0f bulk %5.0f  (cycles per tile)\n",
+                    cur_op.c_str(), h[3], p.nphase, p.tma, h[0] / tl, h[1] / tl, h[2] / tl, h[6] / tl, h[4] / tl, h[5] / tl, h[9] / tl, h[7] / tl,
+                    h[8] / tl, h[10] / tl, h[11] / tl);
+        }
         const double frames = (double)p.B * p.T;
         check_launch("conv_tc3", frames * 4.0 * ((double)p.F_in * (p.C0 + p.C1) + (double)p.F_conv * N * p.nhalf));
     }
@@ -796,6 +807,7 @@ struct Engine {
         p.wscale_inv = L.wscale_inv;
         p.fence_mode = tc3_fence_mode;
         p.dbg = tc3_dbg;
+        p.timing = tc3_timing_buf;
         p.B = B; p.T = T; p.F_in = F_in;
         p.F_conv = (L.stride == 2) ? F_in / 2 : F_in;
         p.F_out = p.F_conv * L.COUT / L.PC3;
@@ -1507,6 +1519,10 @@ int nunet_create(const nunet_config* cfg, const void* blob, size_t blob_bytes, n
         if (const char* c = getenv("NUNET_TC_MIN_BINS")) E.tc_min_bins = atoi(c);
         if (const char* c = getenv("NUNET_TC3_FENCE")) E.tc3_fence_mode = atoi(c);
         if (const char* c = getenv("NUNET_TC3_DBG")) E.tc3_dbg = atoi(c);
+        if (getenv("NUNET_TC3_TIMING")) {
+            CUDA_OK(cudaMalloc(&E.tc3_timing_buf, 16 * sizeof(unsigned long long)));
+            CUDA_OK(cudaMemset(E.tc3_timing_buf, 0, 16 * sizeof(unsigned long long)));
+        }
         if (const char* c = getenv("NUNET_TC3_TMA")) E.tc3_tma = atoi(c);
         if (const char* c = getenv("NUNET_TC3_CLUSTER")) E.tc3_cluster = atoi(c);
         if (const char* c = getenv("NUNET_TC3_TMA_MINF")) E.tc3_tma_minf = std::max(8, atoi(c));
