@@ -42,6 +42,7 @@
 //                         buffers, NB-1 buffers ahead
 //   warp  12    MMA       one elected thread: tcgen05.mma kind::f16, M=128, N, K=16; accumulators double-buffered
 #pragma once
+#include <cuda.h>        // CUtensorMap
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -95,7 +96,20 @@ struct Tc3Params {
     int fence_mode;        // experiments only: 2 = skip the consumer-side fence.proxy.async
     int src_eo, out_eo;    // bins of the sources / of the output are stored [even | odd] inside each plane
     int cluster;           // 1: launched as 2-CTA clusters (the two halves of a 128-channel unit): bulk copies are multicast
-    int tma;               // 1: stride-1 single-image unit with F_in >= 32: row segments move with bulk copies (TMA)
+    int tma;               // 1: row segments move with 1-D bulk copies; 2: whole tile images move as tensor-map boxes (see tm*)
+    // tma == 2: a tile whose frame rows lie inside one clip is fetched with ONE cp.async.bulk.tensor per (plane, image):
+    // the box is tm_rows whole frame rows x P positions starting at storage position tm_c[img]; positions outside the
+    // plane (the frequency pads) and rows outside the clip (the causal time pad, the tail) are zero-filled by the copy
+    // engine.  The image then starts on a row boundary, so the MMA adds (q0 mod P) + tm_delta[img] to its tap offsets.
+    // Tiles that straddle two clips fall back to the slot-table cp.async loader.
+    int tm_rank;           // 4: {2 x 8-byte words per position run, plane, t, b}; 5: {16 words = 8 positions, run, plane, t, b}
+    int tm_rows;           // frame rows per box
+    int tm_c[2];           // first storage position of a box row per image (<= 0), in positions
+    int tm_delta[2];       // image index of flat position (rho_a, x) is x + tm_delta[img]
+    int tm_par[2];         // [even | odd] sources: which parity half image img reads
+    int tm_img_bytes;      // byte offset of image 1 inside a plane (128-byte multiple)
+    int tm_box_bytes;      // tm_rows * P * 16
+    alignas(64) CUtensorMap tm_map[2];   // src0 / src1
     unsigned long long* timing;   // experiments: CTA 0 writes per-role cycle counters here (null = off)
     int dbg;               // experiments only: 1 = no loads, 2 = no stores, 4 = no MMAs, 8 = no LN/split math
 };
@@ -139,6 +153,40 @@ __device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_n(uint64_t* bar, uint32_t n) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(n) : "memory");
+}
+__device__ __forceinline__ void tensor_g2s_4d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tensor_g2s_5d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ int floor_div(int n, int d) { return (n >= 0) ? n / d : -((-n + d - 1) / d); }
+// tma == 2: does the tile whose image starts at flat position qa fit one clip (-> tensor-map boxes), and where does the
+// image start inside its first frame row?  Evaluated identically by the loaders and the MMA warp.
+struct T3TileGeo {
+    int box;       // 1: tensor boxes, 0: slot-table fallback
+    int xoff;      // qa - rho_a * P
+    int b, t;      // clip and frame (may be -1: the causal pad row) of frame row rho_a
+};
+__device__ __forceinline__ T3TileGeo t3_tile_geo(int qa, int P, int Tp, int padrow, int slots, int dmax) {
+    T3TileGeo g;
+    const int rho_a = floor_div(qa, P);
+    g.xoff = qa - rho_a * P;
+    const int need = (g.xoff + dmax + slots - 1) / P + 1;       // frame rows the MMAs can touch
+    g.b = floor_div(rho_a, Tp);
+    const int tp = rho_a - g.b * Tp;
+    g.t = tp - padrow;
+    g.box = (rho_a >= 0 && tp + need <= Tp) ? 1 : 0;
+    return g;
 }
 __device__ __forceinline__ uint32_t elect_one() {
     uint32_t pred;
@@ -273,7 +321,7 @@ __device__ __forceinline__ void split8p(const float2* v, uint4& hi, uint4& lo) {
 // N: conv channels of this CTA (32 / 64); PC: channels per OUTPUT pixel (N, or 32 for the 64-column sub-pixel
 // shuffle that makes two pixels); LN: LayerNorm + PReLU over each PC-channel group (false: bias only).
 template <int N, int PC, bool LN>
-__global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params p) {
+__global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_constant__ Tc3Params p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* a_full = bars;                     // [T3_MAXNB]
@@ -299,7 +347,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
     const int half = (int)blockIdx.x % p.nhalf;
     if (threadIdx.x == 0) {
         for (int i = 0; i < T3_MAXNB; ++i) {
-            mbar_init(&a_full[i], p.tma ? T3_LD_WARPS : T3_LD_THREADS);   // TMA: one arrival per loader warp (+ tx bytes)
+            mbar_init(&a_full[i], p.tma == 1 ? T3_LD_WARPS : T3_LD_THREADS);   // bulk rows: one arrival per loader warp (+ tx bytes)
             mbar_init(&a_empty[i], p.cluster ? 2 : 1);     // cluster: both CTAs' MMAs must be done before either refills
         }
         for (int i = 0; i < 2; ++i) {
@@ -452,6 +500,44 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
             const int tile = cta + it * ncta;
             const int q0 = tile * tile_pos - p.lead;
             const long long tl0 = clock64();
+            if (p.tma == 2) {
+                const T3TileGeo tg = t3_tile_geo(q0, p.P, Tp, p.padrow, p.slots, max(p.tm_delta[0], p.tm_delta[1]));
+                if (tg.box) {
+                    // one box per image into this warp's plane; 32 arrivals per warp keep the barrier count of the fallback
+                    for (int ph = 0; ph < p.nphase; ++ph, ++g) {
+                        const long long tl1 = clock64();
+                        if (g >= NB) mbar_wait_relaxed(&a_empty[buf], round ^ 1);
+                        const long long tl2 = clock64();
+                        tl_wait += tl2 - tl1;
+                        if (lane == 0) {
+                            const int c0 = ph * T3_KCH;
+                            const bool first = c0 < p.C0;
+                            const int cc = first ? c0 : c0 - p.C0;
+                            const int plane = part * cpp0 + (cc >> 3) + chunk;
+                            const CUtensorMap* map = &p.tm_map[first ? 0 : 1];
+                            uint8_t* dstp = abuf0 + (size_t)buf * abuf_bytes + (size_t)lw * p.plane_bytes;
+                            if (!(p.dbg & 1)) {
+                                mbar_expect_tx(&a_full[buf], (uint32_t)(p.nimg * p.tm_box_bytes));
+                                for (int img = 0; img < p.nimg; ++img) {
+                                    const int pl = p.src_eo ? 2 * plane + p.tm_par[img] : plane;
+                                    if (p.tm_rank == 4)
+                                        tensor_g2s_4d(dstp + (size_t)img * p.tm_img_bytes, map, 2 * p.tm_c[img], pl, tg.t, tg.b, &a_full[buf]);
+                                    else
+                                        tensor_g2s_5d(dstp + (size_t)img * p.tm_img_bytes, map, 0, p.tm_c[img] >> 3, pl, tg.t, tg.b, &a_full[buf]);
+                                }
+                            }
+                            mbar_arrive_n(&a_full[buf], 32);
+                        }
+                        __syncwarp();
+                        tl_issue += clock64() - tl2;
+                        if (++buf == NB) {
+                            buf = 0;
+                            round ^= 1;
+                        }
+                    }
+                    continue;
+                }
+            }
             if (it > 0) asm volatile("bar.sync 1, %0;" ::"n"(T3_LD_THREADS) : "memory");   // everyone is done with the old table
             {
                 // (row, x) of slot 0 by two real divisions per tile; every entry then needs only small-number
@@ -487,7 +573,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
             // zero fill touches only those
             int seg_dst = 0, seg_src = 0, seg_n = 0;
             uint32_t padmask = 0;
-            if (p.tma) {
+            if (p.tma == 1) {
                 for (int k = 0; k < nit; ++k) padmask |= (slot_tbl[e0 + k * ESTEP] < 0) ? (1u << k) : 0u;
                 // two-image (stride-2) units: lanes 0-15 describe image 0, lanes 16-31 image 1 (<= 16 rows per tile);
                 // their sources are stored [even | odd], so each image's bins are consecutive storage positions
@@ -525,7 +611,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
                 const uint8_t* pbp = (first ? p.prev0 : p.prev1) + plane_off;                                 // history plane
                 uint32_t d = dst0 + (uint32_t)buf * abuf_bytes;
                 const int* tb = slot_tbl + e0;
-                if (p.tma) {
+                if (p.tma == 1) {
                     // zero the pad slots of this plane (generic proxy), then hand the row segments to the copy engine
                     const long long tf0 = clock64();
                     if (padmask) {
@@ -609,8 +695,20 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
         int buf = 0, round = 0;
         long long tm_full = 0, tm_acc = 0;                         // per-role cycle counters (Tc3Params::timing)
         const long long tm_begin = clock64();
+        uint32_t tap_img1 = 0;                                     // bit tap: the tap reads image 1
+        for (int tap = 0; tap < p.ntaps; ++tap) tap_img1 |= (uint32_t)p.tap_img[tap] << tap;
         for (int it = 0; it < my_tiles; ++it) {
             const int accb = it & 1;
+            // tensor-box tiles: the image starts on a frame-row boundary and image 1 sits at tm_img_bytes
+            uint32_t adj0 = 0, adj1 = 0;
+            if (p.tma == 2) {
+                const T3TileGeo tg = t3_tile_geo((cta + it * ncta) * tile_pos - p.lead, p.P, Tp, p.padrow, p.slots,
+                                                 max(p.tm_delta[0], p.tm_delta[1]));
+                if (tg.box) {
+                    adj0 = (uint32_t)(tg.xoff + p.tm_delta[0]);
+                    adj1 = (uint32_t)(tg.xoff + p.tm_delta[1] + (p.tm_img_bytes >> 4) - p.slots);
+                }
+            }
             const long long tm0 = clock64();
             if (it >= 2) mbar_wait(&acc_empty[accb], ((it >> 1) - 1) & 1);
             tc_fence_after();
@@ -630,7 +728,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const Tc3Params
                         if (tap < p.ntaps) {
                             const uint32_t acc = (ph == 0 && tap == 0) ? 0u : 1u;
                             if (!(p.dbg & 4)) {
-                                const uint32_t al = alow + tapd[tap];
+                                const uint32_t al = alow + tapd[tap] + (((tap_img1 >> tap) & 1u) ? adj1 : adj0);
                                 tc_mma_f16_w(d0, al, da_hiw, wlow, db_hiw, IDESC_2N, acc);                  // a_hi x [b_hi | b_lo]
                                 tc_mma_f16_w(d0, al + a_lo_delta, da_hiw, wlow, db_hiw, IDESC_N, 1u);       // a_lo x b_hi
                                 if (p.mt == 2) {

@@ -8,6 +8,7 @@
 //   streaming: tensors are [max_streams][F][C] x 2 (ping-pong by step parity); the previous-frame tap is the
 //              other parity's buffer, so the reference's 104 conv-history tensors are simply last step's
 //              activations and never copied.  LSTM h/c are [max_streams][21], updated in place.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -21,6 +22,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/nunet_b200.h"
@@ -382,7 +384,9 @@ struct Engine {
     bool tc3_pdl = true;     // NUNET_TC3_PDL=0: plain stream order between consecutive conv kernels
     bool stream_tc3 = true;  // NUNET_STREAM_CONV=simt keeps the streaming plan on the FP32 SIMT units
     int tc3_force_mt = 0;    // NUNET_TC3_MT (experiments)
-    int tc3_tma = 1;         // NUNET_TC3_TMA=0 keeps every unit on the cp.async loaders (default: bulk copies for stride-1 units, F_in >= 32)
+    int tc3_tma = 2;         // NUNET_TC3_TMA: 0 = cp.async loaders everywhere, 1 = 1-D bulk copies per frame-row segment (F >= 32),
+                             // 2 (default) = one tensor-map box per tile image where the source order allows, else as 1
+    int tc3_box_minf = 4;    // NUNET_TC3_BOX_MINF (experiments): smallest F_conv of a unit that uses tensor-map boxes
     int tc3_tma_minf = 32;   // NUNET_TC3_TMA_MINF (experiments): smallest F_in of a stride-1 unit that uses bulk copies
     int tc3_cluster = 0;     // NUNET_TC3_CLUSTER=1: the two CTAs of a 128-channel unit form a cluster and multicast their bulk copies
                              // (one L2 read feeds both); measured neutral on B200, kept as an option
@@ -738,6 +742,51 @@ struct Engine {
         return true;
     }
 
+    // cuTensorMapEncodeTiled through the runtime's driver entry-point lookup (no link-time dependency on libcuda)
+    typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeTiledFn tc3_encode_tiled() {
+        static EncodeTiledFn fn = [] {
+            void* f = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+                f = nullptr;
+            return reinterpret_cast<EncodeTiledFn>(f);
+        }();
+        return fn;
+    }
+    // Tensor map over one sh16 source [B][T][plane][Fp positions][16 bytes]: rank 4 = {2 Fp words of 8 bytes, plane, t, b} with a
+    // box of {2 P, 1, rows, 1}; rank 5 = {16 words, Fp / 8 lines, plane, t, b} with a box of {16, P / 8, 1, rows, 1}.  Out-of-range
+    // coordinates are zero-filled, which is what makes the frequency pads and the causal time pad free.
+    std::map<std::tuple<const void*, int, int, int, int, int, int, int>, CUtensorMap> tc3_maps;
+    CUtensorMap tc3_tensor_map(const uint8_t* base, int Fp, int planes, int T, int B, size_t row_bytes, int P, int rows, int rank) {
+        const auto key = std::make_tuple((const void*)base, Fp, planes, T, B, P, rows, rank);
+        auto it = tc3_maps.find(key);
+        if (it != tc3_maps.end()) return it->second;
+        CUtensorMap m;
+        cuuint64_t dims[5], strides[4];
+        cuuint32_t box[5], es[5] = {1, 1, 1, 1, 1};
+        if (rank == 4) {
+            dims[0] = 2ull * Fp; dims[1] = planes; dims[2] = T; dims[3] = B;
+            strides[0] = (cuuint64_t)Fp * 16; strides[1] = row_bytes; strides[2] = (cuuint64_t)T * row_bytes;
+            box[0] = 2 * P; box[1] = 1; box[2] = rows; box[3] = 1;
+        } else {
+            dims[0] = 16; dims[1] = Fp / 8; dims[2] = planes; dims[3] = T; dims[4] = B;
+            strides[0] = 128; strides[1] = (cuuint64_t)Fp * 16; strides[2] = row_bytes; strides[3] = (cuuint64_t)T * row_bytes;
+            box[0] = 16; box[1] = P / 8; box[2] = 1; box[3] = rows; box[4] = 1;
+        }
+        const CUresult r = tc3_encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT64, (cuuint32_t)rank, const_cast<uint8_t*>(base), dims, strides, box,
+                                              es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS)
+            fail(NUNET_EINVAL, "cuTensorMapEncodeTiled failed (%d) for Fp=%d planes=%d T=%d B=%d P=%d rows=%d rank=%d", (int)r, Fp, planes, T, B, P,
+                 rows, rank);
+        if (tc3_maps.size() > 4096) tc3_maps.clear();
+        tc3_maps[key] = m;
+        return m;
+    }
+
     template <int N, int PC, bool LN>
     void launch_tc3_t(const Tc3Params& p, int grid, size_t smem, cudaStream_t st) {
         static bool attr_set = false;
@@ -816,12 +865,21 @@ struct Engine {
         p.padrow = (L.KT == 2) ? 1 : 0;
         p.nimg = 1;
         p.img_mul[0] = 1; p.img_add[0] = 0; p.img_mul[1] = 1; p.img_add[1] = 0;
+        // Tensor-map boxes (tma == 2) need contiguous source positions per image: stride-1 units over bin-ordered sources,
+        // stride-2 units over [even | odd] sources.  A box row is P positions: up to 128 it is one run of 8-byte words with
+        // the exact pitch; wider rows are made of 128-byte lines, so their pitch is rounded up to 8 positions.
+        const int Fp = (L.stride == 2) ? F_in / 2 : F_in;     // storage positions one image row can read
+        const int P_min = (L.KT == 1 && L.KF == 1) ? F_in : (L.stride == 1 && L.KF == 3) ? F_in + 2 : Fp + 1;
+        const bool box = tc3_tma == 2 && tc3_encode_tiled() && !p.prev0 && (L.stride == 2) == src_eo && p.F_conv >= tc3_box_minf &&
+                         (P_min <= 128 || Fp % 8 == 0);
+        const bool box_lines = box && P_min > 128;
+        const int P_pad = box_lines ? (P_min + 7) / 8 * 8 - P_min : 0;    // extra zero positions per flat row
         if (L.stride == 1 && L.KF == 3 && L.padl == 1 && L.KT == 2) {          // spconv
-            p.P = F_in + 2; p.img_add[0] = -1; p.lead = p.P + 1; p.xlo = 1;
+            p.P = F_in + 2 + P_pad; p.img_add[0] = -1; p.lead = p.P + 1; p.xlo = 1;
             for (int kt = 0; kt < 2; ++kt)
                 for (int kf = 0; kf < 3; ++kf) { p.tap_img[kt * 3 + kf] = 0; p.tap_off[kt * 3 + kf] = kt * p.P + kf; }
         } else if (L.stride == 2 && L.KF == 3 && L.padl == 1 && L.KT == 2) {   // conv
-            p.P = p.F_conv + 1; p.nimg = 2; p.lead = p.P; p.xlo = 0;
+            p.P = p.F_conv + 1 + P_pad; p.nimg = 2; p.lead = p.P; p.xlo = 0;
             p.img_mul[0] = 2; p.img_add[0] = 0; p.img_mul[1] = 2; p.img_add[1] = -1;
             for (int kt = 0; kt < 2; ++kt) {
                 p.tap_img[kt * 3 + 0] = 1; p.tap_off[kt * 3 + 0] = kt * p.P;
@@ -831,11 +889,11 @@ struct Engine {
         } else if (L.KT == 1 && L.KF == 1) {                                   // inconv 1x1
             p.P = F_in; p.lead = 0; p.xlo = 0; p.tap_img[0] = 0; p.tap_off[0] = 0;
         } else if (L.KT == 1 && L.KF == 3 && L.stride == 2 && L.padl == 0) {   // down_sampling
-            p.P = p.F_conv + 1; p.nimg = 2; p.lead = 0; p.xlo = 0;
+            p.P = p.F_conv + 1 + P_pad; p.nimg = 2; p.lead = 0; p.xlo = 0;
             p.img_mul[0] = 2; p.img_add[0] = 0; p.img_mul[1] = 2; p.img_add[1] = 1;
             p.tap_img[0] = 0; p.tap_off[0] = 0; p.tap_img[1] = 1; p.tap_off[1] = 0; p.tap_img[2] = 0; p.tap_off[2] = 1;
         } else if (L.KT == 1 && L.KF == 2 && L.stride == 1 && L.padl == 1) {   // up_sampling o inconv
-            p.P = F_in + 1; p.img_add[0] = -1; p.lead = 1; p.xlo = 1;
+            p.P = F_in + 1 + P_pad; p.img_add[0] = -1; p.lead = 1; p.xlo = 1;
             p.tap_img[0] = 0; p.tap_off[0] = 0; p.tap_img[1] = 0; p.tap_off[1] = 1;
         } else {
             fail(NUNET_EINVAL, "conv_tc3: unsupported unit geometry");
@@ -845,7 +903,25 @@ struct Engine {
         // bulk-copy (TMA) row segments need contiguous source bins: stride-1 units over bin-ordered sources, stride-2 units
         // over [even | odd] sources; <= 32 (16 per image) frame rows per tile
         p.tma = (tc3_tma && !p.prev0 && ((p.nimg == 1 && !src_eo && F_in >= tc3_tma_minf) || (p.nimg == 2 && src_eo && p.F_conv >= 32))) ? 1 : 0;
-        p.cluster = (p.tma && L.nhalf3 == 2 && tc3_cluster) ? 1 : 0;
+        int box_dmax = 0;
+        if (box) {
+            p.tma = 2;
+            p.tm_rank = box_lines ? 5 : 4;
+            int cmin = 0;
+            for (int i = 0; i < p.nimg; ++i) {
+                const int par = (L.stride == 2) ? (p.img_add[i] & 1) : 0;
+                p.tm_par[i] = par;
+                p.tm_delta[i] = (L.stride == 2) ? (p.img_add[i] - par) / 2 : p.img_add[i];     // a_i: storage position read by x = 0
+                cmin = std::min(cmin, p.tm_delta[i]);
+            }
+            for (int i = 0; i < p.nimg; ++i) {
+                p.tm_c[i] = box_lines ? (cmin < 0 ? -8 : 0) : p.tm_delta[i];
+                p.tm_delta[i] -= p.tm_c[i];
+                box_dmax = std::max(box_dmax, p.tm_delta[i]);
+                if (p.tm_c[i] + p.P < Fp) fail(NUNET_EINVAL, "conv_tc3: box row does not cover the source row");
+            }
+        }
+        p.cluster = (p.tma == 1 && L.nhalf3 == 2 && tc3_cluster) ? 1 : 0;
         p.nphase = (L.CA + L.CB) / T3_KCH;
         p.nhalf = L.nhalf3;
         p.w_half_bytes = p.nphase * p.ntaps * L.N3 * 64;
@@ -859,7 +935,14 @@ struct Engine {
         auto geometry = [&](int mt, int& slots, int& plane_bytes, size_t& abuf) {
             slots = mt * 128 + maxoff;
             int plane16 = (p.nimg * slots + 31) / 32 * 32;   // both images + the loaders' round-up padding
-            while (plane16 % 8 != 2) ++plane16;
+            if (box) {   // whole frame rows per image, every image and plane on a 128-byte boundary (tensor-copy destination)
+                const int rows = (p.P - 1 + box_dmax + slots - 1) / p.P + 1;
+                const int img16 = (rows * p.P + 7) / 8 * 8;
+                plane16 = std::max(plane16, p.nimg * img16);
+                if (rows > 256) return 0;
+            } else {
+                while (plane16 % 8 != 2) ++plane16;
+            }
             plane_bytes = plane16 * 16;
             abuf = (size_t)4 * plane_bytes;
             if (p.nimg * slots > T3_TBL - 32 || fixed + 2 * abuf > limit) return 0;
@@ -878,6 +961,14 @@ struct Engine {
         p.nabuf = two ? nb2 : nb1;
         const size_t smem = fixed + (size_t)p.nabuf * (two ? abuf2 : abuf1);
         if (!ok) fail(NUNET_EINVAL, "conv_tc3: unit does not fit shared memory");
+        if (box) {
+            p.tm_rows = (p.P - 1 + box_dmax + p.slots - 1) / p.P + 1;
+            p.tm_box_bytes = p.tm_rows * p.P * 16;
+            p.tm_img_bytes = (p.tm_rows * p.P + 7) / 8 * 8 * 16;
+            const int planes = (src_eo ? 2 : 1) * (L.CA / 4);          // hi | lo  x  C/8 chunks (x parity halves)
+            p.tm_map[0] = tc3_tensor_map(p.src0, Fp, planes, T, B, (size_t)F_in * L.CA * 4, p.P, p.tm_rows, p.tm_rank);
+            if (p.src1) p.tm_map[1] = tc3_tensor_map(p.src1, Fp, planes, T, B, (size_t)F_in * L.CA * 4, p.P, p.tm_rows, p.tm_rank);
+        }
         p.ntiles = (int)((total + p.mt * 128 - 1) / (p.mt * 128));
         const int grid = std::max(1, std::min(p.ntiles, num_sms / p.nhalf)) * p.nhalf;
         const bool ln = (L.epi != EPI_BIAS);
@@ -1525,6 +1616,7 @@ int nunet_create(const nunet_config* cfg, const void* blob, size_t blob_bytes, n
         }
         if (const char* c = getenv("NUNET_TC3_TMA")) E.tc3_tma = atoi(c);
         if (const char* c = getenv("NUNET_TC3_CLUSTER")) E.tc3_cluster = atoi(c);
+        if (const char* c = getenv("NUNET_TC3_BOX_MINF")) E.tc3_box_minf = atoi(c);
         if (const char* c = getenv("NUNET_TC3_TMA_MINF")) E.tc3_tma_minf = std::max(8, atoi(c));
         if (const char* c = getenv("NUNET_TC3_MT")) E.tc3_force_mt = atoi(c);
         if (const char* c = getenv("NUNET_STREAM_CONV")) E.stream_tc3 = strcmp(c, "simt") != 0;
