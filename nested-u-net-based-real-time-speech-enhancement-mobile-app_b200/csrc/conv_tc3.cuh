@@ -102,9 +102,9 @@ struct Tc3Params {
     // plane (the frequency pads) and rows outside the clip (the causal time pad, the tail) are zero-filled by the copy
     // engine.  The image then starts on a row boundary, so the MMA adds (q0 mod P) + tm_delta[img] to its tap offsets.
     // Tiles that straddle two clips fall back to the slot-table cp.async loader.
-    int tm_rank;           // 4: {2 x 8-byte words per position run, plane, t, b}; 5: {16 words = 8 positions, run, plane, t, b}
+    int tm_rank;           // 4: {8-byte words of a plane row, plane, t, b}; 5: {words of a 128-byte line | of a position, line | position, plane, t, b}
     int tm_rows;           // frame rows per box
-    int tm_c[2];           // first storage position of a box row per image (<= 0), in positions
+    int tm_c[2];           // box start per image: coordinate 0 (rank 4) / coordinate 1 (rank 5) of the first position of a box row
     int tm_delta[2];       // image index of flat position (rho_a, x) is x + tm_delta[img]
     int tm_par[2];         // [even | odd] sources: which parity half image img reads
     int tm_img_bytes;      // byte offset of image 1 inside a plane (128-byte multiple)
@@ -521,9 +521,9 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
                                 for (int img = 0; img < p.nimg; ++img) {
                                     const int pl = p.src_eo ? 2 * plane + p.tm_par[img] : plane;
                                     if (p.tm_rank == 4)
-                                        tensor_g2s_4d(dstp + (size_t)img * p.tm_img_bytes, map, 2 * p.tm_c[img], pl, tg.t, tg.b, &a_full[buf]);
+                                        tensor_g2s_4d(dstp + (size_t)img * p.tm_img_bytes, map, p.tm_c[img], pl, tg.t, tg.b, &a_full[buf]);
                                     else
-                                        tensor_g2s_5d(dstp + (size_t)img * p.tm_img_bytes, map, 0, p.tm_c[img] >> 3, pl, tg.t, tg.b, &a_full[buf]);
+                                        tensor_g2s_5d(dstp + (size_t)img * p.tm_img_bytes, map, 0, p.tm_c[img], pl, tg.t, tg.b, &a_full[buf]);
                                 }
                             }
                             mbar_arrive_n(&a_full[buf], 32);
@@ -728,12 +728,14 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
                         if (tap < p.ntaps) {
                             const uint32_t acc = (ph == 0 && tap == 0) ? 0u : 1u;
                             if (!(p.dbg & 4)) {
-                                const uint32_t al = alow + tapd[tap] + (((tap_img1 >> tap) & 1u) ? adj1 : adj0);
-                                tc_mma_f16_w(d0, al, da_hiw, wlow, db_hiw, IDESC_2N, acc);                  // a_hi x [b_hi | b_lo]
-                                tc_mma_f16_w(d0, al + a_lo_delta, da_hiw, wlow, db_hiw, IDESC_N, 1u);       // a_lo x b_hi
-                                if (p.mt == 2) {
-                                    tc_mma_f16_w(d0 + 2 * N, al + 128, da_hiw, wlow, db_hiw, IDESC_2N, acc);
-                                    tc_mma_f16_w(d0 + 2 * N, al + 128 + a_lo_delta, da_hiw, wlow, db_hiw, IDESC_N, 1u);
+                                uint32_t al = alow + tapd[tap] + (((tap_img1 >> tap) & 1u) ? adj1 : adj0);
+                                if (p.dbg & 16) al &= ~7u;
+                                // the two tiles' accumulators alternate, so back-to-back MMAs never chain on one accumulator
+                                tc_mma_f16_w(d0, al, da_hiw, wlow, db_hiw, IDESC_2N, acc);                                   // a_hi x [b_hi | b_lo]
+                                if (p.mt == 2) tc_mma_f16_w(d0 + 2 * N, al + 128, da_hiw, wlow, db_hiw, IDESC_2N, acc);
+                                if (!(p.dbg & 64)) {
+                                    tc_mma_f16_w(d0, al + a_lo_delta, da_hiw, wlow, db_hiw, IDESC_N, 1u);                    // a_lo x b_hi
+                                    if (p.mt == 2) tc_mma_f16_w(d0 + 2 * N, al + 128 + a_lo_delta, da_hiw, wlow, db_hiw, IDESC_N, 1u);
                                 }
                             }
                             wlow += N * 4;   // next (phase, tap) stage: N * 64 bytes

@@ -386,6 +386,7 @@ struct Engine {
     int tc3_force_mt = 0;    // NUNET_TC3_MT (experiments)
     int tc3_tma = 2;         // NUNET_TC3_TMA: 0 = cp.async loaders everywhere, 1 = 1-D bulk copies per frame-row segment (F >= 32),
                              // 2 (default) = one tensor-map box per tile image where the source order allows, else as 1
+    int tc3_box_strided = 1; // NUNET_TC3_BOX_STRIDED=0 (experiments): stride-2 units over bin-ordered sources stay on the slot-table loader
     int tc3_box_minf = 4;    // NUNET_TC3_BOX_MINF (experiments): smallest F_conv of a unit that uses tensor-map boxes
     int tc3_tma_minf = 32;   // NUNET_TC3_TMA_MINF (experiments): smallest F_in of a stride-1 unit that uses bulk copies
     int tc3_cluster = 0;     // NUNET_TC3_CLUSTER=1: the two CTAs of a 128-channel unit form a cluster and multicast their bulk copies
@@ -756,12 +757,15 @@ struct Engine {
         }();
         return fn;
     }
-    // Tensor map over one sh16 source [B][T][plane][Fp positions][16 bytes]: rank 4 = {2 Fp words of 8 bytes, plane, t, b} with a
-    // box of {2 P, 1, rows, 1}; rank 5 = {16 words, Fp / 8 lines, plane, t, b} with a box of {16, P / 8, 1, rows, 1}.  Out-of-range
-    // coordinates are zero-filled, which is what makes the frequency pads and the causal time pad free.
+    // Tensor map over one sh16 source [B][T][plane][Fp positions][16 bytes].  kind 0: rank 4 = {2 Fp words of 8 bytes, plane, t, b}
+    // with a box of {2 P, 1, rows, 1}; kind 1: rank 5 = {16 words, Fp / 8 lines, plane, t, b} with a box of {16, P / 8, 1, rows, 1};
+    // kind 2: rank 5 = {2 words, Fp positions, plane, t, b} traversed with a stride of two positions, box {2, 2 P, 1, rows, 1}
+    // (P positions land).  Out-of-range coordinates are zero-filled, which is what makes the frequency pads and the causal
+    // time pad free.
     std::map<std::tuple<const void*, int, int, int, int, int, int, int>, CUtensorMap> tc3_maps;
-    CUtensorMap tc3_tensor_map(const uint8_t* base, int Fp, int planes, int T, int B, size_t row_bytes, int P, int rows, int rank) {
-        const auto key = std::make_tuple((const void*)base, Fp, planes, T, B, P, rows, rank);
+    CUtensorMap tc3_tensor_map(const uint8_t* base, int Fp, int planes, int T, int B, size_t row_bytes, int P, int rows, int kind) {
+        const int rank = kind == 0 ? 4 : 5;
+        const auto key = std::make_tuple((const void*)base, Fp, planes, T, B, P, rows, kind);
         auto it = tc3_maps.find(key);
         if (it != tc3_maps.end()) return it->second;
         CUtensorMap m;
@@ -771,10 +775,15 @@ struct Engine {
             dims[0] = 2ull * Fp; dims[1] = planes; dims[2] = T; dims[3] = B;
             strides[0] = (cuuint64_t)Fp * 16; strides[1] = row_bytes; strides[2] = (cuuint64_t)T * row_bytes;
             box[0] = 2 * P; box[1] = 1; box[2] = rows; box[3] = 1;
-        } else {
+        } else if (kind == 1) {
             dims[0] = 16; dims[1] = Fp / 8; dims[2] = planes; dims[3] = T; dims[4] = B;
             strides[0] = 128; strides[1] = (cuuint64_t)Fp * 16; strides[2] = row_bytes; strides[3] = (cuuint64_t)T * row_bytes;
             box[0] = 16; box[1] = P / 8; box[2] = 1; box[3] = rows; box[4] = 1;
+        } else {
+            dims[0] = 2; dims[1] = Fp; dims[2] = planes; dims[3] = T; dims[4] = B;
+            strides[0] = 16; strides[1] = (cuuint64_t)Fp * 16; strides[2] = row_bytes; strides[3] = (cuuint64_t)T * row_bytes;
+            box[0] = 2; box[1] = 2 * P; box[2] = 1; box[3] = rows; box[4] = 1;
+            es[1] = 2;
         }
         const CUresult r = tc3_encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT64, (cuuint32_t)rank, const_cast<uint8_t*>(base), dims, strides, box,
                                               es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -839,7 +848,8 @@ struct Engine {
 
     // Split-half tensor-core path (offline plans with sh16 tensors): every conv unit of the topology is eligible.
     void launch_conv_tc3(const ConvLayer& L, const float* a_cur, const float* b_cur, const float* a_prev, const float* b_prev,
-                         float* out, int B, int T, int F_in, bool src_eo, bool out_eo, cudaStream_t st) {
+                         float* out, int B, int T, int F_in, bool src_eo, bool out_eo, cudaStream_t st, bool allow_box = true,
+                         bool* probe_two = nullptr) {
         Tc3Params p{};
         if (a_prev && T != 1) fail(NUNET_EINVAL, "conv_tc3: a carried history row needs T = 1");
         p.prev0 = (L.KT == 2) ? reinterpret_cast<const uint8_t*>(a_prev) : nullptr;
@@ -870,8 +880,11 @@ struct Engine {
         // the exact pitch; wider rows are made of 128-byte lines, so their pitch is rounded up to 8 positions.
         const int Fp = (L.stride == 2) ? F_in / 2 : F_in;     // storage positions one image row can read
         const int P_min = (L.KT == 1 && L.KF == 1) ? F_in : (L.stride == 1 && L.KF == 3) ? F_in + 2 : Fp + 1;
-        const bool box = tc3_tma == 2 && tc3_encode_tiled() && !p.prev0 && (L.stride == 2) == src_eo && p.F_conv >= tc3_box_minf &&
-                         (P_min <= 128 || Fp % 8 == 0);
+        // Stride-2 units over bin-ordered sources (the inner convs of a sub-U-Net, whose inputs also feed stride-1 skips) use
+        // a traversal stride of two positions instead: the box dimension is 2 P positions, so P <= 128.
+        const bool box_strided = L.stride == 2 && !src_eo;
+        const bool box = allow_box && tc3_tma == 2 && tc3_encode_tiled() && !p.prev0 && (L.stride == 2 || !src_eo) && p.F_conv >= tc3_box_minf &&
+                         (P_min <= 128 || (Fp % 8 == 0 && !box_strided)) && (!box_strided || tc3_box_strided);
         const bool box_lines = box && P_min > 128;
         const int P_pad = box_lines ? (P_min + 7) / 8 * 8 - P_min : 0;    // extra zero positions per flat row
         if (L.stride == 1 && L.KF == 3 && L.padl == 1 && L.KT == 2) {          // spconv
@@ -906,19 +919,20 @@ struct Engine {
         int box_dmax = 0;
         if (box) {
             p.tma = 2;
-            p.tm_rank = box_lines ? 5 : 4;
+            p.tm_rank = (box_lines || box_strided) ? 5 : 4;
             int cmin = 0;
             for (int i = 0; i < p.nimg; ++i) {
-                const int par = (L.stride == 2) ? (p.img_add[i] & 1) : 0;
+                const int par = (L.stride == 2 && src_eo) ? (p.img_add[i] & 1) : 0;
                 p.tm_par[i] = par;
-                p.tm_delta[i] = (L.stride == 2) ? (p.img_add[i] - par) / 2 : p.img_add[i];     // a_i: storage position read by x = 0
+                p.tm_delta[i] = (L.stride == 2 && src_eo) ? (p.img_add[i] - par) / 2 : p.img_add[i];     // a_i: storage position read by x = 0
                 cmin = std::min(cmin, p.tm_delta[i]);
             }
             for (int i = 0; i < p.nimg; ++i) {
-                p.tm_c[i] = box_lines ? (cmin < 0 ? -8 : 0) : p.tm_delta[i];
-                p.tm_delta[i] -= p.tm_c[i];
+                const int c = box_lines ? (cmin < 0 ? -8 : 0) : p.tm_delta[i];     // first storage position of a box row
+                p.tm_delta[i] -= c;
                 box_dmax = std::max(box_dmax, p.tm_delta[i]);
-                if (p.tm_c[i] + p.P < Fp) fail(NUNET_EINVAL, "conv_tc3: box row does not cover the source row");
+                if (c + (box_strided ? 2 : 1) * p.P < (box_strided ? F_in : Fp)) fail(NUNET_EINVAL, "conv_tc3: box row does not cover the source row");
+                p.tm_c[i] = box_lines ? c / 8 : box_strided ? c : 2 * c;
             }
         }
         p.cluster = (p.tma == 1 && L.nhalf3 == 2 && tc3_cluster) ? 1 : 0;
@@ -932,11 +946,17 @@ struct Engine {
         const size_t limit = 227 * 1024;
         // tile = mt x 128 positions; prefer two tiles per iteration unless that leaves a ring of fewer than three
         // image buffers while one tile would allow it (the ring depth is what hides the HBM latency)
+        // a box image starts on a frame-row boundary, (tile * mt * 128 - lead) mod P positions before the tile's first one
+        auto box_xoff_max = [&](int mt) {
+            int g = mt * 128, b = p.P;
+            while (b) { const int r = g % b; g = b; b = r; }
+            return p.P - g + (g - p.lead % g) % g;
+        };
         auto geometry = [&](int mt, int& slots, int& plane_bytes, size_t& abuf) {
             slots = mt * 128 + maxoff;
             int plane16 = (p.nimg * slots + 31) / 32 * 32;   // both images + the loaders' round-up padding
             if (box) {   // whole frame rows per image, every image and plane on a 128-byte boundary (tensor-copy destination)
-                const int rows = (p.P - 1 + box_dmax + slots - 1) / p.P + 1;
+                const int rows = (box_xoff_max(mt) + box_dmax + slots - 1) / p.P + 1;
                 const int img16 = (rows * p.P + 7) / 8 * 8;
                 plane16 = std::max(plane16, p.nimg * img16);
                 if (rows > 256) return 0;
@@ -955,6 +975,20 @@ struct Engine {
         bool two = nb2 >= 2;   // larger tiles beat a deeper ring (measured): per-tile overheads dominate
         if (tc3_force_mt == 1 && nb1 >= 2) two = false;
         if (tc3_force_mt == 2 && nb2 >= 2) two = true;
+        if (probe_two) {
+            *probe_two = two;
+            return;
+        }
+        if (box && !two) {
+            // whole-row boxes are larger than the exact images of the row-segment loader: when only the latter fits two tiles
+            // per iteration, it wins (measured: 128-channel stride-2 unit at 128 bins, 2.3 ms against 3.3 ms)
+            bool two_rows = false;
+            launch_conv_tc3(L, a_cur, b_cur, a_prev, b_prev, out, B, T, F_in, src_eo, out_eo, st, false, &two_rows);
+            if (two_rows) {
+                launch_conv_tc3(L, a_cur, b_cur, a_prev, b_prev, out, B, T, F_in, src_eo, out_eo, st, false);
+                return;
+            }
+        }
         p.mt = two ? 2 : 1;
         p.slots = two ? slots2 : slots1;
         p.plane_bytes = two ? plane2 : plane1;
@@ -962,12 +996,14 @@ struct Engine {
         const size_t smem = fixed + (size_t)p.nabuf * (two ? abuf2 : abuf1);
         if (!ok) fail(NUNET_EINVAL, "conv_tc3: unit does not fit shared memory");
         if (box) {
-            p.tm_rows = (p.P - 1 + box_dmax + p.slots - 1) / p.P + 1;
+            p.tm_rows = (box_xoff_max(p.mt) + box_dmax + p.slots - 1) / p.P + 1;
             p.tm_box_bytes = p.tm_rows * p.P * 16;
             p.tm_img_bytes = (p.tm_rows * p.P + 7) / 8 * 8 * 16;
             const int planes = (src_eo ? 2 : 1) * (L.CA / 4);          // hi | lo  x  C/8 chunks (x parity halves)
-            p.tm_map[0] = tc3_tensor_map(p.src0, Fp, planes, T, B, (size_t)F_in * L.CA * 4, p.P, p.tm_rows, p.tm_rank);
-            if (p.src1) p.tm_map[1] = tc3_tensor_map(p.src1, Fp, planes, T, B, (size_t)F_in * L.CA * 4, p.P, p.tm_rows, p.tm_rank);
+            const int kind = box_strided ? 2 : box_lines ? 1 : 0;
+            const int Fm = box_strided ? F_in : Fp;
+            p.tm_map[0] = tc3_tensor_map(p.src0, Fm, planes, T, B, (size_t)F_in * L.CA * 4, p.P, p.tm_rows, kind);
+            if (p.src1) p.tm_map[1] = tc3_tensor_map(p.src1, Fm, planes, T, B, (size_t)F_in * L.CA * 4, p.P, p.tm_rows, kind);
         }
         p.ntiles = (int)((total + p.mt * 128 - 1) / (p.mt * 128));
         const int grid = std::max(1, std::min(p.ntiles, num_sms / p.nhalf)) * p.nhalf;
@@ -1617,6 +1653,7 @@ int nunet_create(const nunet_config* cfg, const void* blob, size_t blob_bytes, n
         if (const char* c = getenv("NUNET_TC3_TMA")) E.tc3_tma = atoi(c);
         if (const char* c = getenv("NUNET_TC3_CLUSTER")) E.tc3_cluster = atoi(c);
         if (const char* c = getenv("NUNET_TC3_BOX_MINF")) E.tc3_box_minf = atoi(c);
+        if (const char* c = getenv("NUNET_TC3_BOX_STRIDED")) E.tc3_box_strided = atoi(c);
         if (const char* c = getenv("NUNET_TC3_TMA_MINF")) E.tc3_tma_minf = std::max(8, atoi(c));
         if (const char* c = getenv("NUNET_TC3_MT")) E.tc3_force_mt = atoi(c);
         if (const char* c = getenv("NUNET_STREAM_CONV")) E.stream_tc3 = strcmp(c, "simt") != 0;
