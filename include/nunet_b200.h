@@ -120,7 +120,10 @@ int nunet_stream_step_wav_host(nunet_engine* h, const float* hop, int S, float* 
 /* History wire format: the tensors of the reference signature (converter_proposed.py:26-187 inputs,
  * :729-867 outputs), addressed by their reference names without the _prev/_cur infix, e.g.
  * "msfe6_ee_1" <-> msfe6_ee_prev1/msfe6_ee_cur1, "msfe6_en_h", "state_c".
- * buf is a HOST buffer of nunet_state_numel(name) floats. */
+ * buf is a HOST buffer of nunet_state_numel(name) floats.
+ * Not enumerated by nunet_state_count/name but accepted by numel/export/import, for stream checkpoints: the frame
+ * loop's "in_buffer" and "out_buffer" (512 floats each, interpreter_proposed.py:30-31) and, with
+ * stream_ctfa_history, the attention rings "ctfa_ring<i>" (32 x 64 floats, oldest frame first). */
 int nunet_state_count(nunet_engine* h);
 int nunet_state_name(nunet_engine* h, int index, char* name_out, int cap);
 int nunet_state_numel(nunet_engine* h, const char* name);

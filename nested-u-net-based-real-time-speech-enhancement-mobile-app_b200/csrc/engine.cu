@@ -1518,9 +1518,41 @@ struct Engine {
         if (s.ddb_k) return s.ddb_d * (s.a->F / DDB_RING) * s.a->C * s.ddb_k;
         return s.a->F * (s.a->C + (s.b ? s.b->C : 0));
     }
+    // Framing state that is not part of the signature's tensor list but belongs to a stream checkpoint: the analysis
+    // window `in_buffer` and the overlap-add accumulator `out_buffer` of the frame loop (interpreter_proposed.py:30-31),
+    // and, when the engine keeps real attention history (stream_ctfa_history), the 32-frame rings "ctfa_ring<i>"
+    // (oldest frame first).  Returns the element count, or -1 for other names.
+    int extra_state(const std::string& name, const Ten** ten, int* ring) const {
+        *ring = 0;
+        if (name == "in_buffer") { *ten = s_inbuf; return s_inbuf ? NFFT : -1; }
+        if (name == "out_buffer") { *ten = s_outbuf; return s_outbuf ? NFFT : -1; }
+        if (name.rfind("ctfa_ring", 0) == 0) {
+            const int i = atoi(name.c_str() + 9);
+            if (i < 0 || i >= (int)stream.rings.size() || name != "ctfa_ring" + std::to_string(i)) return -1;
+            *ten = stream.rings[i];
+            *ring = 1;
+            return CTFA_WINDOW * 64;
+        }
+        return -1;
+    }
     void state_xfer(int sid, const std::string& name, float* buf, bool to_host) {
         if (!stream.arena) fail(NUNET_EINVAL, "streaming path disabled (max_streams = 0)");
         if (sid < 0 || sid >= stream.cap) fail(NUNET_EINVAL, "stream id out of range");
+        const Ten* xt = nullptr;
+        int xring = 0;
+        const int xn = extra_state(name, &xt, &xring);
+        if (xn > 0) {
+            CUDA_OK(cudaDeviceSynchronize());
+            float* dev = stream.cur(xt, 0) + (size_t)sid * xn;
+            for (int r = 0; r < (xring ? CTFA_WINDOW : 1); ++r) {
+                // ring row r (oldest first) lives in slot (steps + r) mod 32: slot steps mod 32 is overwritten next
+                const int slot = xring ? ((stream_steps + r) & (CTFA_WINDOW - 1)) : 0;
+                const size_t n = xring ? 64 : (size_t)xn;
+                if (to_host) CUDA_OK(cudaMemcpy(buf + (size_t)r * n, dev + (size_t)slot * n, n * sizeof(float), cudaMemcpyDeviceToHost));
+                else CUDA_OK(cudaMemcpy(dev + (size_t)slot * n, buf + (size_t)r * n, n * sizeof(float), cudaMemcpyHostToDevice));
+            }
+            return;
+        }
         const Plan::StateRef* s = find_state(name);
         if (!s) fail(NUNET_ESTATE, "unknown state tensor '%s'", name.c_str());
         CUDA_OK(cudaDeviceSynchronize());
@@ -1787,6 +1819,10 @@ int nunet_state_numel(nunet_engine* h, const char* name) {
     int n = 0;
     int rc = guarded([&] {
         if (!h || !name) fail(NUNET_EINVAL, "null argument");
+        const Ten* xt = nullptr;
+        int xring = 0;
+        n = h->e.extra_state(name, &xt, &xring);
+        if (n > 0) return;
         const Plan::StateRef* s = h->e.find_state(name);
         if (!s) fail(NUNET_ESTATE, "unknown state tensor '%s'", name);
         n = h->e.state_numel(*s);

@@ -44,6 +44,7 @@ class NunetEngine:
                           DC_MODES[dc_mode], int(bool(stream_ctfa_history)), 0)
         self.max_frames, self.max_streams = int(max_frames), int(max_streams)
         self.ctfa_mode, self.dc_mode = ctfa_mode, dc_mode
+        self.variant, self.stream_ctfa_history = int(variant), bool(stream_ctfa_history)
         buf = (C.c_char * len(blob)).from_buffer_copy(blob)
         check(self._L.nunet_create(C.byref(cfg), buf, len(blob), C.byref(self._h)))
 
