@@ -60,8 +60,9 @@ constexpr int T3_THREADS = 32 * (T3_EPI_WARPS + T3_LD_WARPS + 1);
 constexpr int T3_MAXNB = 8;         // image ring depth
 constexpr int T3_TBL = 1024;        // slot table entries (nimg*slots <= 1024)
 constexpr int T3_PREV_FLAG = 1 << 30;   // slot-table entry: read the history tensor (streaming) instead of the source
-constexpr int T3_PAR_OFF = 256;     // bias / gamma / beta staged as floats: 3 x 64
-constexpr int T3_TBL_OFF = 1024;
+constexpr int T3_PEER_OFF = 256;    // pair mode: barriers the partner CTA arrives on (peer_full[T3_MAXNB], peer_acc_empty[2])
+constexpr int T3_PAR_OFF = 512;     // bias[128] | gamma[64] | beta[64] staged as floats
+constexpr int T3_TBL_OFF = 2048;
 constexpr int T3_FIXED_BYTES = T3_TBL_OFF + T3_TBL * 4;
 
 struct Tc3Params {
@@ -95,6 +96,11 @@ struct Tc3Params {
     int w_half_bytes;      // nphase * ntaps * N * 64
     int fence_mode;        // experiments only: 2 = skip the consumer-side fence.proxy.async
     int src_eo, out_eo;    // bins of the sources / of the output are stored [even | odd] inside each plane
+    int pair;              // 1: 2-CTA clusters issue cta_group::2 MMAs (M = 256): CTA r of a cluster owns one 128-position tile and
+                           // holds the weights of channel half r; the leader's MMA reads both CTAs' images and weight halves.  The
+                           // two tiles of a pair lie pair_m tiles (a whole number of frame rows) apart, so both images start at the
+                           // same offset inside their first frame row and one A descriptor serves both CTAs.
+    int pair_m;            // P / gcd(P, 128)
     int cluster;           // 1: launched as 2-CTA clusters (the two halves of a 128-channel unit): bulk copies are multicast
     int tma;               // 1: row segments move with 1-D bulk copies; 2: whole tile images move as tensor-map boxes (see tm*)
     // tma == 2: a tile whose frame rows lie inside one clip is fetched with ONE cp.async.bulk.tensor per (plane, image):
@@ -187,6 +193,35 @@ __device__ __forceinline__ T3TileGeo t3_tile_geo(int qa, int P, int Tp, int padr
     g.t = tp - padrow;
     g.box = (rho_a >= 0 && tp + need <= Tp) ? 1 : 0;
     return g;
+}
+// ---- CTA-pair (cta_group::2) helpers
+// Arrive on the same barrier of CTA `cta` of the cluster.  Relaxed: what the leader consumes afterwards was written by the copy
+// engine / read by tcgen05.ld and is ordered by the local barrier the forwarding thread waited on; a release at cluster scope
+// costs ~1000 cycles per arrival (measured) and would serialise the forwarding loop.
+__device__ __forceinline__ void mbar_arrive_peer(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {   // completion of the pair's MMAs arrives on both CTAs' barrier
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_w2(uint32_t d_tmem, uint32_t a_low, uint32_t a_high, uint32_t b_low, uint32_t b_high,
+                                              uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_low), "r"(a_high), "r"(b_low), "r"(b_high), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ uint32_t elect_one() {
     uint32_t pred;
@@ -320,7 +355,8 @@ __device__ __forceinline__ void split8p(const float2* v, uint4& hi, uint4& lo) {
 
 // N: conv channels of this CTA (32 / 64); PC: channels per OUTPUT pixel (N, or 32 for the 64-column sub-pixel
 // shuffle that makes two pixels); LN: LayerNorm + PReLU over each PC-channel group (false: bias only).
-template <int N, int PC, bool LN>
+// PAIR: the cta_group::2 variant (must be launched as 2-CTA clusters; Tc3Params::pair set)
+template <int N, int PC, bool LN, bool PAIR = false>
 __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_constant__ Tc3Params p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
@@ -330,6 +366,8 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
     uint64_t* acc_empty = acc_full + 2;          // [2]
     uint64_t* w_full = acc_empty + 2;            // [1]
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 24);
+    uint64_t* peer_full = reinterpret_cast<uint64_t*>(smem_raw + T3_PEER_OFF);   // [T3_MAXNB] pair mode, leader CTA: the partner's image landed
+    uint64_t* peer_acc_empty = peer_full + T3_MAXNB;                             // [2] pair mode, leader CTA: the partner drained its accumulator
     float* par_s = reinterpret_cast<float*>(smem_raw + T3_PAR_OFF);   // bias[64] | gamma[64] | beta[64]
     int* slot_tbl = reinterpret_cast<int*>(smem_raw + T3_TBL_OFF);
     uint8_t* wsm = smem_raw + T3_FIXED_BYTES;
@@ -349,33 +387,51 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
         for (int i = 0; i < T3_MAXNB; ++i) {
             mbar_init(&a_full[i], p.tma == 1 ? T3_LD_WARPS : T3_LD_THREADS);   // bulk rows: one arrival per loader warp (+ tx bytes)
             mbar_init(&a_empty[i], p.cluster ? 2 : 1);     // cluster: both CTAs' MMAs must be done before either refills
+            mbar_init(&peer_full[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&acc_full[i], 1);
-            mbar_init(&acc_empty[i], 128 * p.mt);
+            mbar_init(&acc_empty[i], PAIR ? 256 : 128 * p.mt);   // pair: both warp groups drain every tile (one channel half each)
+            mbar_init(&peer_acc_empty[i], 1);
         }
         mbar_init(w_full, 1);
         fence_barrier_init();
     }
-    if (threadIdx.x < 64) {
-        par_s[threadIdx.x] = (threadIdx.x < N) ? __ldg(p.bias + half * N + threadIdx.x) : 0.f;
-        par_s[64 + threadIdx.x] = (LN && threadIdx.x < PC) ? __ldg(p.gamma + threadIdx.x) : 0.f;
-        par_s[128 + threadIdx.x] = (LN && threadIdx.x < PC) ? __ldg(p.beta + threadIdx.x) : 0.f;
+    if (threadIdx.x < 128) {   // pair mode stages the bias of both channel halves
+        const int nb = PAIR ? 2 * N : N;
+        par_s[threadIdx.x] = ((int)threadIdx.x < nb) ? __ldg(p.bias + (PAIR ? 0 : half * N) + threadIdx.x) : 0.f;
+        if (threadIdx.x < 64) {
+            par_s[128 + threadIdx.x] = (LN && threadIdx.x < PC) ? __ldg(p.gamma + threadIdx.x) : 0.f;
+            par_s[192 + threadIdx.x] = (LN && threadIdx.x < PC) ? __ldg(p.beta + threadIdx.x) : 0.f;
+        }
     }
     if (warp == MMA_WARP) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (p.cluster) cluster_sync_all();     // the partner's barriers exist before anything is multicast to them
+    if (p.cluster || PAIR) cluster_sync_all();     // the partner's barriers exist before anything is multicast to them
     const uint32_t tmem_base = *tmem_ptr_s;
 
     const int Tp = p.T + p.padrow;
     const int cta = (int)blockIdx.x / p.nhalf, ncta = (int)gridDim.x / p.nhalf;
     const int my_tiles = (cta < p.ntiles) ? (p.ntiles - cta + ncta - 1) / ncta : 0;
     const int tile_pos = p.mt * 128;
+    // first flat position of the tile CTA-rank `r` works on in iteration `it`.  Pair mode: cluster unit u = (block, j) maps to
+    // the 128-position tiles block * 2m + j (rank 0) and block * 2m + j + m (rank 1), m * 128 = a whole number of frame rows.
+    auto tile_q = [&](int it, int r) {
+        const int u = cta + it * ncta;
+        if (!PAIR) return u * tile_pos;
+        const int blk = u / p.pair_m, j = u - blk * p.pair_m;
+        return (blk * 2 * p.pair_m + j + r * p.pair_m) * 128;
+    };
 
     if (warp < T3_EPI_WARPS) {
         // ================================================================= epilogue
@@ -394,25 +450,27 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
         const long long t_begin = clock64();
         for (int it = 0; it < my_tiles; ++it) {
             const int mt = (p.mt == 2) ? eg : 0;
-            if (p.mt == 1 && (it & 1) != eg) continue;
-            const int tile = cta + it * ncta;
+            if (p.mt == 1 && !PAIR && (it & 1) != eg) continue;
             const int ab = it & 1;
             const long long tq0 = clock64();
             mbar_wait_relaxed(&acc_full[ab], (it >> 1) & 1);
             tc_fence_after();
             const long long tq1 = clock64();
             t_wait += tq1 - tq0;
-            const int q = tile * tile_pos + mt * 128 + row;
+            const int q = tile_q(it, half) + mt * 128 + row;
             const int rho = q / p.P;
             const int x = q - rho * p.P;
             const int b = rho / Tp;
             const int t = (rho - b * Tp) - p.padrow;
             const bool valid = (q < p.total_flat) && (t >= 0) && (x >= p.xlo) && (x < p.xlo + p.F_conv);
             // output bins of this conv pixel: obin0 + g (g < NPX); storage position inside a plane of the frame row
-            const int obin0 = (x - p.xlo) * npx + half * NPX;
+            const int ohalf = PAIR ? eg : half;       // channel half (= output pixel group) this thread finishes
+            const int obin0 = (x - p.xlo) * npx + ohalf * NPX;
             const int opos0 = p.out_eo ? (obin0 & 1) * (p.F_out >> 1) + (obin0 >> 1) : obin0;
             uint8_t* orow = p.out + ((long long)b * p.T + t) * out_rs + (long long)opos0 * 16;
-            const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((ab * p.mt + mt) * 2 * N);
+            // pair accumulator: [hh | hl + lh] of half 0, then [hh + lh | hl] of half 1 (the a_lo x b_hi product lands on columns N .. 3N)
+            const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(PAIR ? (ab * 2 + eg) * 2 * N : (ab * p.mt + mt) * 2 * N);
+            const float* bias_s = par_s + (PAIR ? eg * N : 0);
             float2 v[N / 2];
             float* vf = reinterpret_cast<float*>(v);
 #pragma unroll
@@ -432,14 +490,14 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
                 const float2 sc = make_float2(p.wscale_inv, p.wscale_inv);
 #pragma unroll
                 for (int c = 0; c < N; c += 4) {
-                    const float4 bv = *reinterpret_cast<const float4*>(par_s + c);
+                    const float4 bv = *reinterpret_cast<const float4*>(bias_s + c);
                     v[c / 2] = __ffma2_rn(v[c / 2], sc, make_float2(bv.x, bv.y));
                     v[c / 2 + 1] = __ffma2_rn(v[c / 2 + 1], sc, make_float2(bv.z, bv.w));
                 }
             }
             if (LN && !(p.dbg & 8)) {
 #pragma unroll
-                for (int g = 0; g < NPX; ++g) ln_prelu_s<PC>(v + g * PC / 2, par_s + 64, par_s + 128, alpha);
+                for (int g = 0; g < NPX; ++g) ln_prelu_s<PC>(v + g * PC / 2, par_s + 128, par_s + 192, alpha);
             }
             if (valid && !(p.dbg & 2)) {
                 if (NPX == 2 && !p.out_eo) {
@@ -497,12 +555,14 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
         int buf = 0, round = 0;        // ring position of phase g and the parity of its use count
         int g = 0;
         for (int it = 0; it < my_tiles; ++it) {
-            const int tile = cta + it * ncta;
-            const int q0 = tile * tile_pos - p.lead;
+            const int q0 = tile_q(it, half) - p.lead;
             const long long tl0 = clock64();
             if (p.tma == 2) {
                 const T3TileGeo tg = t3_tile_geo(q0, p.P, Tp, p.padrow, p.slots, max(p.tm_delta[0], p.tm_delta[1]));
-                if (tg.box) {
+                // pair mode: one A descriptor serves both CTAs, so both must use the same image layout
+                const int peer_box = PAIR ? t3_tile_geo(tile_q(it, half ^ 1) - p.lead, p.P, Tp, p.padrow, p.slots,
+                                                          max(p.tm_delta[0], p.tm_delta[1])).box : 1;
+                if (tg.box && peer_box) {
                     // one box per image into this warp's plane; 32 arrivals per warp keep the barrier count of the fallback
                     for (int ph = 0; ph < p.nphase; ++ph, ++g) {
                         const long long tl1 = clock64();
@@ -680,6 +740,9 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
         }
         constexpr uint32_t IDESC_2N = (1u << 4) | ((uint32_t)((2 * N) >> 3) << 17) | ((128u >> 4) << 24);   // f16 x f16 -> f32, N' = 2N
         constexpr uint32_t IDESC_N = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+        // pair mode: M = 256 over both CTAs, N' = both CTAs' [b_hi | b_lo] blocks = 4N, then a_lo x both b_hi blocks = 2N
+        constexpr uint32_t IDESC_P4N = (1u << 4) | ((uint32_t)((4 * N) >> 3) << 17) | ((256u >> 4) << 24);
+        constexpr uint32_t IDESC_P2N = (1u << 4) | ((uint32_t)((2 * N) >> 3) << 17) | ((256u >> 4) << 24);
         // Descriptors differ only in their 14-bit start-address field (bytes >> 4): keep the invariant high words and
         // per-tap address deltas in registers so that one MMA costs a couple of integer adds.
         const uint64_t da0 = make_desc(smem_u32(abuf0), p.plane_bytes);
@@ -697,28 +760,60 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
         const long long tm_begin = clock64();
         uint32_t tap_img1 = 0;                                     // bit tap: the tap reads image 1
         for (int tap = 0; tap < p.ntaps; ++tap) tap_img1 |= (uint32_t)p.tap_img[tap] << tap;
+        if (PAIR && half == 1) {
+            // The partner of the leader issues no MMAs: it forwards "my image landed" and "my accumulator is drained" to the
+            // leader's barriers, in the order the leader waits for them.
+            for (int it = 0; it < my_tiles; ++it) {
+                if (it >= 2) {
+                    mbar_wait(&acc_empty[it & 1], ((it >> 1) - 1) & 1);
+                    if (lane == 0) mbar_arrive_peer(&peer_acc_empty[it & 1], 0);
+                }
+                const int dm = max(p.tm_delta[0], p.tm_delta[1]);
+                const bool boxed = t3_tile_geo(tile_q(it, 0) - p.lead, p.P, Tp, p.padrow, p.slots, dm).box &&
+                                   t3_tile_geo(tile_q(it, 1) - p.lead, p.P, Tp, p.padrow, p.slots, dm).box;
+                for (int ph = 0; ph < p.nphase; ++ph) {
+                    mbar_wait(&a_full[buf], round);
+                    if (!boxed) fence_proxy_async();   // only the cp.async fallback writes through the generic proxy
+                    if (lane == 0) mbar_arrive_peer(&peer_full[buf], 0);
+                    __syncwarp();
+                    if (++buf == p.nabuf) {
+                        buf = 0;
+                        round ^= 1;
+                    }
+                }
+            }
+        } else
         for (int it = 0; it < my_tiles; ++it) {
             const int accb = it & 1;
             // tensor-box tiles: the image starts on a frame-row boundary and image 1 sits at tm_img_bytes
             uint32_t adj0 = 0, adj1 = 0;
+            bool boxed = false;
             if (p.tma == 2) {
-                const T3TileGeo tg = t3_tile_geo((cta + it * ncta) * tile_pos - p.lead, p.P, Tp, p.padrow, p.slots,
-                                                 max(p.tm_delta[0], p.tm_delta[1]));
-                if (tg.box) {
+                const T3TileGeo tg = t3_tile_geo(tile_q(it, 0) - p.lead, p.P, Tp, p.padrow, p.slots, max(p.tm_delta[0], p.tm_delta[1]));
+                const int peer_box = PAIR ? t3_tile_geo(tile_q(it, 1) - p.lead, p.P, Tp, p.padrow, p.slots,
+                                                          max(p.tm_delta[0], p.tm_delta[1])).box : 1;
+                if (tg.box && peer_box) {
+                    boxed = true;
                     adj0 = (uint32_t)(tg.xoff + p.tm_delta[0]);
                     adj1 = (uint32_t)(tg.xoff + p.tm_delta[1] + (p.tm_img_bytes >> 4) - p.slots);
                 }
             }
             const long long tm0 = clock64();
-            if (it >= 2) mbar_wait(&acc_empty[accb], ((it >> 1) - 1) & 1);
+            if (it >= 2) {
+                mbar_wait(&acc_empty[accb], ((it >> 1) - 1) & 1);
+                if (PAIR) mbar_wait(&peer_acc_empty[accb], ((it >> 1) - 1) & 1);
+            }
             tc_fence_after();
             tm_acc += clock64() - tm0;
             uint32_t wlow = db_low0;
-            const uint32_t d0 = tmem_base + (uint32_t)(accb * p.mt * 2 * N);
+            const uint32_t d0 = tmem_base + (uint32_t)(PAIR ? accb * 4 * N : accb * p.mt * 2 * N);
             for (int ph = 0; ph < p.nphase; ++ph) {
                 const long long tm1 = clock64();
                 mbar_wait(&a_full[buf], round);
-                if (p.fence_mode != 2) fence_proxy_async();   // cp.async wrote through the generic proxy, the MMA reads through the async proxy
+                if (PAIR) mbar_wait(&peer_full[buf], round);   // (a cluster-scope acquire here costs ~1000 cycles per wait: measured)
+                // cp.async / st.shared wrote through the generic proxy, the MMA reads through the async proxy; tensor-box tiles
+                // were written by the copy engine itself and need no proxy fence
+                if (!boxed && p.fence_mode != 2) fence_proxy_async();
                 tc_fence_after();
                 tm_full += clock64() - tm1;
                 if (leader) {
@@ -730,6 +825,10 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
                             if (!(p.dbg & 4)) {
                                 uint32_t al = alow + tapd[tap] + (((tap_img1 >> tap) & 1u) ? adj1 : adj0);
                                 if (p.dbg & 16) al &= ~7u;
+                                if (PAIR) {
+                                    tc_mma_f16_w2(d0, al, da_hiw, wlow, db_hiw, IDESC_P4N, acc);                             // a_hi x [b_hi | b_lo] of both halves
+                                    if (!(p.dbg & 64)) tc_mma_f16_w2(d0 + N, al + a_lo_delta, da_hiw, wlow, db_hiw, IDESC_P2N, 1u);   // a_lo x b_hi of both halves
+                                } else {
                                 // the two tiles' accumulators alternate, so back-to-back MMAs never chain on one accumulator
                                 tc_mma_f16_w(d0, al, da_hiw, wlow, db_hiw, IDESC_2N, acc);                                   // a_hi x [b_hi | b_lo]
                                 if (p.mt == 2) tc_mma_f16_w(d0 + 2 * N, al + 128, da_hiw, wlow, db_hiw, IDESC_2N, acc);
@@ -737,11 +836,13 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
                                     tc_mma_f16_w(d0, al + a_lo_delta, da_hiw, wlow, db_hiw, IDESC_N, 1u);                    // a_lo x b_hi
                                     if (p.mt == 2) tc_mma_f16_w(d0 + 2 * N, al + 128 + a_lo_delta, da_hiw, wlow, db_hiw, IDESC_N, 1u);
                                 }
+                                }
                             }
                             wlow += N * 4;   // next (phase, tap) stage: N * 64 bytes
                         }
                     }
-                    if (p.cluster) tc_commit_mc(&a_empty[buf], (uint16_t)3);
+                    if (PAIR) tc_commit_pair(&a_empty[buf]);
+                    else if (p.cluster) tc_commit_mc(&a_empty[buf], (uint16_t)3);
                     else tc_commit(&a_empty[buf]);
                 }
                 __syncwarp();
@@ -750,7 +851,10 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
                     round ^= 1;
                 }
             }
-            if (leader) tc_commit(&acc_full[accb]);
+            if (leader) {
+                if (PAIR) tc_commit_pair(&acc_full[accb]);
+                else tc_commit(&acc_full[accb]);
+            }
             __syncwarp();
         }
         if (p.timing && blockIdx.x == 0 && lane == 0) {
@@ -764,9 +868,10 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
     // ------------------------------------------------------------------ teardown
     tc_fence_before();
     __syncthreads();
-    if (p.cluster) cluster_sync_all();     // nobody leaves while the partner can still write to / arrive on this CTA
+    if (p.cluster || PAIR) cluster_sync_all();     // nobody leaves while the partner can still write to / arrive on this CTA
     if (warp == MMA_WARP) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 

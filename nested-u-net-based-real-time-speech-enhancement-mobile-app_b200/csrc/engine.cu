@@ -387,6 +387,8 @@ struct Engine {
     int tc3_tma = 2;         // NUNET_TC3_TMA: 0 = cp.async loaders everywhere, 1 = 1-D bulk copies per frame-row segment (F >= 32),
                              // 2 (default) = one tensor-map box per tile image where the source order allows, else as 1
     int tc3_box_strided = 1; // NUNET_TC3_BOX_STRIDED=0 (experiments): stride-2 units over bin-ordered sources stay on the slot-table loader
+    int tc3_pair = 1;        // NUNET_TC3_PAIR=0: 128-channel units run as two independent CTAs per tile instead of cta_group::2 pairs
+    int tc3_pair_minf = 4;   // NUNET_TC3_PAIR_MINF (experiments)
     int tc3_box_minf = 4;    // NUNET_TC3_BOX_MINF (experiments): smallest F_conv of a unit that uses tensor-map boxes
     int tc3_tma_minf = 32;   // NUNET_TC3_TMA_MINF (experiments): smallest F_in of a stride-1 unit that uses bulk copies
     int tc3_cluster = 0;     // NUNET_TC3_CLUSTER=1: the two CTAs of a 128-channel unit form a cluster and multicast their bulk copies
@@ -796,10 +798,10 @@ struct Engine {
         return m;
     }
 
-    template <int N, int PC, bool LN>
+    template <int N, int PC, bool LN, bool PAIR = false>
     void launch_tc3_t(const Tc3Params& p, int grid, size_t smem, cudaStream_t st) {
         static bool attr_set = false;
-        auto kfn = conv_tc3_kernel<N, PC, LN>;
+        auto kfn = conv_tc3_kernel<N, PC, LN, PAIR>;
         if (!attr_set) {
             CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             attr_set = true;
@@ -814,14 +816,14 @@ struct Engine {
         at[0].val.programmaticStreamSerializationAllowed = tc3_pdl ? 1 : 0;
         lc.attrs = at;
         lc.numAttrs = 1;
-        if (p.cluster) {
+        if (p.cluster || p.pair) {
             at[1].id = cudaLaunchAttributeClusterDimension;
             at[1].val.clusterDim.x = 2;
             at[1].val.clusterDim.y = 1;
             at[1].val.clusterDim.z = 1;
             lc.numAttrs = 2;
         }
-        if (p.cluster) {
+        if (p.cluster || p.pair) {
             // a persistent grid must be co-resident: clamp to the number of 2-CTA clusters the device can hold at once
             static int max_clusters = -1;
             if (max_clusters < 0) {
@@ -831,7 +833,12 @@ struct Engine {
             }
             if ((int)lc.gridDim.x > 2 * max_clusters) lc.gridDim = dim3((unsigned)(2 * max_clusters));
         }
-        CUDA_OK(cudaLaunchKernelEx(&lc, kfn, p));
+        {
+            const cudaError_t le = cudaLaunchKernelEx(&lc, kfn, p);
+            if (le != cudaSuccess)
+                fail(NUNET_ECUDA, "conv_tc3 launch (%s): %s [grid %u, smem %zu, cluster %d, pair %d, tiles %d, mt %d, ring %d]", cur_op.c_str(),
+                     cudaGetErrorString(le), lc.gridDim.x, smem, p.cluster, p.pair, p.ntiles, p.mt, p.nabuf);
+        }
         if (tc3_timing_buf) {   // experiments: per-role cycles of CTA 0, per tile (serialises the stream)
             unsigned long long h[12];
             CUDA_OK(cudaStreamSynchronize(st));
@@ -975,11 +982,15 @@ struct Engine {
         bool two = nb2 >= 2;   // larger tiles beat a deeper ring (measured): per-tile overheads dominate
         if (tc3_force_mt == 1 && nb1 >= 2) two = false;
         if (tc3_force_mt == 2 && nb2 >= 2) two = true;
+        // 128-channel units over box images: CTA pairs with cta_group::2 MMAs (one 128-position tile per CTA)
+        const bool pair = box && L.nhalf3 == 2 && L.N3 == 64 && L.PC3 == 64 && L.epi != EPI_BIAS && tc3_pair && nb1 >= 2 &&
+                          p.F_conv >= tc3_pair_minf;
+        if (pair) two = false;
         if (probe_two) {
             *probe_two = two;
             return;
         }
-        if (box && !two) {
+        if (box && !two && !pair) {
             // whole-row boxes are larger than the exact images of the row-segment loader: when only the latter fits two tiles
             // per iteration, it wins (measured: 128-channel stride-2 unit at 128 bins, 2.3 ms against 3.3 ms)
             bool two_rows = false;
@@ -1006,9 +1017,17 @@ struct Engine {
             if (p.src1) p.tm_map[1] = tc3_tensor_map(p.src1, Fm, planes, T, B, (size_t)F_in * L.CA * 4, p.P, p.tm_rows, kind);
         }
         p.ntiles = (int)((total + p.mt * 128 - 1) / (p.mt * 128));
+        if (pair) {
+            int g = 128, b = p.P;
+            while (b) { const int r = g % b; g = b; b = r; }
+            p.pair = 1;
+            p.pair_m = p.P / g;                                          // tiles between the two CTAs of a pair = 128 / g frame rows
+            p.ntiles = (p.ntiles + 2 * p.pair_m - 1) / (2 * p.pair_m) * p.pair_m;   // cluster work units
+        }
         const int grid = std::max(1, std::min(p.ntiles, num_sms / p.nhalf)) * p.nhalf;
         const bool ln = (L.epi != EPI_BIAS);
         if (L.N3 == 32 && L.PC3 == 32 && ln) launch_tc3_t<32, 32, true>(p, grid, smem, st);
+        else if (L.N3 == 64 && L.PC3 == 64 && ln && p.pair) launch_tc3_t<64, 64, true, true>(p, grid, smem, st);
         else if (L.N3 == 64 && L.PC3 == 64 && ln) launch_tc3_t<64, 64, true>(p, grid, smem, st);
         else if (L.N3 == 64 && L.PC3 == 64 && !ln) launch_tc3_t<64, 64, false>(p, grid, smem, st);
         else if (L.N3 == 64 && L.PC3 == 32 && ln) launch_tc3_t<64, 32, true>(p, grid, smem, st);
@@ -1685,6 +1704,8 @@ int nunet_create(const nunet_config* cfg, const void* blob, size_t blob_bytes, n
         if (const char* c = getenv("NUNET_TC3_TMA")) E.tc3_tma = atoi(c);
         if (const char* c = getenv("NUNET_TC3_CLUSTER")) E.tc3_cluster = atoi(c);
         if (const char* c = getenv("NUNET_TC3_BOX_MINF")) E.tc3_box_minf = atoi(c);
+        if (const char* c = getenv("NUNET_TC3_PAIR")) E.tc3_pair = atoi(c);
+        if (const char* c = getenv("NUNET_TC3_PAIR_MINF")) E.tc3_pair_minf = atoi(c);
         if (const char* c = getenv("NUNET_TC3_BOX_STRIDED")) E.tc3_box_strided = atoi(c);
         if (const char* c = getenv("NUNET_TC3_TMA_MINF")) E.tc3_tma_minf = std::max(8, atoi(c));
         if (const char* c = getenv("NUNET_TC3_MT")) E.tc3_force_mt = atoi(c);
