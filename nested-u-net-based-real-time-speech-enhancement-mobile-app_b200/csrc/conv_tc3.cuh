@@ -274,6 +274,30 @@ __device__ __forceinline__ void st_global_32B(void* p, const uint4& a, const uin
                  "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
 }
 
+// tcgen05.ld of 32 columns WITHOUT the wait, so that several loads are in flight before one tcgen05.wait::ld.  The values
+// may be used only after tmem_ld_wait() + tmem_ld_fence32() on the same registers (the empty asm ties them to the wait).
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_fence32(uint32_t* r) {
+    asm volatile(""
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                   "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+                   "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
+                   "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
+
 // hi/lo split of 8 consecutive values into two 16-byte vectors of halves
 __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
     uint32_t h[4], l[4];
@@ -457,30 +481,33 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
             tc_fence_after();
             const long long tq1 = clock64();
             t_wait += tq1 - tq0;
-            const int q = tile_q(it, half) + mt * 128 + row;
-            const int rho = q / p.P;
-            const int x = q - rho * p.P;
-            const int b = rho / Tp;
-            const int t = (rho - b * Tp) - p.padrow;
-            const bool valid = (q < p.total_flat) && (t >= 0) && (x >= p.xlo) && (x < p.xlo + p.F_conv);
-            // output bins of this conv pixel: obin0 + g (g < NPX); storage position inside a plane of the frame row
-            const int ohalf = PAIR ? eg : half;       // channel half (= output pixel group) this thread finishes
-            const int obin0 = (x - p.xlo) * npx + ohalf * NPX;
-            const int opos0 = p.out_eo ? (obin0 & 1) * (p.F_out >> 1) + (obin0 >> 1) : obin0;
-            uint8_t* orow = p.out + ((long long)b * p.T + t) * out_rs + (long long)opos0 * 16;
             // pair accumulator: [hh | hl + lh] of half 0, then [hh + lh | hl] of half 1 (the a_lo x b_hi product lands on columns N .. 3N)
             const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(PAIR ? (ab * 2 + eg) * 2 * N : (ab * p.mt + mt) * 2 * N);
             const float* bias_s = par_s + (PAIR ? eg * N : 0);
             float2 v[N / 2];
-            float* vf = reinterpret_cast<float*>(v);
+            {
+                // both column blocks of the accumulator, the loads in flight together: one wait per 32 + 32..64 columns
+                uint32_t rv[N], ru[32];
 #pragma unroll
-            for (int c = 0; c < N; c += 32) tmem_ld32(taddr + c, vf + c);           // a_hi*b_hi + a_lo*b_hi
+                for (int c = 0; c < N; c += 32) tmem_ld32_issue(taddr + c, rv + c);          // a_hi*b_hi (+ a_lo*b_hi)
+                tmem_ld32_issue(taddr + N, ru);                                                // a_hi*b_lo (+ a_lo*b_hi)
+                tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < N; c += 32) {                                        // + a_hi*b_lo
-                float2 u[16];
-                tmem_ld32(taddr + N + c, reinterpret_cast<float*>(u));
+                for (int c = 0; c < N; c += 32) tmem_ld_fence32(rv + c);
+                tmem_ld_fence32(ru);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[c / 2 + i] = __fadd2_rn(v[c / 2 + i], u[i]);
+                for (int i = 0; i < 16; ++i)
+                    v[i] = __fadd2_rn(make_float2(__uint_as_float(rv[2 * i]), __uint_as_float(rv[2 * i + 1])),
+                                      make_float2(__uint_as_float(ru[2 * i]), __uint_as_float(ru[2 * i + 1])));
+                if (N == 64) {
+                    tmem_ld32_issue(taddr + N + 32, ru);
+                    tmem_ld_wait();
+                    tmem_ld_fence32(ru);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        v[16 + i] = __fadd2_rn(make_float2(__uint_as_float(rv[32 + 2 * i]), __uint_as_float(rv[32 + 2 * i + 1])),
+                                               make_float2(__uint_as_float(ru[2 * i]), __uint_as_float(ru[2 * i + 1])));
+                }
             }
             // the accumulator is in registers: hand the TMEM buffer back to the MMA warp right away
             tc_fence_before();
@@ -499,6 +526,18 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
 #pragma unroll
                 for (int g = 0; g < NPX; ++g) ln_prelu_s<PC>(v + g * PC / 2, par_s + 128, par_s + 192, alpha);
             }
+            // where this row goes (computed only now: nothing of it has to stay live across the arithmetic above)
+            const int q = tile_q(it, half) + mt * 128 + row;
+            const int rho = q / p.P;
+            const int x = q - rho * p.P;
+            const int b = rho / Tp;
+            const int t = (rho - b * Tp) - p.padrow;
+            const bool valid = (q < p.total_flat) && (t >= 0) && (x >= p.xlo) && (x < p.xlo + p.F_conv);
+            // output bins of this conv pixel: obin0 + g (g < NPX); storage position inside a plane of the frame row
+            const int ohalf = PAIR ? eg : half;       // channel half (= output pixel group) this thread finishes
+            const int obin0 = (x - p.xlo) * npx + ohalf * NPX;
+            const int opos0 = p.out_eo ? (obin0 & 1) * (p.F_out >> 1) + (obin0 >> 1) : obin0;
+            uint8_t* orow = p.out + ((long long)b * p.T + t) * out_rs + (long long)opos0 * 16;
             if (valid && !(p.dbg & 2)) {
                 if (NPX == 2 && !p.out_eo) {
                     // two neighbouring output bins per thread: one 32-byte store per chunk (whole sectors)
