@@ -422,6 +422,8 @@ struct Engine {
         for (auto& pe : prof) cudaEventDestroy(pe.ev);
         if (prof_start) cudaEventDestroy(prof_start);
         if (own_stream) cudaStreamDestroy(own_stream);
+        for (auto& kv : step_graphs) cudaGraphExecDestroy(kv.second.exec);
+        if (cap_stream) cudaStreamDestroy(cap_stream);
     }
 
     // -------------------------------------------------------------------------------- parameter packing
@@ -1487,12 +1489,104 @@ struct Engine {
         ++stream_steps;
     }
 
+    // ---- CUDA graphs for the streaming step.  One step is ~200 small kernels whose arguments depend only on the step parity
+    // (and on the ring slot for the DDB / attention-history rings), the stream count and the caller's buffers: each such
+    // combination is captured once (on a private stream, so that callers may use the legacy default stream) and replayed
+    // with one cudaGraphLaunch.  The first two steps run eagerly (lazy function attributes, occupancy queries).
+    struct StepGraph {
+        cudaGraphExec_t exec = nullptr;
+        int launches = 0;
+    };
+    std::map<std::tuple<int, int, int, int, const void*, void*, void*>, StepGraph> step_graphs;
+    int stream_graphs = 1;          // NUNET_STREAM_GRAPH=0: always launch kernel by kernel
+    int eager_steps = 0;
+    cudaStream_t cap_stream = nullptr;
+
+    template <typename Body>
+    void graph_step(int kind, int S, const void* in, void* out, void* out2, cudaStream_t st, Body&& body) {
+        const bool rings = is_ddb() || cfg.stream_ctfa_history;
+        if (!stream_graphs || prof_on || tc3_timing_buf || eager_steps < 2) {
+            ++eager_steps;
+            body(st);
+            return;
+        }
+        const auto key = std::make_tuple(kind, S, stream_parity, rings ? (stream_steps & (DDB_RING - 1)) : 0, in, out, out2);
+        auto it = step_graphs.find(key);
+        if (it == step_graphs.end()) {
+            if (step_graphs.size() >= 512) {   // callers that keep changing buffers: stop caching
+                body(st);
+                return;
+            }
+            const int parity0 = stream_parity, steps0 = stream_steps;
+            if (!cap_stream) CUDA_OK(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
+            cudaGraph_t g = nullptr;
+            StepGraph sg;
+            bool ok = cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok) {
+                try {
+                    launches = 0;
+                    body(cap_stream);
+                    sg.launches = launches;
+                } catch (const std::exception&) {
+                    ok = false;
+                }
+                if (cudaStreamEndCapture(cap_stream, &g) != cudaSuccess || !g) ok = false;
+            }
+            if (ok && cudaGraphInstantiate(&sg.exec, g, 0) != cudaSuccess) ok = false;
+            if (g) cudaGraphDestroy(g);
+            if (!ok) {   // capture is an optimisation, never a requirement: fall back to plain launches for good
+                cudaGetLastError();
+                stream_graphs = 0;
+                stream_parity = parity0;
+                stream_steps = steps0;
+                body(st);
+                return;
+            }
+            step_graphs[key] = sg;
+            CUDA_OK(cudaGraphLaunch(sg.exec, st));
+            return;
+        }
+        CUDA_OK(cudaGraphLaunch(it->second.exec, st));
+        launches = it->second.launches;
+        stream_parity ^= 1;
+        ++stream_steps;
+    }
+
     void stream_step_wav(const float* hop, int S, float* out_hop, float* out_mag, cudaStream_t st) {
         check_streams(S);
         launches = 0;
         cur_op = "framing";
         order_begin(st);
         prof_begin(st);
+        if (stream_graphs && !prof_on && !tc3_timing_buf) {
+            // the graph works on the engine's own staging buffers, so it does not depend on the caller's pointers
+            const size_t n = (size_t)S * HOP * sizeof(float);
+            if (hop != h_in) CUDA_OK(cudaMemcpyAsync(h_in, hop, n, cudaMemcpyDeviceToDevice, st));
+            graph_step(1, S, nullptr, nullptr, nullptr, st, [&](cudaStream_t s) { stream_step_wav_body(h_in, S, h_out, nullptr, s); });
+            if (out_hop != h_out) CUDA_OK(cudaMemcpyAsync(out_hop, h_out, n, cudaMemcpyDeviceToDevice, st));
+            if (out_mag) CUDA_OK(cudaMemcpyAsync(out_mag, stream.cur(s_est, 0), (size_t)S * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        } else {
+            stream_step_wav_body(hop, S, out_hop, out_mag, st);
+        }
+        order_end(st);
+    }
+    // one hop of the network alone (magnitudes in, magnitudes out), staged the same way
+    void stream_step_mag_api(const float* mag, int S, float* out, cudaStream_t st) {
+        check_streams(S);
+        if (stream_graphs && !prof_on && !tc3_timing_buf) {
+            const size_t n = (size_t)S * 256 * sizeof(float);
+            float* m = stream.cur(s_mag, 0);
+            float* est = stream.cur(s_est, 0);
+            CUDA_OK(cudaMemcpyAsync(m, mag, n, cudaMemcpyDeviceToDevice, st));
+            graph_step(0, S, nullptr, nullptr, nullptr, st, [&](cudaStream_t s) { stream_step_mag(m, S, est, s); });
+            CUDA_OK(cudaMemcpyAsync(out, est, n, cudaMemcpyDeviceToDevice, st));
+        } else {
+            stream_step_mag(mag, S, out, st);
+        }
+    }
+
+    void stream_step_wav_body(const float* hop, int S, float* out_hop, float* out_mag, cudaStream_t st) {
+        cur_op = "framing";
         float* mag = stream.cur(s_mag, 0);
         float2* ph = reinterpret_cast<float2*>(stream.cur(s_ph, 0));
         float* est = stream.cur(s_est, 0);
@@ -1505,7 +1599,6 @@ struct Engine {
         stream_synthesis_kernel<<<fblocks, 32 * FRAMES_PER_CTA, 0, st>>>(est, ph, tables(true), stream.cur(s_outbuf, 0), out_hop, S,
                                                                        cfg.dc_mode == NUNET_DC_EDGE);
         check_launch("stream_synthesis", S * 4.0 * (256 + 514 + 512 + 512 + 256));
-        order_end(st);
     }
 
     void stream_reset(int first, int count, cudaStream_t st) {
@@ -1705,6 +1798,7 @@ int nunet_create(const nunet_config* cfg, const void* blob, size_t blob_bytes, n
         if (const char* c = getenv("NUNET_TC3_CLUSTER")) E.tc3_cluster = atoi(c);
         if (const char* c = getenv("NUNET_TC3_BOX_MINF")) E.tc3_box_minf = atoi(c);
         if (const char* c = getenv("NUNET_TC3_PAIR")) E.tc3_pair = atoi(c);
+        if (const char* c = getenv("NUNET_STREAM_GRAPH")) E.stream_graphs = atoi(c);
         if (const char* c = getenv("NUNET_TC3_PAIR_MINF")) E.tc3_pair_minf = atoi(c);
         if (const char* c = getenv("NUNET_TC3_BOX_STRIDED")) E.tc3_box_strided = atoi(c);
         if (const char* c = getenv("NUNET_TC3_TMA_MINF")) E.tc3_tma_minf = std::max(8, atoi(c));
@@ -1799,7 +1893,7 @@ int nunet_stream_step_mag_dev(nunet_engine* h, const float* mag, int S, float* o
         h->e.launches = 0;
         h->e.order_begin(static_cast<cudaStream_t>(stream));
         h->e.prof_begin(static_cast<cudaStream_t>(stream));
-        h->e.stream_step_mag(mag, S, out_mag, static_cast<cudaStream_t>(stream));
+        h->e.stream_step_mag_api(mag, S, out_mag, static_cast<cudaStream_t>(stream));
         h->e.order_end(static_cast<cudaStream_t>(stream));
     });
 }
