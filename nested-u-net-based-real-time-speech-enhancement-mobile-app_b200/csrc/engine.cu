@@ -324,8 +324,13 @@ struct Plan {
         unit_floats = ptop + shigh;
     }
     float* ptr(size_t off) const { return arena + off * (size_t)cap; }
-    float* cur(const Ten* t, int parity) const { return ptr(t->off[parity & 1]); }
-    float* prev(const Ten* t, int parity) const { return streaming ? ptr(t->off[(parity ^ 1) & 1]) : nullptr; }
+    // unit0: first unit (stream) the ops enqueued next work on -- lets one step be enqueued as several independent chains
+    // over disjoint stream ranges (CUDA-graph branches); 0 everywhere else
+    int unit0 = 0;
+    float* cur(const Ten* t, int parity) const { return ptr(t->off[parity & 1]) + (size_t)unit0 * t->numel(); }
+    float* prev(const Ten* t, int parity) const {
+        return streaming ? ptr(t->off[(parity ^ 1) & 1]) + (size_t)unit0 * t->numel() : nullptr;
+    }
     ~Plan() {
         if (arena) cudaFree(arena);
     }
@@ -423,7 +428,10 @@ struct Engine {
         if (prof_start) cudaEventDestroy(prof_start);
         if (own_stream) cudaStreamDestroy(own_stream);
         for (auto& kv : step_graphs) cudaGraphExecDestroy(kv.second.exec);
-        if (cap_stream) cudaStreamDestroy(cap_stream);
+        for (int i = 0; i < 4; ++i) {
+            if (cap_stream[i]) cudaStreamDestroy(cap_stream[i]);
+            if (cap_event[i]) cudaEventDestroy(cap_event[i]);
+        }
     }
 
     // -------------------------------------------------------------------------------- parameter packing
@@ -1477,14 +1485,16 @@ struct Engine {
         if (S != stream.cap) fail(NUNET_EINVAL, "a step must cover all max_streams = %d streams (got S = %d)", stream.cap, S);
     }
 
+    // S may be a sub-range of the streams (graph chains); the entry points check the full count
     void stream_step_mag(const float* mag, int S, float* out, cudaStream_t st) {
-        check_streams(S);
         Run r;
         r.B = S; r.T = 1; r.st = st; r.mag_in = mag; r.est_out = out; r.est_stride = 256; r.est_off = 0;
         r.parity = stream_parity ^ 1;
         r.ring_pos = stream_steps & (CTFA_WINDOW - 1);
         r.step = stream_steps;
         run_plan(stream, r);
+    }
+    void stream_advance() {
         stream_parity ^= 1;
         ++stream_steps;
     }
@@ -1497,59 +1507,90 @@ struct Engine {
         cudaGraphExec_t exec = nullptr;
         int launches = 0;
     };
-    std::map<std::tuple<int, int, int, int, const void*, void*, void*>, StepGraph> step_graphs;
+    std::map<std::tuple<int, int, int, int>, StepGraph> step_graphs;
     int stream_graphs = 1;          // NUNET_STREAM_GRAPH=0: always launch kernel by kernel
+    int stream_split = 1;           // NUNET_STREAM_SPLIT=2..4 (experiments): parallel chains per captured step, from 64 streams per
+                                    // chain.  Measured at 1024 streams: 2.69 ms (1 chain), 2.90 ms (2), 4.48 ms (4) -- the 1-CTA-per-SM
+                                    // conv kernels of different chains do not overlap, so more chains only add launches
     int eager_steps = 0;
-    cudaStream_t cap_stream = nullptr;
+    cudaStream_t cap_stream[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t cap_event[4] = {nullptr, nullptr, nullptr, nullptr};
 
+    // body(stream, first, count) enqueues one step for streams [first, first + count) WITHOUT advancing the step counters.
     template <typename Body>
-    void graph_step(int kind, int S, const void* in, void* out, void* out2, cudaStream_t st, Body&& body) {
+    void graph_step(int kind, int S, cudaStream_t st, Body&& body) {
         const bool rings = is_ddb() || cfg.stream_ctfa_history;
         if (!stream_graphs || prof_on || tc3_timing_buf || eager_steps < 2) {
             ++eager_steps;
-            body(st);
+            body(st, 0, S);
+            stream_advance();
             return;
         }
-        const auto key = std::make_tuple(kind, S, stream_parity, rings ? (stream_steps & (DDB_RING - 1)) : 0, in, out, out2);
+        const auto key = std::make_tuple(kind, S, stream_parity, rings ? (stream_steps & (DDB_RING - 1)) : 0);
         auto it = step_graphs.find(key);
         if (it == step_graphs.end()) {
-            if (step_graphs.size() >= 512) {   // callers that keep changing buffers: stop caching
-                body(st);
-                return;
-            }
-            const int parity0 = stream_parity, steps0 = stream_steps;
-            if (!cap_stream) CUDA_OK(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
+            // Streams are independent and most kernels of a step are far too small to fill the GPU, so a step of many
+            // streams is captured as several parallel chains over disjoint stream ranges: the graph lets kernels of
+            // different chains run side by side.
+            const int nsplit = (S >= 64 * stream_split) ? std::min(stream_split, 4) : 1;
+            if (!cap_stream[0])
+                for (int i = 0; i < 4; ++i) {
+                    CUDA_OK(cudaStreamCreateWithFlags(&cap_stream[i], cudaStreamNonBlocking));
+                    CUDA_OK(cudaEventCreateWithFlags(&cap_event[i], cudaEventDisableTiming));
+                }
             cudaGraph_t g = nullptr;
             StepGraph sg;
-            bool ok = cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            std::string why;
+            bool ok = cudaStreamBeginCapture(cap_stream[0], cudaStreamCaptureModeThreadLocal) == cudaSuccess;
             if (ok) {
                 try {
                     launches = 0;
-                    body(cap_stream);
+                    if (nsplit > 1) CUDA_OK(cudaEventRecord(cap_event[0], cap_stream[0]));
+                    for (int i = 1; i < nsplit; ++i) CUDA_OK(cudaStreamWaitEvent(cap_stream[i], cap_event[0], 0));
+                    for (int i = 0; i < nsplit; ++i) {
+                        const int first = (int)((long long)S * i / nsplit), last = (int)((long long)S * (i + 1) / nsplit);
+                        stream.unit0 = first;
+                        body(cap_stream[i], first, last - first);
+                    }
+                    for (int i = 1; i < nsplit; ++i) {
+                        CUDA_OK(cudaEventRecord(cap_event[i], cap_stream[i]));
+                        CUDA_OK(cudaStreamWaitEvent(cap_stream[0], cap_event[i], 0));
+                    }
                     sg.launches = launches;
-                } catch (const std::exception&) {
+                } catch (const std::exception& ex) {
+                    why = ex.what();
                     ok = false;
                 }
-                if (cudaStreamEndCapture(cap_stream, &g) != cudaSuccess || !g) ok = false;
+                stream.unit0 = 0;
+                const cudaError_t ce = cudaStreamEndCapture(cap_stream[0], &g);
+                if (ce != cudaSuccess || !g) {
+                    if (why.empty()) why = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce);
+                    ok = false;
+                }
+            } else {
+                why = "cudaStreamBeginCapture failed";
             }
-            if (ok && cudaGraphInstantiate(&sg.exec, g, 0) != cudaSuccess) ok = false;
+            if (ok) {
+                const cudaError_t ie = cudaGraphInstantiate(&sg.exec, g, 0);
+                if (ie != cudaSuccess) {
+                    why = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie);
+                    ok = false;
+                }
+            }
             if (g) cudaGraphDestroy(g);
             if (!ok) {   // capture is an optimisation, never a requirement: fall back to plain launches for good
+                fprintf(stderr, "nunet_b200: streaming step not captured as a CUDA graph (%s); launching kernel by kernel\n", why.c_str());
                 cudaGetLastError();
                 stream_graphs = 0;
-                stream_parity = parity0;
-                stream_steps = steps0;
-                body(st);
+                body(st, 0, S);
+                stream_advance();
                 return;
             }
-            step_graphs[key] = sg;
-            CUDA_OK(cudaGraphLaunch(sg.exec, st));
-            return;
+            it = step_graphs.emplace(key, sg).first;
         }
         CUDA_OK(cudaGraphLaunch(it->second.exec, st));
         launches = it->second.launches;
-        stream_parity ^= 1;
-        ++stream_steps;
+        stream_advance();
     }
 
     void stream_step_wav(const float* hop, int S, float* out_hop, float* out_mag, cudaStream_t st) {
@@ -1562,11 +1603,14 @@ struct Engine {
             // the graph works on the engine's own staging buffers, so it does not depend on the caller's pointers
             const size_t n = (size_t)S * HOP * sizeof(float);
             if (hop != h_in) CUDA_OK(cudaMemcpyAsync(h_in, hop, n, cudaMemcpyDeviceToDevice, st));
-            graph_step(1, S, nullptr, nullptr, nullptr, st, [&](cudaStream_t s) { stream_step_wav_body(h_in, S, h_out, nullptr, s); });
+            graph_step(1, S, st, [&](cudaStream_t s, int first, int count) {
+                stream_step_wav_body(h_in + (size_t)first * HOP, count, h_out + (size_t)first * HOP, nullptr, s);
+            });
             if (out_hop != h_out) CUDA_OK(cudaMemcpyAsync(out_hop, h_out, n, cudaMemcpyDeviceToDevice, st));
             if (out_mag) CUDA_OK(cudaMemcpyAsync(out_mag, stream.cur(s_est, 0), (size_t)S * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
         } else {
             stream_step_wav_body(hop, S, out_hop, out_mag, st);
+            stream_advance();
         }
         order_end(st);
     }
@@ -1575,13 +1619,12 @@ struct Engine {
         check_streams(S);
         if (stream_graphs && !prof_on && !tc3_timing_buf) {
             const size_t n = (size_t)S * 256 * sizeof(float);
-            float* m = stream.cur(s_mag, 0);
-            float* est = stream.cur(s_est, 0);
-            CUDA_OK(cudaMemcpyAsync(m, mag, n, cudaMemcpyDeviceToDevice, st));
-            graph_step(0, S, nullptr, nullptr, nullptr, st, [&](cudaStream_t s) { stream_step_mag(m, S, est, s); });
-            CUDA_OK(cudaMemcpyAsync(out, est, n, cudaMemcpyDeviceToDevice, st));
+            CUDA_OK(cudaMemcpyAsync(stream.cur(s_mag, 0), mag, n, cudaMemcpyDeviceToDevice, st));
+            graph_step(0, S, st, [&](cudaStream_t s, int, int count) { stream_step_mag(stream.cur(s_mag, 0), count, stream.cur(s_est, 0), s); });
+            CUDA_OK(cudaMemcpyAsync(out, stream.cur(s_est, 0), n, cudaMemcpyDeviceToDevice, st));
         } else {
             stream_step_mag(mag, S, out, st);
+            stream_advance();
         }
     }
 
@@ -1799,6 +1842,7 @@ int nunet_create(const nunet_config* cfg, const void* blob, size_t blob_bytes, n
         if (const char* c = getenv("NUNET_TC3_BOX_MINF")) E.tc3_box_minf = atoi(c);
         if (const char* c = getenv("NUNET_TC3_PAIR")) E.tc3_pair = atoi(c);
         if (const char* c = getenv("NUNET_STREAM_GRAPH")) E.stream_graphs = atoi(c);
+        if (const char* c = getenv("NUNET_STREAM_SPLIT")) E.stream_split = std::max(1, std::min(4, atoi(c)));
         if (const char* c = getenv("NUNET_TC3_PAIR_MINF")) E.tc3_pair_minf = atoi(c);
         if (const char* c = getenv("NUNET_TC3_BOX_STRIDED")) E.tc3_box_strided = atoi(c);
         if (const char* c = getenv("NUNET_TC3_TMA_MINF")) E.tc3_tma_minf = std::max(8, atoi(c));

@@ -416,3 +416,37 @@ def test_ddb_signature_runner_contract(ddb_weights, golden_o2_ddb):
         assert np.abs(out["model_out"].reshape(256) - golden_o2_ddb["model_out"][t]).max() <= 1e-4 * 2
         state = {k.replace("_cur", "_prev"): v for k, v in out.items() if k != "model_out"}
     assert out["ddb_cur6"].shape == (1, 32, 4, 192) and out["msfe3_en_ddb_cur_in"].shape == (1, 1, 1, 32)
+
+
+@pytest.mark.parametrize("variant", ["lstm", "ddb"])
+def test_streaming_graph_with_parallel_chains_equals_plain_launches(blob, ddb_weights, variant, monkeypatch):
+    """The streaming step replayed as a CUDA graph -- here also split into two parallel chains over disjoint stream
+    ranges (NUNET_STREAM_SPLIT) -- computes exactly what kernel-by-kernel launches compute (wav and mag entry points,
+    both variants)."""
+    from nunet_b200._lib import NUNET_VARIANT_DDB, NUNET_VARIANT_LSTM
+    from nunet_b200.engine import NunetEngine
+    from nunet_b200.synth import synth_clips
+    from nunet_b200.weights import VARIANT_DDB, pack_blob
+    S, steps = 160, 7
+    if variant == "ddb":
+        b, v = pack_blob(ddb_weights, VARIANT_DDB), NUNET_VARIANT_DDB
+    else:
+        b, v = blob, NUNET_VARIANT_LSTM
+    wav = np.tile(synth_clips(8, 256 * steps, first_clip=90), (S // 8, 1))
+    wav *= np.linspace(0.5, 1.0, S, dtype=np.float32)[:, None]          # every stream different
+    outs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("NUNET_STREAM_GRAPH", mode)
+        monkeypatch.setenv("NUNET_STREAM_SPLIT", "2")      # two chains of 80 streams inside the captured step
+        eng = NunetEngine(b, max_streams=S, variant=v)
+        eng.stream_reset()
+        ys = []
+        for t in range(steps):
+            ys.append(eng.stream_step_wav(torch.from_numpy(wav[:, 256 * t:256 * (t + 1)]).cuda()).cpu().numpy().copy())
+        mags = torch.from_numpy(np.abs(wav[:, :256]) * 20).cuda()
+        ys.append(eng.stream_step_mag(mags).cpu().numpy().copy())
+        ys.append(eng.stream_step_mag(mags).cpu().numpy().copy())
+        outs[mode] = ys
+        eng.close()
+    for a, g in zip(outs["0"], outs["1"]):
+        assert np.isfinite(g).all() and np.abs(a - g).max() <= 1e-6
