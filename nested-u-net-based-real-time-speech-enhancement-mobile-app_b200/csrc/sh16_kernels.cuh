@@ -144,6 +144,59 @@ __global__ void __launch_bounds__(256) ctfa_ta_sh_kernel(const uint8_t* __restri
     if (frame < frames) ta_out[frame * 64 + (threadIdx.x & 63)] = t;
 }
 
+// CTFA stage 1 for blocks with few bins (F <= 64): one WARP per frame, eight frames per CTA iteration, grid-stride.  Lane
+// (c8 = lane & 7, fq = lane >> 3) sums chunk c8 over the bins f = fq, fq + 4, ..: one load instruction of the warp reads
+// four neighbouring positions (64 contiguous bytes) of each of the eight planes.  The per-frame MLP runs inside the warp
+// (same operation order as mlp_apply).  The CTA-per-four-frames kernel above spends ~10 us of fixed latency per CTA, which
+// is all there is at F <= 32 (0.24 ms per launch whatever the size); this one does not.
+__global__ void __launch_bounds__(256) ctfa_ta_warp_sh_kernel(const uint8_t* __restrict__ x, MlpW ta, float* __restrict__ ta_out, int F,
+                                                             long long frames) {
+    __shared__ MlpSmem w_s;
+    __shared__ float mean_s[8][64];
+    __shared__ float h_s[8][16];
+    mlp_stage(w_s, ta);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c8 = lane & 7, fq = lane >> 3;
+    for (long long frame = (long long)blockIdx.x * 8 + warp; frame < frames; frame += (long long)gridDim.x * 8) {
+        const uint8_t* row = x + (size_t)frame * F * 256;
+        float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+        for (int f = fq; f < F; f += 4) {
+            float v[8];
+            sh16_load8(row, F, 64, f, c8, v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s[e] += v[e];
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            s[e] += __shfl_xor_sync(0xffffffffu, s[e], 8);
+            s[e] += __shfl_xor_sync(0xffffffffu, s[e], 16);
+        }
+        if (fq == 0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) mean_s[warp][c8 * 8 + e] = s[e] / (float)F;
+        }
+        __syncwarp();
+        if (lane < 16) {
+            float a = w_s.b0[lane];
+#pragma unroll 16
+            for (int k = 0; k < 64; ++k) a = fmaf(mean_s[warp][k], w_s.k0[k * 16 + lane], a);
+            h_s[warp][lane] = fmaxf(a, 0.0f);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const int c = lane + 32 * hf;
+            float o = w_s.b1[c];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o = fmaf(h_s[warp][j], w_s.k1[j * 64 + c], o);
+            ta_out[frame * 64 + c] = sigmoidf_(o);
+        }
+        __syncwarp();
+    }
+}
+
 // storage position of bin f inside a plane: natural order, or [even bins | odd bins]
 __device__ __forceinline__ int sh16_pos(int f, int F, int eo) { return eo ? (f & 1) * (F >> 1) + (f >> 1) : f; }
 
