@@ -1319,8 +1319,12 @@ struct Engine {
                 ctfa_ta_kernel<<<frames, 256, 0, r.st>>>(pp->cur(x, r.parity), E.mlpw(mta), pp->cur(ta, 0), F0);
             E.check_launch("ctfa_ta", frames * 4.0 * (F0 * 64 + 64));
             const int div32 = pp->streaming ? 1 : (off_mode == NUNET_CTFA_FRAME_DIV32);
-            ctfa_gate_kernel<<<frames, 64, 0, r.st>>>(pp->cur(ta, 0), E.mlpw(mfa), pp->cur(gate, 0), r.T, div32,
-                                                     ring ? pp->cur(ring, 0) : nullptr, r.ring_pos);
+            if (!ring && frames >= 64)
+                ctfa_gate_warp_kernel<<<std::min((frames + 7) / 8, E.num_sms * 8), 256, 0, r.st>>>(pp->cur(ta, 0), E.mlpw(mfa), pp->cur(gate, 0),
+                                                                                                    r.T, div32, (long long)frames);
+            else
+                ctfa_gate_kernel<<<frames, 64, 0, r.st>>>(pp->cur(ta, 0), E.mlpw(mfa), pp->cur(gate, 0), r.T, div32,
+                                                         ring ? pp->cur(ring, 0) : nullptr, r.ring_pos);
             E.check_launch("ctfa_gate", frames * 4.0 * (64 + 64));
             const long long n4 = (long long)frames * F0 * 16;
             if (pp->sh16 && fuse_out_conv) {

@@ -197,6 +197,56 @@ __global__ void __launch_bounds__(256) ctfa_ta_warp_sh_kernel(const uint8_t* __r
     }
 }
 
+// CTFA stage 2 (see ctfa_gate_kernel) with one WARP per frame and the MLP weights staged once per CTA: lane l owns channels
+// l and l + 32.  Same summation order (oldest row first) and MLP operation order as ctfa_gate_kernel, so the results are
+// bit-identical; no ring (offline plans and the reference's one-frame rule only).
+__global__ void __launch_bounds__(256) ctfa_gate_warp_kernel(const float* __restrict__ ta, MlpW fa, float* __restrict__ gate, int T,
+                                                            int mode_div32, long long frames) {
+    __shared__ MlpSmem w_s;
+    __shared__ float avg_s[8][64];
+    __shared__ float h_s[8][16];
+    mlp_stage(w_s, fa);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (long long frame = (long long)blockIdx.x * 8 + warp; frame < frames; frame += (long long)gridDim.x * 8) {
+        const float tv0 = ta[frame * 64 + lane], tv1 = ta[frame * 64 + 32 + lane];
+        float a0, a1;
+        if (mode_div32) {
+            a0 = tv0 * (1.0f / CTFA_WINDOW);
+            a1 = tv1 * (1.0f / CTFA_WINDOW);
+        } else {
+            const int t = (int)(frame % T);
+            const int n = min(t + 1, CTFA_WINDOW);
+            float s0 = 0.0f, s1 = 0.0f;
+            for (int d = n - 1; d >= 0; --d) {
+                s0 += ta[(frame - d) * 64 + lane];
+                s1 += ta[(frame - d) * 64 + 32 + lane];
+            }
+            a0 = s0 * (1.0f / CTFA_WINDOW);
+            a1 = s1 * (1.0f / CTFA_WINDOW);
+        }
+        avg_s[warp][lane] = a0;
+        avg_s[warp][32 + lane] = a1;
+        __syncwarp();
+        if (lane < 16) {
+            float a = w_s.b0[lane];
+#pragma unroll 8
+            for (int k = 0; k < 64; ++k) a = fmaf(avg_s[warp][k], w_s.k0[k * 16 + lane], a);
+            h_s[warp][lane] = fmaxf(a, 0.0f);
+        }
+        __syncwarp();
+        float o0 = w_s.b1[lane], o1 = w_s.b1[32 + lane];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            o0 = fmaf(h_s[warp][j], w_s.k1[j * 64 + lane], o0);
+            o1 = fmaf(h_s[warp][j], w_s.k1[j * 64 + 32 + lane], o1);
+        }
+        gate[frame * 64 + lane] = sigmoidf_(o0) * tv0;
+        gate[frame * 64 + 32 + lane] = sigmoidf_(o1) * tv1;
+        __syncwarp();
+    }
+}
+
 // storage position of bin f inside a plane: natural order, or [even bins | odd bins]
 __device__ __forceinline__ int sh16_pos(int f, int F, int eo) { return eo ? (f & 1) * (F >> 1) + (f >> 1) : f; }
 
