@@ -100,7 +100,12 @@ struct Tc3Params {
                            // holds the weights of channel half r; the leader's MMA reads both CTAs' images and weight halves.  The
                            // two tiles of a pair lie pair_m tiles (a whole number of frame rows) apart, so both images start at the
                            // same offset inside their first frame row and one A descriptor serves both CTAs.
-    int pair_m;            // P / gcd(P, 128)
+    int pair_m;            // P / gcd(P, 128); row tiles: tiles per frame row (the partner works one frame row further)
+    int row_tpr;           // 0: tiles are consecutive runs of 128 flat positions.  > 0 ("row tiles", units with F_conv a multiple of
+                           // 128): tile u covers bins [128 j, 128 j + 128) of frame row u / row_tpr, j = u % row_tpr -- no pad position is
+                           // ever computed and a tile image starts at a fixed offset of its first frame row (fewest box rows)
+    int tile2_off;         // flat distance between the two tiles of an iteration (mt == 2): 128, or P for one row tile per row
+    int tm_dmin;           // min(tm_delta): the image may start tm_dmin positions late without losing its first position
     int cluster;           // 1: launched as 2-CTA clusters (the two halves of a 128-channel unit): bulk copies are multicast
     int tma;               // 1: row segments move with 1-D bulk copies; 2: whole tile images move as tensor-map boxes (see tm*)
     // tma == 2: a tile whose frame rows lie inside one clip is fetched with ONE cp.async.bulk.tensor per (plane, image):
@@ -183,10 +188,10 @@ struct T3TileGeo {
     int xoff;      // qa - rho_a * P
     int b, t;      // clip and frame (may be -1: the causal pad row) of frame row rho_a
 };
-__device__ __forceinline__ T3TileGeo t3_tile_geo(int qa, int P, int Tp, int padrow, int slots, int dmax) {
+__device__ __forceinline__ T3TileGeo t3_tile_geo(int qa, int P, int Tp, int padrow, int slots, int dmax, int dmin) {
     T3TileGeo g;
-    const int rho_a = floor_div(qa, P);
-    g.xoff = qa - rho_a * P;
+    const int rho_a = floor_div(qa + dmin, P);   // image index of flat position f is f - rho_a * P + delta >= 0
+    g.xoff = qa - rho_a * P;                      // >= -dmin
     const int need = (g.xoff + dmax + slots - 1) / P + 1;       // frame rows the MMAs can touch
     g.b = floor_div(rho_a, Tp);
     const int tp = rho_a - g.b * Tp;
@@ -447,14 +452,20 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
     const int Tp = p.T + p.padrow;
     const int cta = (int)blockIdx.x / p.nhalf, ncta = (int)gridDim.x / p.nhalf;
     const int my_tiles = (cta < p.ntiles) ? (p.ntiles - cta + ncta - 1) / ncta : 0;
-    const int tile_pos = p.mt * 128;
     // first flat position of the tile CTA-rank `r` works on in iteration `it`.  Pair mode: cluster unit u = (block, j) maps to
     // the 128-position tiles block * 2m + j (rank 0) and block * 2m + j + m (rank 1), m * 128 = a whole number of frame rows.
     auto tile_q = [&](int it, int r) {
         const int u = cta + it * ncta;
-        if (!PAIR) return u * tile_pos;
-        const int blk = u / p.pair_m, j = u - blk * p.pair_m;
-        return (blk * 2 * p.pair_m + j + r * p.pair_m) * 128;
+        int unit;                                  // index of the 128-position tile
+        if (PAIR) {
+            const int blk = u / p.pair_m, j = u - blk * p.pair_m;
+            unit = blk * 2 * p.pair_m + j + r * p.pair_m;
+        } else {
+            unit = u * p.mt;
+        }
+        if (p.row_tpr == 0) return unit * 128;
+        const int rw = unit / p.row_tpr;
+        return rw * p.P + p.xlo + (unit - rw * p.row_tpr) * 128;
     };
 
     if (warp < T3_EPI_WARPS) {
@@ -527,7 +538,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
                 for (int g = 0; g < NPX; ++g) ln_prelu_s<PC>(v + g * PC / 2, par_s + 128, par_s + 192, alpha);
             }
             // where this row goes (computed only now: nothing of it has to stay live across the arithmetic above)
-            const int q = tile_q(it, half) + mt * 128 + row;
+            const int q = tile_q(it, half) + mt * p.tile2_off + row;
             const int rho = q / p.P;
             const int x = q - rho * p.P;
             const int b = rho / Tp;
@@ -597,10 +608,10 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
             const int q0 = tile_q(it, half) - p.lead;
             const long long tl0 = clock64();
             if (p.tma == 2) {
-                const T3TileGeo tg = t3_tile_geo(q0, p.P, Tp, p.padrow, p.slots, max(p.tm_delta[0], p.tm_delta[1]));
+                const T3TileGeo tg = t3_tile_geo(q0, p.P, Tp, p.padrow, p.slots, max(p.tm_delta[0], p.tm_delta[1]), p.tm_dmin);
                 // pair mode: one A descriptor serves both CTAs, so both must use the same image layout
                 const int peer_box = PAIR ? t3_tile_geo(tile_q(it, half ^ 1) - p.lead, p.P, Tp, p.padrow, p.slots,
-                                                          max(p.tm_delta[0], p.tm_delta[1])).box : 1;
+                                                          max(p.tm_delta[0], p.tm_delta[1]), p.tm_dmin).box : 1;
                 if (tg.box && peer_box) {
                     // one box per image into this warp's plane; 32 arrivals per warp keep the barrier count of the fallback
                     for (int ph = 0; ph < p.nphase; ++ph, ++g) {
@@ -797,6 +808,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
         int buf = 0, round = 0;
         long long tm_full = 0, tm_acc = 0;                         // per-role cycle counters (Tc3Params::timing)
         const long long tm_begin = clock64();
+        const uint32_t t2 = (uint32_t)p.tile2_off;                 // second tile of an iteration, in image positions
         uint32_t tap_img1 = 0;                                     // bit tap: the tap reads image 1
         for (int tap = 0; tap < p.ntaps; ++tap) tap_img1 |= (uint32_t)p.tap_img[tap] << tap;
         if (PAIR && half == 1) {
@@ -808,8 +820,8 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
                     if (lane == 0) mbar_arrive_peer(&peer_acc_empty[it & 1], 0);
                 }
                 const int dm = max(p.tm_delta[0], p.tm_delta[1]);
-                const bool boxed = t3_tile_geo(tile_q(it, 0) - p.lead, p.P, Tp, p.padrow, p.slots, dm).box &&
-                                   t3_tile_geo(tile_q(it, 1) - p.lead, p.P, Tp, p.padrow, p.slots, dm).box;
+                const bool boxed = t3_tile_geo(tile_q(it, 0) - p.lead, p.P, Tp, p.padrow, p.slots, dm, p.tm_dmin).box &&
+                                   t3_tile_geo(tile_q(it, 1) - p.lead, p.P, Tp, p.padrow, p.slots, dm, p.tm_dmin).box;
                 for (int ph = 0; ph < p.nphase; ++ph) {
                     mbar_wait(&a_full[buf], round);
                     if (!boxed) fence_proxy_async();   // only the cp.async fallback writes through the generic proxy
@@ -828,9 +840,9 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
             uint32_t adj0 = 0, adj1 = 0;
             bool boxed = false;
             if (p.tma == 2) {
-                const T3TileGeo tg = t3_tile_geo(tile_q(it, 0) - p.lead, p.P, Tp, p.padrow, p.slots, max(p.tm_delta[0], p.tm_delta[1]));
+                const T3TileGeo tg = t3_tile_geo(tile_q(it, 0) - p.lead, p.P, Tp, p.padrow, p.slots, max(p.tm_delta[0], p.tm_delta[1]), p.tm_dmin);
                 const int peer_box = PAIR ? t3_tile_geo(tile_q(it, 1) - p.lead, p.P, Tp, p.padrow, p.slots,
-                                                          max(p.tm_delta[0], p.tm_delta[1])).box : 1;
+                                                          max(p.tm_delta[0], p.tm_delta[1]), p.tm_dmin).box : 1;
                 if (tg.box && peer_box) {
                     boxed = true;
                     adj0 = (uint32_t)(tg.xoff + p.tm_delta[0]);
@@ -870,10 +882,10 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
                                 } else {
                                 // the two tiles' accumulators alternate, so back-to-back MMAs never chain on one accumulator
                                 tc_mma_f16_w(d0, al, da_hiw, wlow, db_hiw, IDESC_2N, acc);                                   // a_hi x [b_hi | b_lo]
-                                if (p.mt == 2) tc_mma_f16_w(d0 + 2 * N, al + 128, da_hiw, wlow, db_hiw, IDESC_2N, acc);
+                                if (p.mt == 2) tc_mma_f16_w(d0 + 2 * N, al + t2, da_hiw, wlow, db_hiw, IDESC_2N, acc);
                                 if (!(p.dbg & 64)) {
                                     tc_mma_f16_w(d0, al + a_lo_delta, da_hiw, wlow, db_hiw, IDESC_N, 1u);                    // a_lo x b_hi
-                                    if (p.mt == 2) tc_mma_f16_w(d0 + 2 * N, al + 128 + a_lo_delta, da_hiw, wlow, db_hiw, IDESC_N, 1u);
+                                    if (p.mt == 2) tc_mma_f16_w(d0 + 2 * N, al + t2 + a_lo_delta, da_hiw, wlow, db_hiw, IDESC_N, 1u);
                                 }
                                 }
                             }

@@ -392,6 +392,7 @@ struct Engine {
     int tc3_tma = 2;         // NUNET_TC3_TMA: 0 = cp.async loaders everywhere, 1 = 1-D bulk copies per frame-row segment (F >= 32),
                              // 2 (default) = one tensor-map box per tile image where the source order allows, else as 1
     int tc3_box_strided = 1; // NUNET_TC3_BOX_STRIDED=0 (experiments): stride-2 units over bin-ordered sources stay on the slot-table loader
+    int tc3_row_tiles = 1;   // NUNET_TC3_ROW_TILES=0: flat 128-position tiles for every unit
     int tc3_pair = 1;        // NUNET_TC3_PAIR=0: 128-channel units run as two independent CTAs per tile instead of cta_group::2 pairs
     int tc3_pair_minf = 4;   // NUNET_TC3_PAIR_MINF (experiments)
     int tc3_box_minf = 4;    // NUNET_TC3_BOX_MINF (experiments): smallest F_conv of a unit that uses tensor-map boxes
@@ -944,8 +945,9 @@ struct Engine {
                 p.tm_delta[i] = (L.stride == 2 && src_eo) ? (p.img_add[i] - par) / 2 : p.img_add[i];     // a_i: storage position read by x = 0
                 cmin = std::min(cmin, p.tm_delta[i]);
             }
+            (void)cmin;
             for (int i = 0; i < p.nimg; ++i) {
-                const int c = box_lines ? (cmin < 0 ? -8 : 0) : p.tm_delta[i];     // first storage position of a box row
+                const int c = box_lines ? (p.tm_delta[i] < 0 ? -8 : 0) : p.tm_delta[i];     // first storage position of a box row
                 p.tm_delta[i] -= c;
                 box_dmax = std::max(box_dmax, p.tm_delta[i]);
                 if (c + (box_strided ? 2 : 1) * p.P < (box_strided ? F_in : Fp)) fail(NUNET_EINVAL, "conv_tc3: box row does not cover the source row");
@@ -969,11 +971,24 @@ struct Engine {
             while (b) { const int r = g % b; g = b; b = r; }
             return p.P - g + (g - p.lead % g) % g;
         };
+        // Row tiles (units whose F_conv is a multiple of 128): tile u covers bins [128 j, 128 j + 128) of one frame row, so no pad
+        // position is computed and every image starts 128 j positions into its first frame row -- the fewest box rows.
+        const int row_tpr = (box && tc3_row_tiles && p.F_conv % 128 == 0) ? p.F_conv / 128 : 0;
+        const int tile2_off = (row_tpr == 1) ? p.P : 128;
+        auto box_rows = [&](int mt, int slots) {
+            if (!row_tpr) return (box_xoff_max(mt) + box_dmax + slots - 1) / p.P + 1;
+            int rows = 0;
+            for (int k = 0; k < row_tpr; ++k) {      // an iteration starts at tile k * mt of some frame row
+                const int j = (k * mt) % row_tpr;
+                rows = std::max(rows, (128 * j + box_dmax + slots - 1) / p.P + 1);
+            }
+            return rows;
+        };
         auto geometry = [&](int mt, int& slots, int& plane_bytes, size_t& abuf) {
-            slots = mt * 128 + maxoff;
+            slots = 128 + (mt - 1) * tile2_off + maxoff;
             int plane16 = (p.nimg * slots + 31) / 32 * 32;   // both images + the loaders' round-up padding
             if (box) {   // whole frame rows per image, every image and plane on a 128-byte boundary (tensor-copy destination)
-                const int rows = (box_xoff_max(mt) + box_dmax + slots - 1) / p.P + 1;
+                const int rows = box_rows(mt, slots);
                 const int img16 = (rows * p.P + 7) / 8 * 8;
                 plane16 = std::max(plane16, p.nimg * img16);
                 if (rows > 256) return 0;
@@ -1017,7 +1032,7 @@ struct Engine {
         const size_t smem = fixed + (size_t)p.nabuf * (two ? abuf2 : abuf1);
         if (!ok) fail(NUNET_EINVAL, "conv_tc3: unit does not fit shared memory");
         if (box) {
-            p.tm_rows = (box_xoff_max(p.mt) + box_dmax + p.slots - 1) / p.P + 1;
+            p.tm_rows = box_rows(p.mt, p.slots);
             p.tm_box_bytes = p.tm_rows * p.P * 16;
             p.tm_img_bytes = (p.tm_rows * p.P + 7) / 8 * 8 * 16;
             const int planes = (src_eo ? 2 : 1) * (L.CA / 4);          // hi | lo  x  C/8 chunks (x parity halves)
@@ -1026,13 +1041,18 @@ struct Engine {
             p.tm_map[0] = tc3_tensor_map(p.src0, Fm, planes, T, B, (size_t)F_in * L.CA * 4, p.P, p.tm_rows, kind);
             if (p.src1) p.tm_map[1] = tc3_tensor_map(p.src1, Fm, planes, T, B, (size_t)F_in * L.CA * 4, p.P, p.tm_rows, kind);
         }
-        p.ntiles = (int)((total + p.mt * 128 - 1) / (p.mt * 128));
+        p.row_tpr = row_tpr;
+        p.tile2_off = tile2_off;
+        p.tm_dmin = 0;
+        // 128-position tiles of the launch: consecutive runs of the flat axis, or row_tpr per frame row
+        const long long units = row_tpr ? (long long)B * (T + p.padrow) * row_tpr : (total + 127) / 128;
+        p.ntiles = (int)((units + p.mt - 1) / p.mt);
         if (pair) {
             int g = 128, b = p.P;
             while (b) { const int r = g % b; g = b; b = r; }
             p.pair = 1;
-            p.pair_m = p.P / g;                                          // tiles between the two CTAs of a pair = 128 / g frame rows
-            p.ntiles = (p.ntiles + 2 * p.pair_m - 1) / (2 * p.pair_m) * p.pair_m;   // cluster work units
+            p.pair_m = row_tpr ? row_tpr : p.P / g;                      // tiles between the two CTAs of a pair: a whole number of frame rows
+            p.ntiles = (int)((units + 2 * p.pair_m - 1) / (2 * p.pair_m)) * p.pair_m;   // cluster work units
         }
         const int grid = std::max(1, std::min(p.ntiles, num_sms / p.nhalf)) * p.nhalf;
         const bool ln = (L.epi != EPI_BIAS);
@@ -1848,6 +1868,7 @@ int nunet_create(const nunet_config* cfg, const void* blob, size_t blob_bytes, n
         if (const char* c = getenv("NUNET_TC3_CLUSTER")) E.tc3_cluster = atoi(c);
         if (const char* c = getenv("NUNET_TC3_BOX_MINF")) E.tc3_box_minf = atoi(c);
         if (const char* c = getenv("NUNET_TC3_PAIR")) E.tc3_pair = atoi(c);
+        if (const char* c = getenv("NUNET_TC3_ROW_TILES")) E.tc3_row_tiles = atoi(c);
         if (const char* c = getenv("NUNET_STREAM_GRAPH")) E.stream_graphs = atoi(c);
         if (const char* c = getenv("NUNET_STREAM_SPLIT")) E.stream_split = std::max(1, std::min(4, atoi(c)));
         if (const char* c = getenv("NUNET_TC3_PAIR_MINF")) E.tc3_pair_minf = atoi(c);
