@@ -29,18 +29,27 @@
 // Stride-2 units keep two images (even / odd input bins) back to back inside every plane.
 //
 // Weights stay RESIDENT in shared memory for the whole (persistent) CTA: units with 128 conv channels (last spconv
-// of a block, up_sampling o inconv) are two independent 64-column problems (their LayerNorm runs over each half),
-// so CTA 2c / 2c+1 take half 0 / 1 of the same tiles and every CTA holds <= 96 KB of weights.  The host permutes
-// the weight columns into output-channel order, so the sub-pixel shuffles cost nothing here.
+// of a block, up_sampling o inconv) are two 64-column problems (their LayerNorm runs over each half), so every CTA
+// holds <= 96 KB of weights.  The host permutes the weight columns into output-channel order, so the sub-pixel
+// shuffles cost nothing here.  Those units run as CTA PAIRS (template PAIR, 2-CTA clusters): CTA r owns one
+// 128-position tile and the weights of half r, and the leader issues tcgen05.mma.cta_group::2 (M = 256) over both
+// CTAs' images and weight halves -- see Tc3Params::pair.  (Fallback NUNET_TC3_PAIR=0: CTA 2c / 2c+1 take half 0 / 1
+// of the same tiles independently.)
 //
-// CTA = 13 warps, persistent over tiles of mt*128 flat positions:
-//   warps 0-7   epilogue  two groups of four warps (one M=128 accumulator each, so two warps share every SM
-//                         sub-partition and hide each other's latencies): TMEM -> registers (one thread = one
-//                         position, all its channels: LayerNorm is thread-local) -> bias / two-pass LN / PReLU ->
-//                         hi/lo split -> 16-byte stores, coalesced across the warp by the planar layout
-//   warps 8-11  loaders   one warp per plane (hi|lo x chunk): cp.async (zero-filled pads) into a ring of image
-//                         buffers, NB-1 buffers ahead
-//   warp  12    MMA       one elected thread: tcgen05.mma kind::f16, M=128, N, K=16; accumulators double-buffered
+// CTA = 13 warps, persistent over tiles of mt*128 positions:
+//   warps 0-7   epilogue  two groups of four warps (two warps share every SM sub-partition and hide each other's
+//                         latencies): TMEM -> registers (one thread = one position, all its channels: LayerNorm is
+//                         thread-local) -> bias / two-pass LN / PReLU -> hi/lo split -> 16/32-byte stores, coalesced
+//                         across the warp by the planar layout
+//   warps 8-11  loaders   one warp per plane (hi|lo x chunk) into a ring of image buffers.  Default (tma = 2): ONE
+//                         cp.async.bulk.tensor box per tile image -- whole frame rows, pads and the causal time pad
+//                         zero-filled by the copy engine (Tc3Params::tm_*); tiles that straddle two clips, streaming
+//                         (history row from the other parity's buffer) and NUNET_TC3_TMA=0 use 16-byte cp.async from a
+//                         per-tile slot table; NUNET_TC3_TMA=1 uses 1-D bulk copies per frame-row segment
+//   warp  12    MMA       one elected thread: tcgen05.mma kind::f16, M=128 (256 for pairs), K=16; accumulators
+//                         double-buffered in TMEM, buffers freed by tcgen05.commit
+// Tiles are consecutive runs of 128 flat positions, or, for units with a multiple of 128 output bins, 128-bin pieces
+// of one frame row (Tc3Params::row_tpr): no pad position is computed and box images need the fewest rows.
 #pragma once
 #include <cuda.h>        // CUtensorMap
 #include <cuda_fp16.h>

@@ -938,14 +938,11 @@ struct Engine {
         if (box) {
             p.tma = 2;
             p.tm_rank = (box_lines || box_strided) ? 5 : 4;
-            int cmin = 0;
             for (int i = 0; i < p.nimg; ++i) {
                 const int par = (L.stride == 2 && src_eo) ? (p.img_add[i] & 1) : 0;
                 p.tm_par[i] = par;
                 p.tm_delta[i] = (L.stride == 2 && src_eo) ? (p.img_add[i] - par) / 2 : p.img_add[i];     // a_i: storage position read by x = 0
-                cmin = std::min(cmin, p.tm_delta[i]);
             }
-            (void)cmin;
             for (int i = 0; i < p.nimg; ++i) {
                 const int c = box_lines ? (p.tm_delta[i] < 0 ? -8 : 0) : p.tm_delta[i];     // first storage position of a box row
                 p.tm_delta[i] -= c;
