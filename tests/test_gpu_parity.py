@@ -450,3 +450,50 @@ def test_streaming_graph_with_parallel_chains_equals_plain_launches(blob, ddb_we
         eng.close()
     for a, g in zip(outs["0"], outs["1"]):
         assert np.isfinite(g).all() and np.abs(a - g).max() <= 1e-6
+
+
+def test_full_size_batch_properties(blob, oracles):
+    """BASELINE configs[1] at FULL size (256 clips x 4 s = 63 744 frames, the bench workload), checked through properties
+    that do not need an oracle run of that size: (a) copies of one clip anywhere in the batch come out bit-identical
+    (tiles straddle clips, CTA pairs work on rows of different clips, boxes zero-fill the time pads -- none of it may
+    leak between clips), (b) the first clips equal a 2-clip run of another engine bit for bit, (c) those two clips match
+    the oracle within the bar, (d) everything is finite."""
+    from nunet_b200.synth import synth_clips
+    B, N, T = 256, 64000, 249
+    pool = synth_clips(32, N, first_clip=200)
+    wav = np.tile(pool, (B // 32, 1))
+    eng = _engine(blob, max_frames=B * T)
+    y, est = eng.forward_wav(torch.from_numpy(wav).cuda())
+    y, est = y.cpu().numpy(), est.cpu().numpy()
+    eng.close()
+    assert est.shape == (B, T, 257) and np.isfinite(est).all() and np.isfinite(y).all()
+    for k in range(1, B // 32):
+        assert np.array_equal(est[:32], est[32 * k:32 * (k + 1)]), k
+        assert np.array_equal(y[:32], y[32 * k:32 * (k + 1)]), k
+    small = _engine(blob, max_frames=2 * T)
+    y2, est2 = small.forward_wav(torch.from_numpy(wav[:2]).cuda())
+    assert np.array_equal(est[:2], est2.cpu().numpy()) and np.array_equal(y[:2], y2.cpu().numpy())
+    with torch.no_grad():
+        y_ref, est_ref = oracles["causal_avg32"].forward_wav(wav[:2])
+    assert np.abs(est[:2] - est_ref.numpy()).max() <= TOL_MAG
+    assert np.abs(y[:2] - y_ref.numpy()).max() <= TOL_WAV
+
+
+def test_full_size_streaming_properties(blob):
+    """BASELINE configs[2] at FULL size (1024 concurrent streams): copies of one stream anywhere among the 1024 stay
+    bit-identical over 8 hops (graph replay included), and equal the same streams run alone on a 16-stream engine."""
+    from nunet_b200.synth import synth_clips
+    S, steps = 1024, 8
+    pool = synth_clips(16, 256 * steps, first_clip=300)
+    wav = np.tile(pool, (S // 16, 1))
+    big, small = _engine(blob, max_streams=S), _engine(blob, max_streams=16)
+    big.stream_reset()
+    small.stream_reset()
+    for t in range(steps):
+        hop = wav[:, 256 * t:256 * (t + 1)]
+        yb = big.stream_step_wav(torch.from_numpy(hop).cuda()).cpu().numpy()
+        ys = small.stream_step_wav(torch.from_numpy(hop[:16]).cuda()).cpu().numpy()
+        assert np.isfinite(yb).all()
+        for k in range(1, S // 16):
+            assert np.array_equal(yb[:16], yb[16 * k:16 * (k + 1)]), (t, k)
+        assert np.array_equal(yb[:16], ys), t
