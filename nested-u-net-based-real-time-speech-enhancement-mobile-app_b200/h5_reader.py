@@ -124,6 +124,74 @@ class _H5:
         return np.frombuffer(b, dtype=dtype, count=n, offset=addr).reshape(shape).copy()
 
 
+def _attr_strings(h: _H5, body: int, msize: int):
+    """Decode one attribute message (v1) holding a string or an array of strings: fixed-length (class 3) or
+    variable-length (class 9, elements are global-heap references) -- the two forms h5py writes.  Returns (name, value)."""
+    b = h.b
+    if b[body] != 1:
+        raise H5FormatError("attribute message version")
+    nsz, dtsz, dssz = struct.unpack_from("<HHH", b, body + 2)
+    pad = lambda x: (x + 7) // 8 * 8
+    name = b[body + 8:body + 8 + nsz].split(b"\0")[0].decode()
+    dt = body + 8 + pad(nsz)
+    ds = dt + pad(dtsz)
+    data = ds + pad(dssz)
+    rank = b[ds + 1]
+    dims = struct.unpack_from("<" + "Q" * rank, b, ds + 8) if rank else ()
+    n = int(np.prod(dims)) if rank else 1
+    cls = b[dt] & 0x0F
+    esize = struct.unpack_from("<I", b, dt + 4)[0]
+    vals = []
+    for i in range(n):
+        if cls == 3:
+            raw = b[data + i * esize:data + (i + 1) * esize]
+            vals.append(raw.split(b"\0")[0].decode())
+        elif cls == 9:
+            ln, addr, idx = struct.unpack_from("<IQI", b, data + i * 16)
+            if b[addr:addr + 4] != b"GCOL":
+                raise H5FormatError("bad global heap")
+            pos, s_val = addr + 16, None
+            end = addr + struct.unpack_from("<Q", b, addr + 8)[0]
+            while pos + 16 <= end:
+                oidx, _ref, _r, osize = struct.unpack_from("<HHIQ", b, pos)
+                if oidx == idx:
+                    s_val = b[pos + 16:pos + 16 + ln].decode()
+                    break
+                if oidx == 0:
+                    break
+                pos += 16 + pad(osize)
+            if s_val is None:
+                raise H5FormatError("global heap object not found")
+            vals.append(s_val)
+        else:
+            raise H5FormatError(f"unsupported attribute datatype class {cls}")
+    return name, (vals if rank else vals[0])
+
+
+def read_h5_attrs(path: str) -> Dict[str, Dict[str, object]]:
+    """String attributes of every group: `{'': {'layer_names': [...], 'backend': ..}, '/conv2d': {'weight_names': [...]}}`
+    (what `keras.Model.load_weights` walks: `layer_names` on the root, `weight_names` on each layer group)."""
+    with open(path, "rb") as f:
+        h = _H5(f.read())
+    out: Dict[str, Dict[str, object]] = {}
+
+    def rec(header: int, prefix: str):
+        kids = h.children(header)
+        if kids is None:
+            return
+        attrs = {}
+        for mtype, body, msize in h.messages(header):
+            if mtype == 0x0C:
+                k, v = _attr_strings(h, body, msize)
+                attrs[k] = v
+        out[prefix] = attrs
+        for name, hdr in kids.items():
+            rec(hdr, prefix + "/" + name)
+
+    rec(h.root_header, "")
+    return out
+
+
 def read_h5(path: str) -> Dict[str, np.ndarray]:
     """Return `{'/group/.../name:0': ndarray}` for every dataset in a Keras weight file."""
     with open(path, "rb") as f:

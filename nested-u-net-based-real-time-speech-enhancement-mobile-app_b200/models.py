@@ -49,6 +49,17 @@ class _Model:
         self._weights, self._blob, self._engine = w, pack_blob(w, VARIANT_DDB if ddb else VARIANT_LSTM), None
         return self
 
+    def save_weights(self, path: str):
+        """Keras `model.save_weights(path)` (train_interface.py:99-100): the loaded weight set as a Keras-layout `.h5`
+        (LSTM variant; `keras_export.export_lstm_h5`).  Loading the shipped `.tflite` and saving gives the dequantised
+        checkpoint in the float file format."""
+        if self._blob is None:
+            raise RuntimeError("load_weights() first")
+        if self.variant == NUNET_VARIANT_DDB:
+            raise ValueError("the dilated-dense variant has no .h5 layout in the reference (its only checkpoint is nutls.tflite)")
+        from .keras_export import export_lstm_h5
+        export_lstm_h5(self._weights, path)
+
     def _get_engine(self, frames: int) -> NunetEngine:
         if self._blob is None:
             raise RuntimeError("load_weights() first (the engine has no random initialiser)")

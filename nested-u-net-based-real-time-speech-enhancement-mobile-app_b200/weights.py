@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import re
 import struct
-from typing import Dict
+from typing import Dict, Optional
 
 import numpy as np
 
@@ -53,16 +53,25 @@ def _suffix(name: str) -> int:
     return int(m.group(1)) if m else 0
 
 
-def lstm_weights_from_h5(path: str) -> Dict[str, np.ndarray]:
-    """Role-named float32 weight set of NUNet-TLS-LSTM from the reference `.h5`."""
+def lstm_weights_from_h5(path: str, trace: Optional[Dict[str, str]] = None) -> Dict[str, np.ndarray]:
+    """Role-named float32 weight set of NUNet-TLS-LSTM from the reference `.h5`.  `trace`, when given, receives
+    role key -> dataset path (what `keras_export` needs to write the file back)."""
     raw = read_h5(path)
     groups: Dict[str, Dict[str, Dict[str, np.ndarray]]] = {}
+    paths: Dict[tuple, str] = {}
     for key, arr in raw.items():
         parts = key.strip("/").split("/")
         group, sub, var = parts[0], parts[-2], parts[-1].split(":")[0]
         groups.setdefault(group, {}).setdefault(sub, {})[var] = arr.astype(np.float32)
+        paths[(group, sub, var)] = key
 
     out: Dict[str, np.ndarray] = {}
+
+    def put(role_key: str, group: str, sub: str, var: str, value: np.ndarray) -> None:
+        out[role_key] = value
+        if trace is not None:
+            trace[role_key] = paths[(group, sub, var)]
+
     for group, subs in groups.items():
         role = _H5_TO_DENSE_ROLE.get(group, group)
         if group == "conv2d":
@@ -71,19 +80,20 @@ def lstm_weights_from_h5(path: str) -> Dict[str, np.ndarray]:
         for sub in sorted(subs, key=lambda s: (_suffix(s), s)):
             v = subs[sub]
             if sub.startswith("layer_normalization"):
-                out[f"{role}/gamma"], out[f"{role}/beta"] = v["gamma"], v["beta"]
+                put(f"{role}/gamma", group, sub, "gamma", v["gamma"])
+                put(f"{role}/beta", group, sub, "beta", v["beta"])
             elif sub.startswith("p_re_lu"):
-                out[f"{role}/alpha"] = v["alpha"].reshape(1)
+                put(f"{role}/alpha", group, sub, "alpha", v["alpha"].reshape(1))
             elif sub.startswith("lstm_cell"):
-                out[f"{role}/kernel"] = v["kernel"]
-                out[f"{role}/recurrent_kernel"] = v["recurrent_kernel"]
-                out[f"{role}/bias"] = v["bias"]
+                for var in ("kernel", "recurrent_kernel", "bias"):
+                    put(f"{role}/{var}", group, sub, var, v[var])
             elif role.endswith("_ta") or role.endswith("_fa"):
-                out[f"{role}/kernel{mlp}"] = v["kernel"].reshape(v["kernel"].shape[-2:])
-                out[f"{role}/bias{mlp}"] = v["bias"]
+                put(f"{role}/kernel{mlp}", group, sub, "kernel", v["kernel"].reshape(v["kernel"].shape[-2:]))
+                put(f"{role}/bias{mlp}", group, sub, "bias", v["bias"])
                 mlp += 1
             else:  # Conv2D / Conv2DTranspose / Dense
-                out[f"{role}/kernel"], out[f"{role}/bias"] = v["kernel"], v["bias"]
+                put(f"{role}/kernel", group, sub, "kernel", v["kernel"])
+                put(f"{role}/bias", group, sub, "bias", v["bias"])
     return out
 
 
