@@ -170,7 +170,8 @@ def _options(fb: _FB, op_table: int, op: str) -> Dict[str, object]:
     if op == "GATHER":
         return {"axis": s(t, 0, "i"), "batch_dims": s(t, 1, "i")}
     if op == "FULLY_CONNECTED":
-        return {"act": s(t, 0, "b"), "weights_format": s(t, 1, "b"), "keep_num_dims": bool(s(t, 2, "b"))}
+        return {"act": s(t, 0, "b"), "weights_format": s(t, 1, "b"), "keep_num_dims": bool(s(t, 2, "b")),
+                "asymmetric_quantize_inputs": bool(s(t, 3, "b"))}
     if op == "RESHAPE":
         return {"new_shape": fb.np_vector(t, 0, np.int32)}
     if op in ("ADD", "SUB", "MUL"):

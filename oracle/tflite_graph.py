@@ -34,9 +34,18 @@ def _same_pad(size: int, k: int, stride: int, dil: int):
 class TFLiteGraph:
     """Executes one subgraph in float32.  `run(feed)` takes / returns tensors keyed by signature names."""
 
-    def __init__(self, path: str, dtype=torch.float32):
+    def __init__(self, path: str, dtype=torch.float32, hybrid: bool = False):
+        """hybrid=True emulates what the TFLite runtime actually does with these dynamic-range-quantised files
+        (SURVEY 3A.4 #4, 8(f)3): CONV_2D / FULLY_CONNECTED ops whose weights are int8 run the HYBRID kernels -- the float
+        input is quantised to int8 per call (per batch item for conv, per row for FC), the products are accumulated in
+        int32 and rescaled by input scale x per-channel weight scale.  Restated from the published reference kernels
+        (tensorflow/lite/kernels/conv.cc EvalHybridPerChannel, fully_connected.cc EvalHybrid,
+        internal/reference/portable_tensor_utils.cc Asymmetric/SymmetricQuantizeFloats); no TFLite runtime exists here to
+        pin it against, so it is a model of the deployed arithmetic, not a parity reference.  Default (False): float
+        arithmetic on the dequantised weights, which is what the engine and O1 are tested against."""
         self.g: Graph = read_tflite(path)
         self.dt = dtype
+        self.hybrid = hybrid
         self.sig = self.g.signatures[0]
         self.consts: Dict[int, torch.Tensor] = {}
         for t in self.g.tensors:
@@ -52,6 +61,52 @@ class TFLiteGraph:
         if idx not in self.consts:
             self.consts[idx] = torch.from_numpy(self.g.tensors[idx].dequantized()).to(self.dt)
         return self.consts[idx]
+
+    # ---------------------------------------------------------------- hybrid (dynamic-range) kernels
+    def _is_int8(self, idx: int) -> bool:
+        t = self.g.tensors[idx]
+        return self.hybrid and t.data is not None and t.dtype == np.int8
+
+    def _wq(self, idx: int):
+        """int8 weight values (as float64, exact) and per-output-channel scales (float32) of tensor idx."""
+        t = self.g.tensors[idx]
+        scale = np.asarray(t.scale, np.float32).reshape(-1)
+        n_out = t.shape[0]
+        if scale.size == 1:
+            scale = np.full(n_out, scale[0], np.float32)
+        return torch.from_numpy(t.data.astype(np.float64)), torch.from_numpy(scale)
+
+    @staticmethod
+    def _round_away(x: torch.Tensor) -> torch.Tensor:      # TfLiteRound = std::round: halves away from zero
+        return torch.sign(x) * torch.floor(torch.abs(x) + 0.5)
+
+    @classmethod
+    def _quantize_rows(cls, x2: torch.Tensor, asymmetric: bool):
+        """x2 [rows, n] float32 -> (q - zero_point as float64 [rows, n], scale float32 [rows]) per row, like
+        Asymmetric/SymmetricQuantizeFloats (scale and zero point derived in double, values quantised in float)."""
+        x2 = x2.to(torch.float32)
+        if asymmetric:
+            rmin = torch.clamp(x2.min(dim=1).values.double(), max=0.0)
+            rmax = torch.clamp(x2.max(dim=1).values.double(), min=0.0)
+            flat = rmin == rmax
+            scale = torch.where(flat, torch.ones_like(rmin), (rmax - rmin) / 255.0)
+            zp_min, zp_max = -128.0 - rmin / scale, 127.0 - rmax / scale
+            err_min, err_max = 128.0 + (rmin / scale).abs(), 127.0 + (rmax / scale).abs()
+            zp = torch.where(err_min < err_max, zp_min, zp_max)
+            zp = torch.where(zp <= -128.0, torch.full_like(zp, -128.0),
+                             torch.where(zp >= 127.0, torch.full_like(zp, 127.0), cls._round_away(zp)))
+            zp = torch.where(flat, torch.zeros_like(zp), zp)
+            scale_f = scale.to(torch.float32)
+            inv = (1.0 / scale_f).to(torch.float32)
+            q = cls._round_away(zp.to(torch.float32)[:, None] + x2 * inv[:, None]).clamp(-128, 127)
+            q = torch.where(flat[:, None], torch.zeros_like(q), q)
+            return q.double() - zp[:, None], scale_f
+        rng = x2.abs().max(dim=1).values
+        flat = rng == 0
+        scale_f = torch.where(flat, torch.ones_like(rng), rng / 127.0)
+        inv = torch.where(flat, torch.zeros_like(rng), 127.0 / rng)
+        q = cls._round_away(x2 * inv[:, None]).clamp(-127, 127)
+        return q.double(), scale_f
 
     def input_shapes(self) -> Dict[str, tuple]:
         return {k: self.g.tensors[i].shape for k, i in self.sig.inputs.items()}
@@ -95,7 +150,35 @@ class TFLiteGraph:
     def _exec(self, op: Operator, v, get, ints):
         k, o, a = op.op, op.outputs, op.inputs
         opt = op.options
-        if k == "CONV_2D":
+        if k == "CONV_2D" and self._is_int8(a[1]):
+            # hybrid per-channel conv: the input is quantised per batch item (asymmetric), padding is the zero point
+            x, b = get(a[0]), get(a[2]) if len(a) > 2 else None
+            wq, wscale = self._wq(a[1])
+            sh, sw, dh, dw = opt["stride_h"], opt["stride_w"], opt["dilation_h"], opt["dilation_w"]
+            groups = x.shape[3] // wq.shape[3]
+            xq, xscale = self._quantize_rows(x.reshape(x.shape[0], -1), asymmetric=True)
+            xi = xq.reshape(x.shape).permute(0, 3, 1, 2)
+            if opt["padding"] == 0:   # SAME
+                pt, pb = _same_pad(x.shape[1], wq.shape[1], sh, dh)
+                pl, pr = _same_pad(x.shape[2], wq.shape[2], sw, dw)
+                xi = F.pad(xi, (pl, pr, pt, pb))
+            acc = F.conv2d(xi, wq.permute(0, 3, 1, 2), None, stride=(sh, sw), dilation=(dh, dw), groups=groups)   # exact in float64
+            y = acc.to(torch.float32) * (xscale.reshape(-1, 1, 1, 1) * wscale.reshape(1, -1, 1, 1))
+            if b is not None:
+                y = y + b.to(torch.float32).reshape(1, -1, 1, 1)
+            v[o[0]] = self._act(y.permute(0, 2, 3, 1).to(self.dt), opt["act"])
+        elif k == "FULLY_CONNECTED" and self._is_int8(a[1]):
+            x = get(a[0])
+            b = get(a[2]) if len(a) > 2 and a[2] >= 0 else None
+            wq, wscale = self._wq(a[1])
+            xq, xscale = self._quantize_rows(x.reshape(-1, wq.shape[1]), asymmetric=bool(opt.get("asymmetric_quantize_inputs")))
+            y = (xq @ wq.t()).to(torch.float32) * (xscale[:, None] * wscale[None, :])
+            if b is not None:
+                y = y + b.to(torch.float32)
+            if opt.get("keep_num_dims"):
+                y = y.reshape(*x.shape[:-1], wq.shape[0])
+            v[o[0]] = self._act(y.to(self.dt), opt.get("act", 0))
+        elif k == "CONV_2D":
             x, w, b = get(a[0]), self.weight(a[1]), get(a[2]) if len(a) > 2 else None
             sh, sw, dh, dw = opt["stride_h"], opt["stride_w"], opt["dilation_h"], opt["dilation_w"]
             groups = x.shape[3] // w.shape[3]

@@ -124,3 +124,33 @@ def test_ddb_weight_set_structure(ddb_weights):
     assert sum(v.size for v in ddb_weights.values()) == 2830462
     k = ddb_weights["msfe4_down_sampling/kernel"]
     assert (ddb_weights["msfe4_down_sampling2/kernel"] == k).all() and (ddb_weights["msfe4_down_sampling3/kernel"] == k).all()
+
+
+def test_hybrid_quantisers_follow_the_reference_kernels():
+    """Asymmetric/SymmetricQuantizeFloats (portable_tensor_utils.cc) on hand-checked rows."""
+    from oracle.tflite_graph import TFLiteGraph
+    x = torch.tensor([[-1.0, 0.0, 3.0], [0.0, 0.0, 0.0], [2.0, 4.0, 8.0]])
+    q, s = TFLiteGraph._quantize_rows(x, asymmetric=True)
+    # row 0: scale 4/255, zero point round(-128 + 1/scale) = -64 -> q = (-128, -64, 127); returned minus the zero point
+    assert np.allclose(s.numpy(), [4 / 255, 1.0, 8 / 255]) and q[0].tolist() == [-64.0, 0.0, 191.0] and q[1].tolist() == [0.0, 0.0, 0.0]
+    # all-positive row: zero point -128; 4 lands on -128 + 127.5 = -0.5, which std::round takes away from zero to -1
+    assert q[2].tolist() == [64.0, 127.0, 255.0]
+    q, s = TFLiteGraph._quantize_rows(x, asymmetric=False)
+    assert np.allclose(s.numpy(), [3 / 127, 1.0, 8 / 127]) and q[0].tolist() == [-42.0, 0.0, 127.0] and q[2].tolist() == [32.0, 64.0, 127.0]
+
+
+@needs_ref
+def test_hybrid_emulation_of_the_shipped_graph(golden_o2):
+    """what the TFLite runtime does with the dynamic-range file (int8 activations per call in 170 CONV_2D and
+    35 FULLY_CONNECTED ops) stays close to the float graph -- and nowhere near the 1e-3 bar the engine is held to: on the
+    reference's noisy wav the deployed arithmetic is ~42 dB below the float output (max |d| ~0.7 on a peak of 48)."""
+    from oracle.tflite_graph import TFLiteGraph, stream_frames
+    mag, ref = golden_o2["mag"][:24], golden_o2["model_out"][:24]
+    g = TFLiteGraph(os.path.join(REF_TFLITE, "nutls_lstm.tflite"), hybrid=True)
+    n_hybrid = sum(1 for op in g.g.operators if op.op in ("CONV_2D", "FULLY_CONNECTED") and g._is_int8(op.inputs[1]))
+    assert n_hybrid == 205
+    out = stream_frames(g, mag)
+    snr = 10 * np.log10((ref ** 2).sum() / ((out - ref) ** 2).sum())
+    assert 25.0 < snr < 60.0, snr
+    assert np.abs(out - ref).max() > 1e-2
+    assert np.array_equal(out, stream_frames(TFLiteGraph(os.path.join(REF_TFLITE, "nutls_lstm.tflite"), hybrid=True), mag))
