@@ -129,6 +129,10 @@ int nunet_state_name(nunet_engine* h, int index, char* name_out, int cap);
 int nunet_state_numel(nunet_engine* h, const char* name);
 int nunet_state_export(nunet_engine* h, int stream_id, const char* name, float* buf);
 int nunet_state_import(nunet_engine* h, int stream_id, const char* name, const float* buf);
+/* Counter that changes whenever the resident history changes (a step, a reset, an import).  The signature runner
+ * (interpreter.py) uses it to decide whether the arrays a caller feeds back (interpreter_proposed.py:215 replaces the
+ * whole dict every hop) are still what the engine holds, or must be imported. */
+long long nunet_state_generation(nunet_engine* h);
 
 /* Introspection used by bench.py / tests: kernels launched by the most recent forward/step call. */
 int nunet_last_launch_count(nunet_engine* h);

@@ -20,7 +20,7 @@ EXPORTS = [
     "nunet_last_error", "nunet_abi_version", "nunet_blob_validate", "nunet_create", "nunet_destroy", "nunet_num_frames",
     "nunet_forward_wav_dev", "nunet_forward_wav_host", "nunet_forward_mag_dev",
     "nunet_stream_reset", "nunet_stream_step_mag_dev", "nunet_stream_step_wav_dev", "nunet_stream_step_wav_host",
-    "nunet_state_count", "nunet_state_name", "nunet_state_numel", "nunet_state_export", "nunet_state_import",
+    "nunet_state_count", "nunet_state_name", "nunet_state_numel", "nunet_state_export", "nunet_state_import", "nunet_state_generation",
     "nunet_last_launch_count", "nunet_debug_read",
     "nunet_profile_enable", "nunet_profile_count", "nunet_profile_entry",
 ]
@@ -85,6 +85,8 @@ def lib() -> C.CDLL:
     L.nunet_state_export.argtypes = [vp, i, C.c_char_p, vp]
     L.nunet_state_import.restype = i
     L.nunet_state_import.argtypes = [vp, i, C.c_char_p, vp]
+    L.nunet_state_generation.restype = ll
+    L.nunet_state_generation.argtypes = [vp]
     L.nunet_last_launch_count.restype = i
     L.nunet_last_launch_count.argtypes = [vp]
     L.nunet_profile_enable.restype = i

@@ -55,7 +55,8 @@
 #include <cuda_fp16.h>
 
 #include "common.cuh"
-#include "conv_tc.cuh"   // mbarrier / tcgen05 PTX wrappers, make_desc, tmem_ld32, ln_prelu
+#include "conv_simt.cuh"    // Epi enum
+#include "tcgen05_ptx.cuh"  // mbarrier / tcgen05 PTX wrappers, make_desc, tmem_ld32
 
 namespace nunet {
 

@@ -27,7 +27,6 @@
 
 #include "../../include/nunet_b200.h"
 #include "conv_simt.cuh"
-#include "conv_tc.cuh"
 #include "conv_tc3.cuh"
 #include "framing.cuh"
 #include "misc_kernels.cuh"
@@ -92,11 +91,14 @@ struct Blob {
             if (ndim > 4) fail(NUNET_EINVAL, "weight blob: %s has rank %u", name, ndim);
             Arr a;
             a.n = 1;
+            const size_t avail = (bytes - base) / 4;          // floats behind the table
             for (uint32_t k = 0; k < ndim; ++k) {
+                if (d[k] > 0x7fffffffu) fail(NUNET_EINVAL, "weight blob: %s has a dimension of %u", name, d[k]);
                 a.dims.push_back((int)d[k]);
+                if (d[k] != 0 && a.n > avail / d[k]) fail(NUNET_EINVAL, "weight blob: %s out of range", name);
                 a.n *= d[k];
             }
-            if (base + (off + a.n) * 4 > bytes) fail(NUNET_EINVAL, "weight blob: %s out of range", name);
+            if (off > avail || a.n > avail - off) fail(NUNET_EINVAL, "weight blob: %s out of range", name);
             a.data = reinterpret_cast<const float*>(p + base + off * 4);
             m[name] = a;
         }
@@ -135,7 +137,6 @@ struct ParamPool {
 
 struct ConvLayer {
     size_t w = 0, bias = 0, gamma = 0, beta = 0, alpha = 0;
-    size_t wpk = 0;   // tensor-core path: hi/lo split weights [phase][tap][hi|lo][kchunk][N][4]
     int CA = 0, CB = 0, COUT = 0, KT = 1, KF = 1, padl = 0, stride = 1, epi = EPI_LN;
     // split-half tensor-core path (conv_tc3.cuh): fp16 hi/lo weights, columns in output-channel order
     size_t w3 = 0, b3 = 0;   // float offsets into the pool (w3 holds raw halves)
@@ -166,25 +167,6 @@ static std::vector<float> permute_cols(const std::vector<float>& k, int rows, in
     const int CN = conv_cn(COUT);
     for (int r = 0; r < rows; ++r)
         for (int q = 0; q < COUT; ++q) out[(size_t)r * COUT + q] = k[(size_t)r * COUT + conv_col_to_channel(q, COUT, CN)];
-    return out;
-}
-
-// logical [taps][Cin][COUT] -> 3xTF32 operand stages of conv_tc_kernel
-static std::vector<float> pack_tc(const std::vector<float>& k, int taps, int Cin, int COUT) {
-    const int nph = Cin / TC_KCH, KC4 = TC_KCH / 4;
-    std::vector<float> out((size_t)2 * taps * Cin * COUT);
-    for (int ph = 0; ph < nph; ++ph)
-        for (int tap = 0; tap < taps; ++tap)
-            for (int kc = 0; kc < KC4; ++kc)
-                for (int n = 0; n < COUT; ++n)
-                    for (int e = 0; e < 4; ++e) {
-                        const float w = k[((size_t)tap * Cin + ph * TC_KCH + kc * 4 + e) * COUT + n];
-                        const float hi = host_rna_tf32(w);
-                        const float lo = host_rna_tf32(w - hi);
-                        const size_t stage = ((size_t)ph * taps + tap) * (2 * KC4 * COUT * 4);
-                        out[stage + ((size_t)(0 * KC4 + kc) * COUT + n) * 4 + e] = hi;
-                        out[stage + ((size_t)(1 * KC4 + kc) * COUT + n) * 4 + e] = lo;
-                    }
     return out;
 }
 
@@ -375,6 +357,7 @@ struct Engine {
     Ten *s_mag = nullptr, *s_ph = nullptr, *s_est = nullptr, *s_inbuf = nullptr, *s_outbuf = nullptr;
     int stream_parity = 0;   // parity of the most recent step (its buffers hold the history)
     int stream_steps = 0;
+    long long state_gen = 1;   // bumped whenever the resident history changes (step, reset, import): nunet_state_generation
 
     cudaStream_t own_stream = nullptr;
     float *h_in = nullptr, *h_out = nullptr;   // device staging for the *_host calls
@@ -382,6 +365,7 @@ struct Engine {
     int launches = 0;
     int last_B = 0, last_T = 0;
     int num_sms = 148;
+    bool no_recycle = false; // NUNET_NO_RECYCLE (tools/layer_report.py): every offline tensor keeps its own storage
     bool use_tc = true;     // NUNET_CONV=simt forces the FP32 SIMT units everywhere
     int tc3_fence_mode = 0;  // NUNET_TC3_FENCE
     int tc3_dbg = 0;         // NUNET_TC3_DBG (experiments)
@@ -399,8 +383,6 @@ struct Engine {
     int tc3_tma_minf = 32;   // NUNET_TC3_TMA_MINF (experiments): smallest F_in of a stride-1 unit that uses bulk copies
     int tc3_cluster = 0;     // NUNET_TC3_CLUSTER=1: the two CTAs of a 128-channel unit form a cluster and multicast their bulk copies
                              // (one L2 read feeds both); measured neutral on B200, kept as an option
-    bool use_tc3 = true;    // NUNET_CONV=tc keeps the 3xTF32 kernel (fp32 activations) for the offline plan
-    int tc_min_bins = 1;    // NUNET_TC_MIN_BINS: units with fewer conv-output bins stay on the SIMT kernel
     // per-launch profiling (bench.py roofline leg): one CUDA event after every launch on the launching stream
     bool prof_on = false;
     cudaStream_t prof_stream = nullptr;
@@ -447,7 +429,6 @@ struct Engine {
         L.CA = CA; L.CB = CB; L.COUT = COUT; L.KT = KT; L.KF = KF; L.padl = padl; L.stride = stride; L.epi = epi;
         std::vector<float> kv(k.data, k.data + k.n);
         L.w = pool.add(permute_cols(kv, KT * KF * (CA + CB), COUT));
-        L.wpk = pool.add(pack_tc(kv, KT * KF, CA + CB, COUT));
         L.bias = add_arr(role + "/bias", {COUT});
         {
             const Arr& bb = blob.get(role + "/bias", {COUT});
@@ -512,7 +493,6 @@ struct Engine {
         ConvLayer L;
         L.CA = 64; L.CB = 64; L.COUT = 128; L.KT = 1; L.KF = 2; L.padl = 1; L.stride = 1; L.epi = EPI_SHUF64;
         L.w = pool.add(permute_cols(W, 2 * 128, 128));
-        L.wpk = pool.add(pack_tc(W, 2, 128, 128));
         L.bias = pool.add(B);
         add_tc3(L, W, B);
         L.gamma = add_arr(in_role + "/gamma", {64});
@@ -665,95 +645,6 @@ struct Engine {
         kfn<<<grid, NT, smem, st>>>(p);
         const double frames = (double)p.B * p.T;
         check_launch("conv_unit", frames * 4.0 * ((double)p.F_in * (p.CA + p.CB) + (double)p.F_out * COUT));
-    }
-
-    template <int N, int EPI>
-    void launch_tc_t(const TcParams& p, int grid, size_t smem, cudaStream_t st) {
-        static bool attr_set = false;
-        auto kfn = conv_tc_kernel<N, EPI>;
-        if (!attr_set) {
-            CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            attr_set = true;
-        }
-        kfn<<<grid, TC_THREADS, smem, st>>>(p);
-        const double frames = (double)p.B * p.T;
-        check_launch("conv_tc", frames * 4.0 * ((double)p.F_in * (p.C0 + p.C1) + (double)p.F_conv * N));
-    }
-
-    // Tensor-core path (offline plans).  Returns false when the unit is not eligible (caller falls back to SIMT).
-    bool launch_conv_tc(const ConvLayer& L, const float* a_cur, const float* b_cur, float* out, int B, int T, int F_in,
-                        cudaStream_t st) {
-        TcParams p{};
-        p.src0 = a_cur; p.src1 = b_cur; p.C0 = L.CA; p.C1 = L.CB;
-        p.wpk = pool.at(L.wpk); p.bias = pool.at(L.bias);
-        p.gamma = pool.at(L.gamma); p.beta = pool.at(L.beta); p.alpha = pool.at(L.alpha);
-        p.out = out; p.B = B; p.T = T; p.F_in = F_in;
-        p.F_conv = (L.stride == 2) ? F_in / 2 : F_in;
-        p.ntaps = L.KT * L.KF;
-        p.padrow = (L.KT == 2) ? 1 : 0;
-        p.nimg = 1;
-        p.img_mul[0] = 1; p.img_add[0] = 0; p.img_mul[1] = 1; p.img_add[1] = 0;
-        int maxoff = 0;
-        if (L.stride == 1 && L.KF == 3 && L.padl == 1 && L.KT == 2) {          // spconv
-            p.P = F_in + 2; p.img_add[0] = -1; p.lead = p.P + 1; p.xlo = 1;
-            for (int kt = 0; kt < 2; ++kt)
-                for (int kf = 0; kf < 3; ++kf) { p.tap_img[kt * 3 + kf] = 0; p.tap_off[kt * 3 + kf] = kt * p.P + kf; }
-        } else if (L.stride == 2 && L.KF == 3 && L.padl == 1 && L.KT == 2) {   // conv
-            p.P = p.F_conv + 1; p.nimg = 2; p.lead = p.P; p.xlo = 0;
-            p.img_mul[0] = 2; p.img_add[0] = 0; p.img_mul[1] = 2; p.img_add[1] = -1;
-            for (int kt = 0; kt < 2; ++kt) {
-                p.tap_img[kt * 3 + 0] = 1; p.tap_off[kt * 3 + 0] = kt * p.P;
-                p.tap_img[kt * 3 + 1] = 0; p.tap_off[kt * 3 + 1] = kt * p.P;
-                p.tap_img[kt * 3 + 2] = 1; p.tap_off[kt * 3 + 2] = kt * p.P + 1;
-            }
-        } else if (L.KT == 1 && L.KF == 1) {                                   // inconv 1x1
-            p.P = F_in; p.lead = 0; p.xlo = 0; p.tap_img[0] = 0; p.tap_off[0] = 0;
-        } else if (L.KT == 1 && L.KF == 3 && L.stride == 2 && L.padl == 0) {   // down_sampling
-            p.P = p.F_conv + 1; p.nimg = 2; p.lead = 0; p.xlo = 0;
-            p.img_mul[0] = 2; p.img_add[0] = 0; p.img_mul[1] = 2; p.img_add[1] = 1;
-            p.tap_img[0] = 0; p.tap_off[0] = 0; p.tap_img[1] = 1; p.tap_off[1] = 0; p.tap_img[2] = 0; p.tap_off[2] = 1;
-        } else if (L.KT == 1 && L.KF == 2 && L.stride == 1 && L.padl == 1) {   // up_sampling o inconv
-            p.P = F_in + 1; p.img_add[0] = -1; p.lead = 1; p.xlo = 1;
-            p.tap_img[0] = 0; p.tap_off[0] = 0; p.tap_img[1] = 0; p.tap_off[1] = 1;
-        } else {
-            return false;
-        }
-        for (int i = 0; i < p.ntaps; ++i) maxoff = std::max(maxoff, p.tap_off[i]);
-        p.nphase = (L.CA + L.CB) / TC_KCH;
-        const long long total = (long long)B * (T + p.padrow) * p.P;
-        if (total >= 0x7fffffffLL - 1024) return false;
-        p.total_flat = (int)total;
-        const size_t wstage = (size_t)2 * (TC_KCH / 4) * L.COUT * 16;
-        const size_t fixed = 256 + TC_TBL_INTS * 4 + TC_STAGE_BYTES + TC_WSTAGES * wstage;
-        const size_t limit = 227 * 1024;
-        // tile = mt x 128 positions; prefer two tiles per weight stage and a 3-deep image ring, shrink to fit
-        size_t smem = 0;
-        bool ok = false;
-        for (int mt = TC_MT; mt >= 1 && !ok; --mt)
-            for (int nb = 3; nb >= 2 && !ok; --nb) {
-                if (mt == 1 && nb == 3 && L.COUT == 128) continue;   // MMA-bound units: weight reuse matters more
-                p.mt = mt;
-                p.slots = mt * 128 + maxoff;
-                int plane16 = p.slots;
-                while (plane16 % 8 != 2) ++plane16;
-                p.plane_bytes = plane16 * 16;
-                const size_t abuf = (size_t)p.nimg * 2 * (TC_KCH / 4) * p.plane_bytes;
-                smem = fixed + nb * abuf;
-                if (smem <= limit && p.nimg * p.slots <= TC_TBL_INTS / 2) {
-                    p.nabuf = nb;
-                    ok = true;
-                }
-            }
-        if (!ok) return false;
-        p.ntiles = (int)((total + p.mt * 128 - 1) / (p.mt * 128));
-        const int grid = std::min(p.ntiles, num_sms);
-        if (L.COUT == 32 && L.epi == EPI_LN) launch_tc_t<32, EPI_LN>(p, grid, smem, st);
-        else if (L.COUT == 64 && L.epi == EPI_LN) launch_tc_t<64, EPI_LN>(p, grid, smem, st);
-        else if (L.COUT == 64 && L.epi == EPI_BIAS) launch_tc_t<64, EPI_BIAS>(p, grid, smem, st);
-        else if (L.COUT == 64 && L.epi == EPI_SHUF32) launch_tc_t<64, EPI_SHUF32>(p, grid, smem, st);
-        else if (L.COUT == 128 && L.epi == EPI_SHUF64) launch_tc_t<128, EPI_SHUF64>(p, grid, smem, st);
-        else return false;
-        return true;
     }
 
     // cuTensorMapEncodeTiled through the runtime's driver entry-point lookup (no link-time dependency on libcuda)
@@ -1063,10 +954,6 @@ struct Engine {
 
     void launch_conv(const ConvLayer& L, const float* a_cur, const float* a_prev, const float* b_cur,
                      const float* b_prev, float* out, int B, int T, bool has_prev, int F_in, cudaStream_t st) {
-        if (use_tc && !has_prev) {
-            const int F_conv = (L.stride == 2) ? F_in / 2 : F_in;
-            if (F_conv >= tc_min_bins && launch_conv_tc(L, a_cur, b_cur, out, B, T, F_in, st)) return;
-        }
         ConvParams p;
         p.a_cur = a_cur; p.a_prev = a_prev; p.b_cur = b_cur; p.b_prev = b_prev;
         p.w = pool.at(L.w); p.bias = pool.at(L.bias);
@@ -1376,7 +1263,7 @@ struct Engine {
 
     void build_plan(Plan& P) {
         Plan* pp = &P;
-        const bool recycle = !P.streaming && !getenv("NUNET_NO_RECYCLE");
+        const bool recycle = !P.streaming && !no_recycle;
         Ten* x0 = P.make("input_layer", 256, 64, false);
         x0->sh = P.sh16;
         P.ops.push_back([=](Engine& E, const Run& r) {
@@ -1413,11 +1300,11 @@ struct Engine {
             Ten* en_in = op_conv(P, blk + "_in", y, enc_out[j], blk + "_in", false, /*out_eo=*/true);
             // the last block's gate + residual also applies out_conv (sh16 plans; kept apart when every tensor is retained
             // for tools/layer_report.py)
-            const bool fuse = (i == 5) && P.sh16 && !getenv("NUNET_NO_RECYCLE");
+            const bool fuse = (i == 5) && P.sh16 && !no_recycle;
             y = op_msfe(P, blk, DEC_N[i], en_in, enc_des[j], nullptr, false, true, /*out_eo=*/false, fuse);
             if (recycle) P.release(m);
         }
-        if (!(P.sh16 && !getenv("NUNET_NO_RECYCLE")))
+        if (!(P.sh16 && !no_recycle))
         P.ops.push_back([=](Engine& E, const Run& r) {
             E.cur_op = "out_conv";
             const long long npix = (long long)r.B * r.T * 256;
@@ -1435,7 +1322,7 @@ struct Engine {
 
     void alloc_plan(Plan& P, int cap, bool streaming) {
         P.streaming = streaming;
-        P.sh16 = use_tc && use_tc3 && (!streaming || stream_tc3);
+        P.sh16 = use_tc && (!streaming || stream_tc3);
         P.cap = cap;
         build_plan(P);
         if (streaming) {
@@ -1475,6 +1362,7 @@ struct Engine {
 
     void forward_wav(const float* wav, int B, int n, float* out_wav, float* out_mag, cudaStream_t st) {
         const int T = nunet_num_frames(n);
+        if (B <= 0) fail(NUNET_EINVAL, "bad batch size B=%d", B);
         if (T <= 0) fail(NUNET_EINVAL, "clip shorter than one 512-sample frame");
         if (!offline.arena) fail(NUNET_EINVAL, "offline path disabled (max_frames = 0)");
         if ((long long)B * T > offline.cap) fail(NUNET_ENOMEM, "B*T = %lld exceeds max_frames = %d", (long long)B * T, offline.cap);
@@ -1521,6 +1409,7 @@ struct Engine {
     void stream_advance() {
         stream_parity ^= 1;
         ++stream_steps;
+        ++state_gen;
     }
 
     // ---- CUDA graphs for the streaming step.  One step is ~200 small kernels whose arguments depend only on the step parity
@@ -1671,6 +1560,7 @@ struct Engine {
     void stream_reset(int first, int count, cudaStream_t st) {
         if (!stream.arena) fail(NUNET_EINVAL, "streaming path disabled (max_streams = 0)");
         if (first < 0 || count < 0 || first + count > stream.cap) fail(NUNET_EINVAL, "stream range out of bounds");
+        ++state_gen;
         order_begin(st);
         if (first == 0 && count == stream.cap) {
             CUDA_OK(cudaMemsetAsync(stream.arena, 0, stream.unit_floats * (size_t)stream.cap * sizeof(float), st));
@@ -1717,6 +1607,7 @@ struct Engine {
     void state_xfer(int sid, const std::string& name, float* buf, bool to_host) {
         if (!stream.arena) fail(NUNET_EINVAL, "streaming path disabled (max_streams = 0)");
         if (sid < 0 || sid >= stream.cap) fail(NUNET_EINVAL, "stream id out of range");
+        if (!to_host) ++state_gen;
         const Ten* xt = nullptr;
         int xring = 0;
         const int xn = extra_state(name, &xt, &xring);
@@ -1797,6 +1688,19 @@ struct nunet_engine {
     Engine e;
 };
 
+// Every handle-taking entry point runs with the engine's device current and restores the caller's device on exit, so
+// engines on different GPUs can be used alternately from any host thread.
+struct DeviceGuard {
+    int prev = -1, dev = -1;
+    explicit DeviceGuard(int d) : dev(d) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+    }
+};
+
 template <typename Fn>
 static int guarded(Fn&& fn) {
     try {
@@ -1810,6 +1714,16 @@ static int guarded(Fn&& fn) {
         g_err = e.what();
         return NUNET_EINVAL;
     }
+}
+// guarded() for entry points that take a handle: null check + device guard
+template <typename Fn>
+static int guarded_h(nunet_engine* h, Fn&& fn) {
+    if (!h) {
+        g_err = "null engine handle";
+        return NUNET_EINVAL;
+    }
+    DeviceGuard dg(h->e.cfg.device);
+    return guarded(fn);
 }
 
 extern "C" {
@@ -1840,7 +1754,7 @@ int nunet_create(const nunet_config* cfg, const void* blob, size_t blob_bytes, n
         int ndev = 0;
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) fail(NUNET_ENODEV, "no CUDA device");
         if (cfg->device < 0 || cfg->device >= ndev) fail(NUNET_ENODEV, "device %d not present (%d devices)", cfg->device, ndev);
-        CUDA_OK(cudaSetDevice(cfg->device));
+        DeviceGuard dg(cfg->device);     // the caller's current device is restored on return
         cudaDeviceProp prop;
         CUDA_OK(cudaGetDeviceProperties(&prop, cfg->device));
         if (prop.major != 10) fail(NUNET_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
@@ -1850,30 +1764,33 @@ int nunet_create(const nunet_config* cfg, const void* blob, size_t blob_bytes, n
         Engine& E = h->e;
         E.cfg = *cfg;
         E.num_sms = prop.multiProcessorCount;
-        if (const char* c = getenv("NUNET_CONV")) {
+        // Experiment switches (ablations for tools/ and the graph-vs-plain-launch tests).  They are ignored unless
+        // NUNET_DEBUG_KNOBS=1 is set, so a stray environment variable cannot change kernels or numerics in production.
+        const bool knobs = getenv("NUNET_DEBUG_KNOBS") && atoi(getenv("NUNET_DEBUG_KNOBS")) != 0;
+        auto knob = [&](const char* name) -> const char* { return knobs ? getenv(name) : nullptr; };
+        E.no_recycle = knob("NUNET_NO_RECYCLE") != nullptr;
+        if (const char* c = knob("NUNET_CONV")) {
             E.use_tc = strcmp(c, "simt") != 0;
-            E.use_tc3 = strcmp(c, "tc") != 0;
         }
-        if (const char* c = getenv("NUNET_TC_MIN_BINS")) E.tc_min_bins = atoi(c);
-        if (const char* c = getenv("NUNET_TC3_FENCE")) E.tc3_fence_mode = atoi(c);
-        if (const char* c = getenv("NUNET_TC3_DBG")) E.tc3_dbg = atoi(c);
-        if (getenv("NUNET_TC3_TIMING")) {
+        if (const char* c = knob("NUNET_TC3_FENCE")) E.tc3_fence_mode = atoi(c);
+        if (const char* c = knob("NUNET_TC3_DBG")) E.tc3_dbg = atoi(c);
+        if (knob("NUNET_TC3_TIMING")) {
             CUDA_OK(cudaMalloc(&E.tc3_timing_buf, 16 * sizeof(unsigned long long)));
             CUDA_OK(cudaMemset(E.tc3_timing_buf, 0, 16 * sizeof(unsigned long long)));
         }
-        if (const char* c = getenv("NUNET_TC3_TMA")) E.tc3_tma = atoi(c);
-        if (const char* c = getenv("NUNET_TC3_CLUSTER")) E.tc3_cluster = atoi(c);
-        if (const char* c = getenv("NUNET_TC3_BOX_MINF")) E.tc3_box_minf = atoi(c);
-        if (const char* c = getenv("NUNET_TC3_PAIR")) E.tc3_pair = atoi(c);
-        if (const char* c = getenv("NUNET_TC3_ROW_TILES")) E.tc3_row_tiles = atoi(c);
-        if (const char* c = getenv("NUNET_STREAM_GRAPH")) E.stream_graphs = atoi(c);
-        if (const char* c = getenv("NUNET_STREAM_SPLIT")) E.stream_split = std::max(1, std::min(4, atoi(c)));
-        if (const char* c = getenv("NUNET_TC3_PAIR_MINF")) E.tc3_pair_minf = atoi(c);
-        if (const char* c = getenv("NUNET_TC3_BOX_STRIDED")) E.tc3_box_strided = atoi(c);
-        if (const char* c = getenv("NUNET_TC3_TMA_MINF")) E.tc3_tma_minf = std::max(8, atoi(c));
-        if (const char* c = getenv("NUNET_TC3_MT")) E.tc3_force_mt = atoi(c);
-        if (const char* c = getenv("NUNET_STREAM_CONV")) E.stream_tc3 = strcmp(c, "simt") != 0;
-        if (const char* c = getenv("NUNET_TC3_PDL")) E.tc3_pdl = atoi(c) != 0;
+        if (const char* c = knob("NUNET_TC3_TMA")) E.tc3_tma = atoi(c);
+        if (const char* c = knob("NUNET_TC3_CLUSTER")) E.tc3_cluster = atoi(c);
+        if (const char* c = knob("NUNET_TC3_BOX_MINF")) E.tc3_box_minf = atoi(c);
+        if (const char* c = knob("NUNET_TC3_PAIR")) E.tc3_pair = atoi(c);
+        if (const char* c = knob("NUNET_TC3_ROW_TILES")) E.tc3_row_tiles = atoi(c);
+        if (const char* c = knob("NUNET_STREAM_GRAPH")) E.stream_graphs = atoi(c);
+        if (const char* c = knob("NUNET_STREAM_SPLIT")) E.stream_split = std::max(1, std::min(4, atoi(c)));
+        if (const char* c = knob("NUNET_TC3_PAIR_MINF")) E.tc3_pair_minf = atoi(c);
+        if (const char* c = knob("NUNET_TC3_BOX_STRIDED")) E.tc3_box_strided = atoi(c);
+        if (const char* c = knob("NUNET_TC3_TMA_MINF")) E.tc3_tma_minf = std::max(8, atoi(c));
+        if (const char* c = knob("NUNET_TC3_MT")) E.tc3_force_mt = atoi(c);
+        if (const char* c = knob("NUNET_STREAM_CONV")) E.stream_tc3 = strcmp(c, "simt") != 0;
+        if (const char* c = knob("NUNET_TC3_PDL")) E.tc3_pdl = atoi(c) != 0;
         E.blob.parse(blob, blob_bytes);
         E.pack_params();
         E.pool.upload();
@@ -1884,7 +1801,7 @@ int nunet_create(const nunet_config* cfg, const void* blob, size_t blob_bytes, n
         // staging for the host entry points
         size_t in_f = 0, out_f = 0;
         if (cfg->max_frames > 0) {
-            in_f = (size_t)cfg->max_frames * 2 * HOP + NFFT;
+            in_f = (size_t)cfg->max_frames * 3 * HOP;      // a clip of T frames has < (T + 2) * HOP <= 3 T HOP samples
             out_f = in_f;
         }
         if (cfg->max_streams > 0) {
@@ -1903,24 +1820,25 @@ int nunet_create(const nunet_config* cfg, const void* blob, size_t blob_bytes, n
 
 void nunet_destroy(nunet_engine* h) {
     if (!h) return;
-    cudaSetDevice(h->e.cfg.device);
+    DeviceGuard dg(h->e.cfg.device);
     cudaDeviceSynchronize();
     delete h;
 }
 
 int nunet_forward_wav_dev(nunet_engine* h, const float* wav, int B, int n_samples, float* out_wav, float* out_mag,
                           void* stream) {
-    return guarded([&] {
+    return guarded_h(h, [&] {
         if (!h || !wav) fail(NUNET_EINVAL, "null argument");
         h->e.forward_wav(wav, B, n_samples, out_wav, out_mag, static_cast<cudaStream_t>(stream));
     });
 }
 
 int nunet_forward_wav_host(nunet_engine* h, const float* wav, int B, int n_samples, float* out_wav, float* out_mag) {
-    return guarded([&] {
+    return guarded_h(h, [&] {
         if (!h || !wav) fail(NUNET_EINVAL, "null argument");
         Engine& E = h->e;
         const int T = nunet_num_frames(n_samples);
+        if (B <= 0) fail(NUNET_EINVAL, "bad batch size B=%d", B);
         if (T <= 0) fail(NUNET_EINVAL, "clip shorter than one 512-sample frame");
         const size_t n_in = (size_t)B * n_samples, n_out = (size_t)B * ((size_t)(T - 1) * HOP + NFFT);
         if (n_in > E.h_in_cap || n_out > E.h_out_cap) fail(NUNET_ENOMEM, "host-call staging capacity exceeded");
@@ -1939,7 +1857,7 @@ int nunet_forward_wav_host(nunet_engine* h, const float* wav, int B, int n_sampl
 }
 
 int nunet_forward_mag_dev(nunet_engine* h, const float* mag, int B, int T, float* out_mag, void* stream) {
-    return guarded([&] {
+    return guarded_h(h, [&] {
         if (!h || !mag || !out_mag) fail(NUNET_EINVAL, "null argument");
         h->e.launches = 0;
         h->e.order_begin(static_cast<cudaStream_t>(stream));
@@ -1950,14 +1868,14 @@ int nunet_forward_mag_dev(nunet_engine* h, const float* mag, int B, int T, float
 }
 
 int nunet_stream_reset(nunet_engine* h, int first, int count, void* stream) {
-    return guarded([&] {
+    return guarded_h(h, [&] {
         if (!h) fail(NUNET_EINVAL, "null argument");
         h->e.stream_reset(first, count, static_cast<cudaStream_t>(stream));
     });
 }
 
 int nunet_stream_step_mag_dev(nunet_engine* h, const float* mag, int S, float* out_mag, void* stream) {
-    return guarded([&] {
+    return guarded_h(h, [&] {
         if (!h || !mag || !out_mag) fail(NUNET_EINVAL, "null argument");
         h->e.launches = 0;
         h->e.order_begin(static_cast<cudaStream_t>(stream));
@@ -1968,14 +1886,14 @@ int nunet_stream_step_mag_dev(nunet_engine* h, const float* mag, int S, float* o
 }
 
 int nunet_stream_step_wav_dev(nunet_engine* h, const float* hop, int S, float* out_hop, float* out_mag, void* stream) {
-    return guarded([&] {
+    return guarded_h(h, [&] {
         if (!h || !hop || !out_hop) fail(NUNET_EINVAL, "null argument");
         h->e.stream_step_wav(hop, S, out_hop, out_mag, static_cast<cudaStream_t>(stream));
     });
 }
 
 int nunet_stream_step_wav_host(nunet_engine* h, const float* hop, int S, float* out_hop) {
-    return guarded([&] {
+    return guarded_h(h, [&] {
         if (!h || !hop || !out_hop) fail(NUNET_EINVAL, "null argument");
         Engine& E = h->e;
         E.check_streams(S);
@@ -1992,7 +1910,7 @@ int nunet_stream_step_wav_host(nunet_engine* h, const float* hop, int S, float* 
 int nunet_state_count(nunet_engine* h) { return h ? (int)h->e.stream.states.size() : NUNET_EINVAL; }
 
 int nunet_state_name(nunet_engine* h, int index, char* name_out, int cap) {
-    return guarded([&] {
+    return guarded_h(h, [&] {
         if (!h || !name_out || cap <= 0) fail(NUNET_EINVAL, "null argument");
         if (index < 0 || index >= (int)h->e.stream.states.size()) fail(NUNET_EINVAL, "state index out of range");
         snprintf(name_out, (size_t)cap, "%s", h->e.stream.states[index].name.c_str());
@@ -2001,7 +1919,7 @@ int nunet_state_name(nunet_engine* h, int index, char* name_out, int cap) {
 
 int nunet_state_numel(nunet_engine* h, const char* name) {
     int n = 0;
-    int rc = guarded([&] {
+    int rc = guarded_h(h, [&] {
         if (!h || !name) fail(NUNET_EINVAL, "null argument");
         const Ten* xt = nullptr;
         int xring = 0;
@@ -2015,18 +1933,20 @@ int nunet_state_numel(nunet_engine* h, const char* name) {
 }
 
 int nunet_state_export(nunet_engine* h, int stream_id, const char* name, float* buf) {
-    return guarded([&] {
+    return guarded_h(h, [&] {
         if (!h || !name || !buf) fail(NUNET_EINVAL, "null argument");
         h->e.state_xfer(stream_id, name, buf, true);
     });
 }
 
 int nunet_state_import(nunet_engine* h, int stream_id, const char* name, const float* buf) {
-    return guarded([&] {
+    return guarded_h(h, [&] {
         if (!h || !name || !buf) fail(NUNET_EINVAL, "null argument");
         h->e.state_xfer(stream_id, name, const_cast<float*>(buf), false);
     });
 }
+
+long long nunet_state_generation(nunet_engine* h) { return h ? h->e.state_gen : (long long)NUNET_EINVAL; }
 
 int nunet_last_launch_count(nunet_engine* h) { return h ? h->e.launches : NUNET_EINVAL; }
 
@@ -2039,7 +1959,7 @@ int nunet_profile_enable(nunet_engine* h, int on) {
 int nunet_profile_count(nunet_engine* h) { return h ? (int)h->e.prof.size() : NUNET_EINVAL; }
 
 int nunet_profile_entry(nunet_engine* h, int index, char* name_out, int cap, float* ms_out, double* alg_bytes_out) {
-    return guarded([&] {
+    return guarded_h(h, [&] {
         if (!h || !name_out || !ms_out || !alg_bytes_out) fail(NUNET_EINVAL, "null argument");
         Engine& E = h->e;
         if (index < 0 || index >= (int)E.prof.size()) fail(NUNET_EINVAL, "profile index out of range");
@@ -2054,7 +1974,7 @@ int nunet_profile_entry(nunet_engine* h, int index, char* name_out, int cap, flo
 
 long long nunet_debug_read(nunet_engine* h, const char* tensor_name, float* buf, long long cap) {
     long long n = 0;
-    int rc = guarded([&] {
+    int rc = guarded_h(h, [&] {
         if (!h || !tensor_name) fail(NUNET_EINVAL, "null argument");
         Engine& E = h->e;
         auto it = E.offline.named.find(tensor_name);

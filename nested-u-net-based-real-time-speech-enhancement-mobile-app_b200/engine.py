@@ -22,13 +22,27 @@ def num_frames(n_samples: int) -> int:
 
 
 def _host_ptr(a) -> Tuple[int, object]:
-    """Pointer of a C-contiguous float32 host buffer (numpy array or CPU torch tensor)."""
+    """Pointer of a C-contiguous float32 host INPUT buffer (numpy array or CPU torch tensor; converted if needed)."""
     if isinstance(a, torch.Tensor):
         if a.is_cuda or a.dtype != torch.float32 or not a.is_contiguous():
             raise ValueError("host buffer must be a contiguous float32 CPU tensor")
         return a.data_ptr(), a
     a = np.ascontiguousarray(a, dtype=np.float32)
     return a.ctypes.data, a
+
+
+def _host_out(a, shape, what: str) -> int:
+    """Pointer of a caller-supplied host OUTPUT buffer: it is written through a raw pointer, so it must already be
+    float32, C-contiguous, writable and hold exactly `shape` elements (no silent copy, no short buffer)."""
+    n = int(np.prod(shape))
+    if isinstance(a, torch.Tensor):
+        if a.is_cuda or a.dtype != torch.float32 or not a.is_contiguous() or a.numel() != n:
+            raise ValueError(f"{what}: expected a contiguous float32 CPU tensor of {n} elements {tuple(shape)}")
+        return a.data_ptr()
+    if not (isinstance(a, np.ndarray) and a.dtype == np.float32 and a.flags.c_contiguous and a.flags.writeable
+            and a.size == n):
+        raise ValueError(f"{what}: expected a writable C-contiguous float32 array of {n} elements {tuple(shape)}")
+    return a.ctypes.data
 
 
 class NunetEngine:
@@ -63,10 +77,18 @@ class NunetEngine:
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def _dev(self, t: torch.Tensor) -> torch.Tensor:
-        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.device == self.device):
-            raise ValueError(f"expected a contiguous float32 tensor on {self.device}")
+    def _dev(self, t: torch.Tensor, shape=None, what: str = "tensor") -> torch.Tensor:
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+                and t.device == self.device):
+            raise ValueError(f"{what}: expected a contiguous float32 tensor on {self.device}")
+        if shape is not None and tuple(t.shape) != tuple(shape):
+            raise ValueError(f"{what}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
         return t
+
+    @property
+    def state_generation(self) -> int:
+        """Changes whenever the history resident in the engine changes (step, reset, import)."""
+        return check(self._L.nunet_state_generation(self._h))
 
     @property
     def last_launch_count(self) -> int:
@@ -88,9 +110,13 @@ class NunetEngine:
     # ------------------------------------------------------------------ offline
     def forward_wav(self, wav: torch.Tensor, want_wav: bool = True, want_mag: bool = True):
         """wav [B,N] (cuda) -> (enhanced wav [B,(T-1)*256+512] | None, est magnitudes [B,T,257] | None)."""
-        wav = self._dev(wav)
+        wav = self._dev(wav, what="wav")
+        if wav.dim() != 2:
+            raise ValueError("wav must be [B, N]")
         B, N = wav.shape
         T = num_frames(N)
+        if B < 1 or T < 1:
+            raise _lib.NunetError(-1, "clip shorter than one 512-sample frame" if B >= 1 else "empty batch")
         out_wav = torch.empty((B, (T - 1) * 256 + 512), device=self.device, dtype=torch.float32) if want_wav else None
         out_mag = torch.empty((B, T, 257), device=self.device, dtype=torch.float32) if want_mag else None
         check(self._L.nunet_forward_wav_dev(self._h, wav.data_ptr(), B, N,
@@ -100,17 +126,25 @@ class NunetEngine:
 
     def forward_wav_into(self, wav: torch.Tensor, out_wav: Optional[torch.Tensor], out_mag: Optional[torch.Tensor] = None):
         """Allocation-free variant for benchmarks."""
+        wav = self._dev(wav, what="wav")
+        if wav.dim() != 2:
+            raise ValueError("wav must be [B, N]")
         B, N = wav.shape
+        T = num_frames(N)
+        if out_wav is not None:
+            self._dev(out_wav, (B, (T - 1) * 256 + 512), "out_wav")
+        if out_mag is not None:
+            self._dev(out_mag, (B, T, 257), "out_mag")
         check(self._L.nunet_forward_wav_dev(self._h, wav.data_ptr(), B, N,
                                             out_wav.data_ptr() if out_wav is not None else None,
                                             out_mag.data_ptr() if out_mag is not None else None, self._stream()))
 
     def forward_mag(self, mag: torch.Tensor) -> torch.Tensor:
         """mag [B,T,256] (DC dropped) -> estimated magnitudes [B,T,256]."""
-        mag = self._dev(mag)
+        mag = self._dev(mag, what="mag")
+        if mag.dim() != 3 or mag.shape[2] != 256:
+            raise ValueError("magnitudes must be [B, T, 256] (DC dropped)")
         B, T, F = mag.shape
-        if F != 256:
-            raise ValueError("magnitudes must have 256 bins (DC dropped)")
         out = torch.empty_like(mag)
         check(self._L.nunet_forward_mag_dev(self._h, mag.data_ptr(), B, T, out.data_ptr(), self._stream()))
         return out
@@ -118,14 +152,16 @@ class NunetEngine:
     def forward_wav_host(self, wav, out_wav=None, out_mag=None):
         """End-to-end host call: host wav [B,N] -> host buffers (H2D + kernels + D2H inside the call)."""
         p_in, keep = _host_ptr(wav)
+        if keep.ndim != 2:
+            raise ValueError("wav must be [B, N]")
         B, N = keep.shape
         T = num_frames(N)
+        if B < 1 or T < 1:
+            raise _lib.NunetError(-1, "clip shorter than one 512-sample frame" if B >= 1 else "empty batch")
         if out_wav is None:
             out_wav = np.empty((B, (T - 1) * 256 + 512), np.float32)
-        p_out, _k2 = _host_ptr(out_wav)
-        p_mag = None
-        if out_mag is not None:
-            p_mag, _k3 = _host_ptr(out_mag)
+        p_out = _host_out(out_wav, (B, (T - 1) * 256 + 512), "out_wav")
+        p_mag = _host_out(out_mag, (B, T, 257), "out_mag") if out_mag is not None else None
         check(self._L.nunet_forward_wav_host(self._h, p_in, B, N, p_out, p_mag))
         return out_wav, out_mag
 
@@ -141,25 +177,35 @@ class NunetEngine:
                                          self._stream()))
 
     def stream_step_mag(self, mag: torch.Tensor) -> torch.Tensor:
-        mag = self._dev(mag)
+        mag = self._dev(mag, what="mag")
+        if mag.dim() != 2 or mag.shape[1] != 256:
+            raise ValueError(f"mag must be [S, 256], got {tuple(mag.shape)}")
         out = torch.empty_like(mag)
         check(self._L.nunet_stream_step_mag_dev(self._h, mag.data_ptr(), mag.shape[0], out.data_ptr(), self._stream()))
         return out
 
     def stream_step_wav(self, hop: torch.Tensor, out_hop: Optional[torch.Tensor] = None,
                         out_mag: Optional[torch.Tensor] = None) -> torch.Tensor:
-        hop = self._dev(hop)
+        hop = self._dev(hop, what="hop")
+        if hop.dim() != 2 or hop.shape[1] != 256:
+            raise ValueError(f"hop must be [S, 256], got {tuple(hop.shape)}")
         if out_hop is None:
             out_hop = torch.empty_like(hop)
+        else:
+            self._dev(out_hop, hop.shape, "out_hop")
+        if out_mag is not None:
+            self._dev(out_mag, hop.shape, "out_mag")
         check(self._L.nunet_stream_step_wav_dev(self._h, hop.data_ptr(), hop.shape[0], out_hop.data_ptr(),
                                                 out_mag.data_ptr() if out_mag is not None else None, self._stream()))
         return out_hop
 
     def stream_step_wav_host(self, hop, out_hop=None):
         p_in, keep = _host_ptr(hop)
+        if keep.ndim != 2 or keep.shape[1] != 256:
+            raise ValueError(f"hop must be [S, 256], got {tuple(keep.shape)}")
         if out_hop is None:
             out_hop = np.empty(keep.shape, np.float32)
-        p_out, _k = _host_ptr(out_hop)
+        p_out = _host_out(out_hop, keep.shape, "out_hop")
         check(self._L.nunet_stream_step_wav_host(self._h, p_in, keep.shape[0], p_out))
         return out_hop
 

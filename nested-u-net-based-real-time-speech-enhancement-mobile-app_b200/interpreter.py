@@ -7,9 +7,13 @@
 (`dnn_model/interpreter_proposed.py:374-380, 215-350`; tensor names and shapes `converter_proposed.py:26-187`
 inputs, `:729-867` outputs) and the frame loop `real_time_speech_enhancer` (`interpreter_proposed.py:15-370`).
 
-The engine keeps the history resident on the GPU.  When the caller feeds back exactly the arrays the previous
-call returned (what the reference loop does) nothing is imported; any other array is written into the engine
-first, so foreign histories (e.g. from a real TFLite run) can be injected.
+The engine keeps the history resident on the GPU.  The reference runner is stateless: every call gets the whole
+history.  Here a fed-back array is NOT re-imported only when (a) it is the very object the previous call of this runner
+returned, (b) that array is still read-only (returned arrays are frozen, so an in-place edit needs an explicit
+`setflags(write=True)` or a copy -- both are detected) and (c) the engine's history generation counter
+(`nunet_state_generation`: bumped by every step, reset and import, whoever issued it) still has the value recorded
+with that output.  Anything else -- foreign histories (e.g. from a real TFLite run), edited copies, a reset or a step
+through another runner in between -- is written into the engine first.
 """
 from __future__ import annotations
 
@@ -49,6 +53,7 @@ class SignatureRunner:
         self._e = engine
         self._names: List[str] = engine.state_names()
         self._last_out: Dict[str, np.ndarray] = {}
+        self._last_gen = -1
         self._dev_in = torch.empty((1, 256), device=engine.device, dtype=torch.float32)
         for n in self._names:   # the engine's plan and the reference table must agree tensor by tensor
             ref = _engine_to_ref(n, "cur")
@@ -73,20 +78,25 @@ class SignatureRunner:
         missing = expected - set(kw)
         if missing:
             raise ValueError(f"missing signature inputs: {sorted(missing)[:4]}")
+        resident = e.state_generation == self._last_gen     # nobody stepped / reset / imported since our last call
         for n in self._names:
             given = kw[_engine_to_ref(n, "prev")]
-            if given is self._last_out.get(_engine_to_ref(n, "cur")):
+            mine = self._last_out.get(_engine_to_ref(n, "cur"))
+            if resident and given is mine and not mine.flags.writeable:
                 continue                      # history already resident
-            e.state_import(0, n, given)
+            e.state_import(0, n, given)       # (bumps the generation; the other tensors stay what the engine holds)
         x = np.ascontiguousarray(kw["input"], dtype=np.float32).reshape(1, 256)
         self._dev_in.copy_(torch.from_numpy(x))
         y = e.stream_step_mag(self._dev_in)
         out: Dict[str, np.ndarray] = {}
         for n in self._names:
             ref = _engine_to_ref(n, "cur")
-            out[ref] = e.state_export(0, n).reshape(self._shapes[ref])
+            a = e.state_export(0, n).reshape(self._shapes[ref])
+            a.setflags(write=False)           # an in-place edit of a returned array must not go unnoticed
+            out[ref] = a
         out["model_out"] = y.cpu().numpy().reshape(1, 1, 256, 1)
         self._last_out = out
+        self._last_gen = e.state_generation
         return out
 
 
@@ -113,6 +123,7 @@ class Interpreter:
         self._blob = pack_blob(weights, VARIANT_DDB if self._ddb else 0)
         self._device = device
         self._engine: Optional[NunetEngine] = None
+        self._cached_runner: Optional[SignatureRunner] = None
         self._keys = SIGNATURE_KEYS_DDB if self._ddb else SIGNATURE_KEYS
 
     def allocate_tensors(self):
@@ -122,7 +133,9 @@ class Interpreter:
             self._engine.stream_reset()
 
     def _runner(self) -> SignatureRunner:
-        return SignatureRunner(self._engine, STATE_SHAPES_DDB if self._ddb else STATE_SHAPES)
+        if self._cached_runner is None:      # one runner per interpreter: they all drive stream 0 of the one engine
+            self._cached_runner = SignatureRunner(self._engine, STATE_SHAPES_DDB if self._ddb else STATE_SHAPES)
+        return self._cached_runner
 
     def get_signature_list(self) -> dict:
         self.allocate_tensors()

@@ -1,7 +1,7 @@
 """Names and shapes of the streaming history tensors of NUNet-TLS-LSTM, derived from the topology.
 
 Reference tables: `dnn_model/interpreter_proposed.py:36-198` (zero dict, `*_curK` + LSTM states) and the
-TensorSpecs of `converter_proposed.py:26-187`.  tests/test_state_table.py checks this derivation against a
+TensorSpecs of `converter_proposed.py:26-187`.  tests/test_oracle_pins.py checks this derivation against a
 fixture extracted from those files (tests/golden/state_shapes_lstm.json).
 """
 from __future__ import annotations

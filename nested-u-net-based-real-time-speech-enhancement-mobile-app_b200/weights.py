@@ -365,8 +365,10 @@ def unpack_blob(blob: bytes):
 
 # ---------------------------------------------------------------------------------------------------
 # Default weight artefact.  The reference checkout (and therefore the .h5) does not exist on the GPU box, so
-# `__graft_entry__.build()` converts it once into nunet_b200/data/nutls_lstm.nunetw (git-ignored, travels with
-# the gpurun snapshot).  Nothing here fabricates weights silently: random weights must be asked for by name.
+# `__graft_entry__.build()` converts it once into nunet_b200/data/nutls_lstm.nunetw.  The three blobs under data/ are
+# COMMITTED: they are data extracted from the reference's own .h5 / .tflite by the code above, and the product needs
+# them at run time on boxes without the reference checkout.  Nothing here fabricates weights silently: random weights
+# must be asked for by name.
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))

@@ -436,6 +436,7 @@ def test_streaming_graph_with_parallel_chains_equals_plain_launches(blob, ddb_we
     wav *= np.linspace(0.5, 1.0, S, dtype=np.float32)[:, None]          # every stream different
     outs = {}
     for mode in ("0", "1"):
+        monkeypatch.setenv("NUNET_DEBUG_KNOBS", "1")
         monkeypatch.setenv("NUNET_STREAM_GRAPH", mode)
         monkeypatch.setenv("NUNET_STREAM_SPLIT", "2")      # two chains of 80 streams inside the captured step
         eng = NunetEngine(b, max_streams=S, variant=v)

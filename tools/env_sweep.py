@@ -16,6 +16,6 @@ for spec in sys.argv[1:]:
         step_ms = json.loads(r.stdout.strip().splitlines()[-1])["ms_per_step"]
     except Exception:
         step_ms = float("nan")
-    d = json.load(open(os.path.join(ROOT, "gpurun_out", "bench_kernel_profile.json")))
+    d = json.load(open(os.path.join(ROOT, "gpurun_out", "bench_kernel_profile_lstm.json")))
     t = {n.split(":")[0]: ms for n, ms, b in d["entries"]}
     print(f"step {step_ms:7.2f} ms | {d['total_ms']:8.2f}  " + " ".join(f"{t.get(n, 0.0):12.3f}" for n in names) + "   " + spec, flush=True)

@@ -3,6 +3,7 @@ with the CPU oracle's taps.  Writes gpurun_out/layer_report.txt.   usage: python
 import os
 import sys
 
+os.environ["NUNET_DEBUG_KNOBS"] = "1"
 os.environ["NUNET_NO_RECYCLE"] = "1"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

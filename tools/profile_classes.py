@@ -1,4 +1,4 @@
-"""Aggregate bench_kernel_profile.json (per-launch CUDA-event times from bench.py) by unit class."""
+"""Aggregate bench_kernel_profile_lstm.json (per-launch CUDA-event times from bench.py) by unit class."""
 import collections
 import json
 import re
