@@ -66,7 +66,13 @@ constexpr int T3_MAXTAPS = 6;
 constexpr int T3_EPI_WARPS = 8;
 constexpr int T3_LD_WARPS = 4;
 constexpr int T3_LD_THREADS = 32 * T3_LD_WARPS;
-constexpr int T3_THREADS = 32 * (T3_EPI_WARPS + T3_LD_WARPS + 1);
+// 16 warps = 4 per SM sub-partition: {epilogue, epilogue, loader, MMA issuer | idle}.  The block is launched with 128 registers
+// per thread (the whole register file); right after the prologue every role resizes its allocation with setmaxnreg so that
+// the epilogue threads -- one output row each, N accumulator values + N + 32 raw tcgen05.ld words live at the peak -- get
+// 192 registers and never spill:  2 x 192 + 80 (loader) + 48 (MMA issuer; the three idle warps keep 24) = 512 = 16 K / 32.
+constexpr int T3_WARPS = 16;
+constexpr int T3_THREADS = 32 * T3_WARPS;
+constexpr int T3_REGS_EPI = 192, T3_REGS_LD = 80, T3_REGS_MMA = 48, T3_REGS_IDLE = 24;
 constexpr int T3_MAXNB = 8;         // image ring depth
 constexpr int T3_TBL = 1024;        // slot table entries (nimg*slots <= 1024)
 constexpr int T3_PREV_FLAG = 1 << 30;   // slot-table entry: read the history tensor (streaming) instead of the source
@@ -458,7 +464,6 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
     tc_fence_after();
     if (p.cluster || PAIR) cluster_sync_all();     // the partner's barriers exist before anything is multicast to them
     const uint32_t tmem_base = *tmem_ptr_s;
-
     const int Tp = p.T + p.padrow;
     const int cta = (int)blockIdx.x / p.nhalf, ncta = (int)gridDim.x / p.nhalf;
     const int my_tiles = (cta < p.ntiles) ? (p.ntiles - cta + ncta - 1) / ncta : 0;
@@ -478,7 +483,10 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
         return rw * p.P + p.xlo + (unit - rw * p.row_tpr) * 128;
     };
 
+    // Register re-partitioning: every role resizes its allocation as the first thing in its branch (warpgroups 0-1 epilogue,
+    // 2 loaders, 3 = MMA issuer + three idle warps); the shrinking roles release what the epilogue's increase waits for.
     if (warp < T3_EPI_WARPS) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(T3_REGS_EPI));
         // ================================================================= epilogue
         // Accumulator (it, mt) is drained by warp group ((it * p.mt + mt) & 1): with two tiles per iteration each
         // group owns one of them, with one tile per iteration the groups alternate iterations.
@@ -592,6 +600,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
             p.timing[6] = (unsigned long long)(clock64() - t_begin);
         }
     } else if (warp < MMA_WARP) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T3_REGS_LD));
         // ================================================================= loaders
         // Loader warp w owns plane w = (part hi|lo, chunk) of every buffer; its lanes walk the table entries
         // e = lane + 32 k, so one cp.async instruction moves 32 consecutive 16-byte slots.  A table entry is the
@@ -782,7 +791,8 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
             p.timing[10] = (unsigned long long)tl_fence;
             p.timing[11] = (unsigned long long)tl_issue;
         }
-    } else {
+    } else if (warp == MMA_WARP) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T3_REGS_MMA));
         // ================================================================= MMA issuer (+ one-off weight load)
         // The whole warp stays converged (waits are warp-wide); one elected lane issues, so the tcgen05
         // instructions see warp-uniform operands and need no per-lane serialisation loop.
@@ -924,6 +934,10 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
             p.timing[2] = (unsigned long long)tm_acc;
             p.timing[3] = (unsigned long long)my_tiles;
         }
+    }
+
+    else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T3_REGS_IDLE));
     }
 
     // ------------------------------------------------------------------ teardown

@@ -30,7 +30,7 @@ def _excerpt(n=512 + 256 * 47):
     import os
     here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     d = np.load(os.path.join(here, GOLDEN_WAV))
-    return (d["noisy"][:n].astype(np.float32) / 32768.0)[None]          # what sf.read returns: peak ~0.089
+    return (d["noisy"][:n].astype(np.float32) / 32768.0)[None]          # what sf.read returns (raw PCM scale)
 
 
 def _bar(peak: float) -> float:
@@ -60,9 +60,9 @@ def _check_offline(blob, oracle, wav, mode="causal_avg32"):
 
 @pytest.mark.parametrize("mode", ["causal_avg32", "frame_div32"])
 def test_raw_level_excerpt(blob, oracles, mode):
-    """The reference's own wav at the level its interpreter script feeds it: raw PCM / 32768, peak 0.089."""
+    """The reference's own wav at the level its interpreter script feeds it: raw PCM / 32768, peak 0.023 in this excerpt (0.089 over the whole file)."""
     wav = _excerpt()
-    assert 0.05 < np.abs(wav).max() < 0.2
+    assert 0.01 < np.abs(wav).max() < 0.2
     _check_offline(blob, oracles[mode], wav, mode)
 
 
