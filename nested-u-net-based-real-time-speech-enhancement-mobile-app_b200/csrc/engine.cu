@@ -31,6 +31,7 @@
 #include "framing.cuh"
 #include "misc_kernels.cuh"
 #include "sh16_kernels.cuh"
+#include "lstm_kernels.cuh"
 #include "ddb_kernels.cuh"
 
 namespace nunet {
@@ -147,7 +148,7 @@ struct MlpLayer {
     size_t k0, b0, k1, b1;
 };
 struct LstmLayer {
-    size_t wk, wr, wb, dk, db;
+    size_t wk, wk4, wr, wb, dk, db;
     int D;
 };
 struct DdbLayer {   // one dilated dense block: float offsets into the pool
@@ -513,6 +514,13 @@ struct Engine {
         LstmLayer l;
         l.D = D;
         l.wk = add_arr(lstm + "/kernel", {D, LSTM_GATES});
+        {   // [D/4][84][4]: four consecutive k of one gate in one 16-byte word (lstm_kernels.cuh)
+            const Arr& k = blob.get(lstm + "/kernel", {D, LSTM_GATES});
+            std::vector<float> k4((size_t)D * LSTM_GATES);
+            for (int kk = 0; kk < D; ++kk)
+                for (int g = 0; g < LSTM_GATES; ++g) k4[((size_t)(kk >> 2) * LSTM_GATES + g) * 4 + (kk & 3)] = k.data[(size_t)kk * LSTM_GATES + g];
+            l.wk4 = pool.add(k4);
+        }
         l.wr = add_arr(lstm + "/recurrent_kernel", {LSTM_UNITS, LSTM_GATES});
         l.wb = add_arr(lstm + "/bias", {LSTM_GATES});
         l.dk = add_arr(dense + "/kernel", {LSTM_UNITS, D});
@@ -1029,8 +1037,6 @@ struct Engine {
         const LstmLayer& L = lstms.at(lstm);
         const int D = x->F * x->C;
         if (D != L.D) fail(NUNET_EINVAL, "plan: %s width", lstm.c_str());
-        Ten* xw = P.make("", 1, LSTM_GATES, false, false);
-        Ten* hs = P.make("", 1, LSTM_UNITS, false, false);
         Ten *hst = nullptr, *cst = nullptr;
         if (P.streaming) {
             hst = P.make("", 1, LSTM_UNITS, true, false);
@@ -1047,27 +1053,18 @@ struct Engine {
         P.ops.push_back([=](Engine& E, const Run& r) {
             E.cur_op = out_name;
             const long long rows = (long long)r.B * r.T;
-            const int blocks = (int)((rows + DENSE_RB - 1) / DENSE_RB);
-            float* xwp = pp->cur(xw, 0);
-            float* hsp = pp->cur(hs, 0);
             const int xC = x->C;
+            const size_t smem = (size_t)LSTM_TB * 2 * (D + LSTM_GATES + 24) * sizeof(float);
+            float* hp = hst ? pp->cur(hst, 0) : nullptr;
+            float* cp = cst ? pp->cur(cst, 0) : nullptr;
+            // one CTA per clip / stream: projection, recurrence and Dense in one kernel (lstm_kernels.cuh)
             if (pp->sh16)
-                dense_rows_sh_kernel<true, false><<<blocks, 128, DENSE_RB * D * sizeof(float), r.st>>>(
-                    pp->cur(x, r.parity), E.pool.at(L.wk), E.pool.at(L.wb), xwp, rows, D, LSTM_GATES, xC);
+                lstm_block_kernel<true><<<r.B, LSTM_THREADS, smem, r.st>>>(pp->cur(x, r.parity), E.pool.at(L.wk4), E.pool.at(L.wr), E.pool.at(L.wb),
+                                                                  E.pool.at(L.dk), E.pool.at(L.db), hp, cp, 0, pp->cur(o, r.parity), r.T, D, xC);
             else
-                dense_rows_kernel<<<blocks, 128, DENSE_RB * D * sizeof(float), r.st>>>(pp->cur(x, r.parity), E.pool.at(L.wk),
-                                                                                     E.pool.at(L.wb), xwp, rows, D, LSTM_GATES);
-            E.check_launch("lstm_in_proj", rows * 4.0 * (D + LSTM_GATES));
-            lstm_recur_kernel<<<r.B, 96, 0, r.st>>>(xwp, E.pool.at(L.wr), hst ? pp->cur(hst, 0) : nullptr,
-                                                   cst ? pp->cur(cst, 0) : nullptr, hsp, r.T);
-            E.check_launch("lstm_recur", rows * 4.0 * (LSTM_GATES + LSTM_UNITS));
-            if (pp->sh16)
-                dense_rows_sh_kernel<false, true><<<blocks, 128, DENSE_RB * LSTM_UNITS * sizeof(float), r.st>>>(
-                    hsp, E.pool.at(L.dk), E.pool.at(L.db), pp->cur(o, r.parity), rows, LSTM_UNITS, D, xC);
-            else
-                dense_rows_kernel<<<blocks, 128, DENSE_RB * LSTM_UNITS * sizeof(float), r.st>>>(
-                    hsp, E.pool.at(L.dk), E.pool.at(L.db), pp->cur(o, r.parity), rows, LSTM_UNITS, D);
-            E.check_launch("lstm_dense", rows * 4.0 * (D + LSTM_UNITS));
+                lstm_block_kernel<false><<<r.B, LSTM_THREADS, smem, r.st>>>(pp->cur(x, r.parity), E.pool.at(L.wk4), E.pool.at(L.wr), E.pool.at(L.wb),
+                                                                   E.pool.at(L.dk), E.pool.at(L.db), hp, cp, 0, pp->cur(o, r.parity), r.T, D, xC);
+            E.check_launch("lstm", rows * 4.0 * (2.0 * D + 2 * LSTM_UNITS));
         });
         return o;
     }
