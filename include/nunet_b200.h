@@ -62,13 +62,20 @@ typedef struct nunet_engine nunet_engine;
 typedef struct nunet_config {
     int32_t variant;       /* NUNET_VARIANT_* (must match the blob) */
     int32_t device;        /* CUDA device ordinal */
-    int32_t max_frames;    /* offline capacity: B*T frames per forward call (0 = offline disabled) */
+    int32_t max_frames;    /* offline capacity: frames resident at once (sizes the activation arena; 0 = offline disabled).
+                              Calls with more than max_frames frames are processed in sub-batches of whole clips and, for
+                              clips longer than max_frames, in time chunks (LSTM variant). */
     int32_t max_streams;   /* streaming capacity: concurrent streams (0 = streaming disabled) */
     int32_t ctfa_mode;     /* NUNET_CTFA_* used by the OFFLINE path; streaming is always frame_div32
                               unless stream_ctfa_history != 0 */
     int32_t dc_mode;       /* NUNET_DC_* used by the streaming wav path (offline always pads zero) */
     int32_t stream_ctfa_history; /* extension: carry 31 frames of TA per stream so that streaming == offline */
-    int32_t reserved;
+    int32_t chunk_frames;  /* offline: process every clip in time chunks of at most this many frames, carrying the conv history
+                              rows, LSTM h / c and the 31-frame attention window from chunk to chunk (the reference bounds its
+                              memory the same way: options.py:42 chunk_size, and the one-frame graph converter_proposed.py:
+                              188-867 is the chunk = 1 limit).  0 = whole clips; a clip longer than max_frames is still cut into
+                              chunks of max_frames.  Chunked and unchunked results are bit-identical for chunks of two or more frames
+                              (one-frame chunks use the streaming kernel variants: equal to fp32 rounding). */
 } nunet_config;
 
 /* Text of the last error on the calling thread ("" if none). */

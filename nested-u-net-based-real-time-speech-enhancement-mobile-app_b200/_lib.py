@@ -29,7 +29,7 @@ EXPORTS = [
 class NunetConfig(C.Structure):
     _fields_ = [("variant", C.c_int32), ("device", C.c_int32), ("max_frames", C.c_int32),
                 ("max_streams", C.c_int32), ("ctfa_mode", C.c_int32), ("dc_mode", C.c_int32),
-                ("stream_ctfa_history", C.c_int32), ("reserved", C.c_int32)]
+                ("stream_ctfa_history", C.c_int32), ("chunk_frames", C.c_int32)]
 
 
 class NunetError(RuntimeError):

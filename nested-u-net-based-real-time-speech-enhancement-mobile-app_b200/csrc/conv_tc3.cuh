@@ -84,7 +84,8 @@ constexpr int T3_FIXED_BYTES = T3_TBL_OFF + T3_TBL * 4;
 struct Tc3Params {
     const uint8_t* src0;   // sh16 [frames][F_in][C0]
     const uint8_t* src1;   // sh16 [frames][F_in][C1] or null (C1 == C0 when present)
-    const uint8_t* prev0;  // streaming: history row of src0 per unit [B][F_in][C0] (the other parity's buffer), else null
+    const uint8_t* prev0;  // history row of src0 per clip / stream [B][F_in][C0]: the other parity's buffer (streaming) or the row
+                           // carried over from the previous time chunk (offline); null = zero padding
     const uint8_t* prev1;
     const uint8_t* wpk;    // [nhalf][phase][tap][chunk 2][hi N | lo N][8 halves]
     const float* bias;     // [nhalf * N], packed-column order
@@ -121,6 +122,7 @@ struct Tc3Params {
                            // 128): tile u covers bins [128 j, 128 j + 128) of frame row u / row_tpr, j = u % row_tpr -- no pad position is
                            // ever computed and a tile image starts at a fixed offset of its first frame row (fewest box rows)
     int tile2_off;         // flat distance between the two tiles of an iteration (mt == 2): 128, or P for one row tile per row
+    int prev_rows;         // 1: prev0 / prev1 hold the row in front of every clip (streaming step, or a later time chunk)
     int tm_dmin;           // min(tm_delta): the image may start tm_dmin positions late without losing its first position
     int cluster;           // 1: launched as 2-CTA clusters (the two halves of a 128-channel unit): bulk copies are multicast
     int tma;               // 1: row segments move with 1-D bulk copies; 2: whole tile images move as tensor-map boxes (see tm*)
@@ -204,7 +206,7 @@ struct T3TileGeo {
     int xoff;      // qa - rho_a * P
     int b, t;      // clip and frame (may be -1: the causal pad row) of frame row rho_a
 };
-__device__ __forceinline__ T3TileGeo t3_tile_geo(int qa, int P, int Tp, int padrow, int slots, int dmax, int dmin) {
+__device__ __forceinline__ T3TileGeo t3_tile_geo(int qa, int P, int Tp, int padrow, int slots, int dmax, int dmin, int prev_rows) {
     T3TileGeo g;
     const int rho_a = floor_div(qa + dmin, P);   // image index of flat position f is f - rho_a * P + delta >= 0
     g.xoff = qa - rho_a * P;                      // >= -dmin
@@ -212,7 +214,9 @@ __device__ __forceinline__ T3TileGeo t3_tile_geo(int qa, int P, int Tp, int padr
     g.b = floor_div(rho_a, Tp);
     const int tp = rho_a - g.b * Tp;
     g.t = tp - padrow;
-    g.box = (rho_a >= 0 && tp + need <= Tp) ? 1 : 0;
+    // with carried history rows (time-chunked offline calls) the pad row in front of a clip is real data held in another
+    // tensor: tiles that touch it (tp == 0) take the slot-table loader, which reads it through prev0 / prev1
+    g.box = (rho_a >= 0 && tp + need <= Tp && !(prev_rows && tp < padrow)) ? 1 : 0;
     return g;
 }
 // ---- CTA-pair (cta_group::2) helpers
@@ -627,10 +631,10 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
             const int q0 = tile_q(it, half) - p.lead;
             const long long tl0 = clock64();
             if (p.tma == 2) {
-                const T3TileGeo tg = t3_tile_geo(q0, p.P, Tp, p.padrow, p.slots, max(p.tm_delta[0], p.tm_delta[1]), p.tm_dmin);
+                const T3TileGeo tg = t3_tile_geo(q0, p.P, Tp, p.padrow, p.slots, max(p.tm_delta[0], p.tm_delta[1]), p.tm_dmin, p.prev_rows);
                 // pair mode: one A descriptor serves both CTAs, so both must use the same image layout
                 const int peer_box = PAIR ? t3_tile_geo(tile_q(it, half ^ 1) - p.lead, p.P, Tp, p.padrow, p.slots,
-                                                          max(p.tm_delta[0], p.tm_delta[1]), p.tm_dmin).box : 1;
+                                                          max(p.tm_delta[0], p.tm_delta[1]), p.tm_dmin, p.prev_rows).box : 1;
                 if (tg.box && peer_box) {
                     // one box per image into this warp's plane; 32 arrivals per warp keep the barrier count of the fallback
                     for (int ph = 0; ph < p.nphase; ++ph, ++g) {
@@ -840,8 +844,8 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
                     if (lane == 0) mbar_arrive_peer(&peer_acc_empty[it & 1], 0);
                 }
                 const int dm = max(p.tm_delta[0], p.tm_delta[1]);
-                const bool boxed = t3_tile_geo(tile_q(it, 0) - p.lead, p.P, Tp, p.padrow, p.slots, dm, p.tm_dmin).box &&
-                                   t3_tile_geo(tile_q(it, 1) - p.lead, p.P, Tp, p.padrow, p.slots, dm, p.tm_dmin).box;
+                const bool boxed = t3_tile_geo(tile_q(it, 0) - p.lead, p.P, Tp, p.padrow, p.slots, dm, p.tm_dmin, p.prev_rows).box &&
+                                   t3_tile_geo(tile_q(it, 1) - p.lead, p.P, Tp, p.padrow, p.slots, dm, p.tm_dmin, p.prev_rows).box;
                 for (int ph = 0; ph < p.nphase; ++ph) {
                     mbar_wait(&a_full[buf], round);
                     if (!boxed) fence_proxy_async();   // only the cp.async fallback writes through the generic proxy
@@ -860,9 +864,9 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
             uint32_t adj0 = 0, adj1 = 0;
             bool boxed = false;
             if (p.tma == 2) {
-                const T3TileGeo tg = t3_tile_geo(tile_q(it, 0) - p.lead, p.P, Tp, p.padrow, p.slots, max(p.tm_delta[0], p.tm_delta[1]), p.tm_dmin);
+                const T3TileGeo tg = t3_tile_geo(tile_q(it, 0) - p.lead, p.P, Tp, p.padrow, p.slots, max(p.tm_delta[0], p.tm_delta[1]), p.tm_dmin, p.prev_rows);
                 const int peer_box = PAIR ? t3_tile_geo(tile_q(it, 1) - p.lead, p.P, Tp, p.padrow, p.slots,
-                                                          max(p.tm_delta[0], p.tm_delta[1]), p.tm_dmin).box : 1;
+                                                          max(p.tm_delta[0], p.tm_delta[1]), p.tm_dmin, p.prev_rows).box : 1;
                 if (tg.box && peer_box) {
                     boxed = true;
                     adj0 = (uint32_t)(tg.xoff + p.tm_delta[0]);

@@ -234,6 +234,10 @@ struct Run {   // arguments of one forward / step call
     int est_stride = 256, est_off = 0;
     int ring_pos = 0;
     int step = 0;                    // streaming: absolute step counter (DDB rings)
+    // offline calls cut into time chunks (T frames of every clip per chunk, history carried between chunks):
+    bool use_carry = false;          // this chunk continues its clips: row t = -1, LSTM h / c and the TA window come from the carry arena
+    bool save_carry = false;         // another chunk follows: leave them there
+    int t0 = 0;                      // clip-relative index of the chunk's first frame
 };
 
 struct Engine;
@@ -265,6 +269,26 @@ struct Plan {
     };
     std::vector<StateRef> states;
     std::vector<Ten*> rings;
+    // offline: carried state of time-chunked calls, [carry_cap clips] per region
+    float* carry = nullptr;
+    size_t ctop = 0;             // floats per clip
+    int carry_cap = 0;
+    // (tensor, carry slot) pairs the sub-U-Net being built must save.  A slot belongs to ONE sub-U-Net: the spconv outputs of
+    // an encoder block feed causal convs in the encoder (next spconv) and in the paired decoder (second-level skip), and the
+    // decoder must still see the previous chunk's row after the encoder has saved this chunk's.
+    std::vector<std::pair<Ten*, size_t>> pending_save;
+    size_t carry_alloc(size_t n) {
+        const size_t off = ctop;
+        ctop += (n + 63) & ~size_t(63);
+        return off;
+    }
+    size_t want_carry(Ten* t) {
+        for (auto& pr : pending_save)
+            if (pr.first == t) return pr.second;
+        pending_save.emplace_back(t, carry_alloc(t->numel()));
+        return pending_save.back().second;
+    }
+    float* carry_at(size_t coff) const { return carry + coff * (size_t)carry_cap; }
 
     Ten* make(const std::string& name, int F, int C, bool persistent, bool pingpong = true) {
         auto t = std::make_unique<Ten>();
@@ -316,6 +340,7 @@ struct Plan {
     }
     ~Plan() {
         if (arena) cudaFree(arena);
+        if (carry) cudaFree(carry);
     }
 };
 
@@ -341,7 +366,7 @@ static void state_prefixes(const std::string& block, std::string& pc, std::strin
 }
 
 struct Engine {
-    nunet_config cfg{};
+    nunet_config cfg{};   // (cfg.chunk_frames: forced time-chunk length of offline calls, 0 = only when a clip exceeds max_frames)
     Blob blob;
     ParamPool pool;
     std::map<std::string, ConvLayer> convs;
@@ -768,7 +793,6 @@ struct Engine {
                          float* out, int B, int T, int F_in, bool src_eo, bool out_eo, cudaStream_t st, bool allow_box = true,
                          bool* probe_two = nullptr) {
         Tc3Params p{};
-        if (a_prev && T != 1) fail(NUNET_EINVAL, "conv_tc3: a carried history row needs T = 1");
         p.prev0 = (L.KT == 2) ? reinterpret_cast<const uint8_t*>(a_prev) : nullptr;
         p.prev1 = (L.KT == 2) ? reinterpret_cast<const uint8_t*>(b_prev) : nullptr;
         p.src_eo = src_eo ? 1 : 0;
@@ -800,7 +824,9 @@ struct Engine {
         // Stride-2 units over bin-ordered sources (the inner convs of a sub-U-Net, whose inputs also feed stride-1 skips) use
         // a traversal stride of two positions instead: the box dimension is 2 P positions, so P <= 128.
         const bool box_strided = L.stride == 2 && !src_eo;
-        const bool box = allow_box && tc3_tma == 2 && tc3_encode_tiled() && !p.prev0 && (L.stride == 2 || !src_eo) && p.F_conv >= tc3_box_minf &&
+        p.prev_rows = p.prev0 ? 1 : 0;
+        // (a streaming step, T = 1 with history, has the carried row in every tile: no boxes there)
+        const bool box = allow_box && tc3_tma == 2 && tc3_encode_tiled() && (!p.prev0 || T > 1) && (L.stride == 2 || !src_eo) && p.F_conv >= tc3_box_minf &&
                          (P_min <= 128 || (Fp % 8 == 0 && !box_strided)) && (!box_strided || tc3_box_strided);
         const bool box_lines = box && P_min > 128;
         const int P_pad = box_lines ? (P_min + 7) / 8 * 8 - P_min : 0;    // extra zero positions per flat row
@@ -1018,11 +1044,22 @@ struct Engine {
         if (b && b->eo != a->eo) fail(NUNET_EINVAL, "plan: %s sources disagree on the bin order", role.c_str());
         const bool src_eo = a->eo, dst_eo = o->eo;
         Plan* pp = &P;
+        size_t a_coff = 0, b_coff = 0;
+        if (!P.streaming && P.sh16 && L.KT == 2) {   // causal conv: its inputs' last rows are carried between time chunks
+            a_coff = P.want_carry(a);
+            if (b) b_coff = P.want_carry(b);
+        }
         P.ops.push_back([=](Engine& E, const Run& r) {
             E.cur_op = out_name;
             if (pp->sh16) {
-                E.launch_conv_tc3(L, pp->cur(a, r.parity), b ? pp->cur(b, r.parity) : nullptr, pp->prev(a, r.parity),
-                                  b ? pp->prev(b, r.parity) : nullptr, pp->cur(o, r.parity), r.B, r.T, F_in, src_eo, dst_eo, r.st);
+                const float* ap = pp->prev(a, r.parity);
+                const float* bp = b ? pp->prev(b, r.parity) : nullptr;
+                if (r.use_carry && L.KT == 2) {
+                    ap = pp->carry_at(a_coff);
+                    bp = b ? pp->carry_at(b_coff) : nullptr;
+                }
+                E.launch_conv_tc3(L, pp->cur(a, r.parity), b ? pp->cur(b, r.parity) : nullptr, ap, bp, pp->cur(o, r.parity), r.B, r.T, F_in,
+                                  src_eo, dst_eo, r.st);
                 return;
             }
             E.launch_conv(L, pp->cur(a, r.parity), pp->prev(a, r.parity), b ? pp->cur(b, r.parity) : nullptr,
@@ -1050,6 +1087,7 @@ struct Engine {
         Ten* o = P.make(out_name, x->F, x->C, persistent);
         o->sh = P.sh16;
         Plan* pp = &P;
+        const size_t hc_off = P.streaming ? 0 : P.carry_alloc(2 * 32);     // offline: h | c carried between time chunks, 32 floats each
         P.ops.push_back([=](Engine& E, const Run& r) {
             E.cur_op = out_name;
             const long long rows = (long long)r.B * r.T;
@@ -1057,13 +1095,19 @@ struct Engine {
             const size_t smem = (size_t)LSTM_TB * 2 * (D + LSTM_GATES + 24) * sizeof(float);
             float* hp = hst ? pp->cur(hst, 0) : nullptr;
             float* cp = cst ? pp->cur(cst, 0) : nullptr;
+            int zero_init = 0;
+            if (!pp->streaming && (r.use_carry || r.save_carry)) {
+                hp = pp->carry_at(hc_off);
+                cp = hp + (size_t)pp->carry_cap * LSTM_UNITS;
+                zero_init = r.use_carry ? 0 : 1;
+            }
             // one CTA per clip / stream: projection, recurrence and Dense in one kernel (lstm_kernels.cuh)
             if (pp->sh16)
                 lstm_block_kernel<true><<<r.B, LSTM_THREADS, smem, r.st>>>(pp->cur(x, r.parity), E.pool.at(L.wk4), E.pool.at(L.wr), E.pool.at(L.wb),
-                                                                  E.pool.at(L.dk), E.pool.at(L.db), hp, cp, 0, pp->cur(o, r.parity), r.T, D, xC);
+                                                                  E.pool.at(L.dk), E.pool.at(L.db), hp, cp, zero_init, pp->cur(o, r.parity), r.T, D, xC);
             else
                 lstm_block_kernel<false><<<r.B, LSTM_THREADS, smem, r.st>>>(pp->cur(x, r.parity), E.pool.at(L.wk4), E.pool.at(L.wr), E.pool.at(L.wb),
-                                                                   E.pool.at(L.dk), E.pool.at(L.db), hp, cp, 0, pp->cur(o, r.parity), r.T, D, xC);
+                                                                   E.pool.at(L.dk), E.pool.at(L.db), hp, cp, zero_init, pp->cur(o, r.parity), r.T, D, xC);
             E.check_launch("lstm", rows * 4.0 * (2.0 * D + 2 * LSTM_UNITS));
         });
         return o;
@@ -1100,8 +1144,10 @@ struct Engine {
         const bool sh = P.sh16;
         P.ops.push_back([=](Engine& E, const Run& r) {
             E.cur_op = out_name;
+            if (r.use_carry || r.save_carry)
+                fail(NUNET_EINVAL, "time chunking is not available for the dilated-dense variant: a clip must fit max_frames (T <= %d)", pp->cap);
             const long long units = (long long)r.B * r.T;
-            const long long nin = units * F * h, nout = units * F * C;
+            const long long nin = units * F * h;
             DdbGeom g{pp->streaming ? 1 : 0, r.step & (DDB_RING - 1), r.T};
             float* m[7];
             for (int i = 0; i < 6; ++i) m[i] = pp->cur(mid[i], 0);
@@ -1207,6 +1253,11 @@ struct Engine {
         const MlpLayer mta = mlps.at(blk + "_ta"), mfa = mlps.at(blk + "_fa");
         Plan* pp = &P;
         const int off_mode = cfg.ctfa_mode;
+        // offline: TA rows of the 31 frames in front of a time chunk, and the rows this sub-U-Net must hand to the next chunk
+        const size_t hist_off = P.streaming ? 0 : P.carry_alloc((CTFA_WINDOW - 1) * 64);
+        std::vector<std::pair<Ten*, size_t>> saves;
+        saves.swap(P.pending_save);
+        if ((int)saves.size() > CARRY_MAX) fail(NUNET_EINVAL, "plan: %s carries %zu rows", blk.c_str(), saves.size());
         P.ops.push_back([=](Engine& E, const Run& r) {
             E.cur_op = blk;
             const int frames = r.B * r.T;
@@ -1220,13 +1271,30 @@ struct Engine {
                 ctfa_ta_kernel<<<frames, 256, 0, r.st>>>(pp->cur(x, r.parity), E.mlpw(mta), pp->cur(ta, 0), F0);
             E.check_launch("ctfa_ta", frames * 4.0 * (F0 * 64 + 64));
             const int div32 = pp->streaming ? 1 : (off_mode == NUNET_CTFA_FRAME_DIV32);
-            if (!ring && frames >= 64)
+            if (!pp->streaming && (r.use_carry || r.save_carry) && !pp->sh16) fail(NUNET_EINVAL, "time chunking needs the tensor-core plan");
+            if (!pp->streaming && r.save_carry && saves.size()) {
+                CarrySave cs{};
+                cs.n = (int)saves.size();
+                for (int i = 0; i < cs.n; ++i) {
+                    cs.src[i] = reinterpret_cast<const uint8_t*>(pp->cur(saves[i].first, r.parity));
+                    cs.dst[i] = reinterpret_cast<uint8_t*>(pp->carry_at(saves[i].second));
+                    cs.row16[i] = (int)(saves[i].first->numel() / 4);
+                }
+                carry_save_kernel<<<dim3(cs.n, r.B), 128, 0, r.st>>>(cs, r.T);
+                E.check_launch("carry_save", 0.0);
+            }
+            const float* hist = (!pp->streaming && r.use_carry && !div32) ? pp->carry_at(hist_off) : nullptr;
+            if (!ring && (frames >= 64 || !pp->streaming))
                 ctfa_gate_warp_kernel<<<std::min((frames + 7) / 8, E.num_sms * 8), 256, 0, r.st>>>(pp->cur(ta, 0), E.mlpw(mfa), pp->cur(gate, 0),
-                                                                                                    r.T, div32, (long long)frames);
+                                                                                                    r.T, div32, (long long)frames, hist, r.t0);
             else
                 ctfa_gate_kernel<<<frames, 64, 0, r.st>>>(pp->cur(ta, 0), E.mlpw(mfa), pp->cur(gate, 0), r.T, div32,
                                                          ring ? pp->cur(ring, 0) : nullptr, r.ring_pos);
             E.check_launch("ctfa_gate", frames * 4.0 * (64 + 64));
+            if (!pp->streaming && r.save_carry && !div32) {
+                ctfa_hist_update_kernel<<<r.B, 64, 0, r.st>>>(pp->cur(ta, 0), pp->carry_at(hist_off), r.T, r.use_carry ? 1 : 0);
+                E.check_launch("ctfa_hist", 0.0);
+            }
             const long long n4 = (long long)frames * F0 * 16;
             if (pp->sh16 && fuse_out_conv) {
                 // last decoder block: the 64 -> 1 out_conv is applied on the fly, the block output is never written
@@ -1340,6 +1408,15 @@ struct Engine {
         if (e != cudaSuccess) fail(NUNET_ENOMEM, "cudaMalloc of the %s arena (%.2f GB) failed: %s",
                                    streaming ? "streaming" : "offline", bytes / 1e9, cudaGetErrorString(e));
         CUDA_OK(cudaMemset(P.arena, 0, bytes));
+        if (!streaming && P.sh16 && P.ctop) {
+            // clips whose history can be carried at once: a forced chunk length packs max_frames / chunk_frames clips into a
+            // chunk; without one, time chunking only happens for clips longer than max_frames, one clip at a time
+            P.carry_cap = cfg.chunk_frames > 0 ? std::max(1, cap / cfg.chunk_frames) : 1;
+            const size_t cbytes = P.ctop * (size_t)P.carry_cap * sizeof(float);
+            e = cudaMalloc(&P.carry, cbytes);
+            if (e != cudaSuccess) fail(NUNET_ENOMEM, "cudaMalloc of the carry arena (%.2f GB) failed: %s", cbytes / 1e9, cudaGetErrorString(e));
+            CUDA_OK(cudaMemset(P.carry, 0, cbytes));
+        }
     }
 
     // -------------------------------------------------------------------------------- public operations
@@ -1347,44 +1424,97 @@ struct Engine {
         for (auto& op : P.ops) op(*this, r);
     }
 
-    void forward_mag(const float* mag, int B, int T, float* out, int out_stride, int out_off, cudaStream_t st) {
+    // How a call of B clips x T frames is cut to fit the arena (max_frames): sub-batches of Bs whole clips when a clip fits,
+    // and time chunks of Tc frames with carried history (conv rows, LSTM h / c, the 31-frame TA window) when it does not or
+    // when cfg.chunk_frames asks for it.  Chunked results are bit-identical to unchunked ones: every output position is
+    // computed by the same instruction sequence whatever tile it lands in.
+    struct Cut {
+        int Bs, Tc;
+    };
+    Cut cut_call(int B, int T) const {
         if (!offline.arena) fail(NUNET_EINVAL, "offline path disabled (max_frames = 0)");
         if (B <= 0 || T <= 0) fail(NUNET_EINVAL, "bad shape B=%d T=%d", B, T);
-        if ((long long)B * T > offline.cap) fail(NUNET_ENOMEM, "B*T = %lld exceeds max_frames = %d", (long long)B * T, offline.cap);
+        Cut c;
+        c.Tc = cfg.chunk_frames > 0 ? std::min(cfg.chunk_frames, T) : T;
+        c.Tc = std::min(c.Tc, offline.cap);
+        c.Bs = std::max(1, std::min(B, offline.cap / c.Tc));
+        if (c.Tc < T) {
+            if (!offline.carry) fail(NUNET_ENOMEM, "B*T = %lld exceeds max_frames = %d and this plan cannot carry history between time chunks",
+                                     (long long)B * T, offline.cap);
+            c.Bs = std::min(c.Bs, offline.carry_cap);
+        }
+        return c;
+    }
+
+    // one chunk of the network: mag [Bc*Tc][256] dense -> out (frame-dense with stride / offset)
+    void net_chunk(const float* mag, int Bc, int Tc, int t0, bool more, float* out, int out_stride, int out_off, cudaStream_t st) {
         Run r;
-        r.B = B; r.T = T; r.st = st; r.mag_in = mag; r.est_out = out; r.est_stride = out_stride; r.est_off = out_off;
-        last_B = B; last_T = T;
+        r.B = Bc; r.T = Tc; r.st = st; r.mag_in = mag; r.est_out = out; r.est_stride = out_stride; r.est_off = out_off;
+        r.t0 = t0; r.use_carry = t0 > 0; r.save_carry = more;
+        last_B = Bc; last_T = Tc;
         run_plan(offline, r);
+    }
+
+    void forward_mag(const float* mag, int B, int T, float* out, cudaStream_t st) {
+        const Cut c = cut_call(B, T);
+        if (c.Bs >= B && c.Tc >= T) {
+            net_chunk(mag, B, T, 0, false, out, 256, 0, st);
+            return;
+        }
+        float* mg = offline.cur(o_mag, 0);    // [frames][256] staging of a chunk's input
+        float* es = offline.cur(o_est, 0);    // [frames][257] (column 0 unused)
+        for (int b0 = 0; b0 < B; b0 += c.Bs) {
+            const int Bc = std::min(c.Bs, B - b0);
+            for (int t0 = 0; t0 < T; t0 += c.Tc) {
+                const int Tc = std::min(c.Tc, T - t0);
+                CUDA_OK(cudaMemcpy2DAsync(mg, (size_t)Tc * 256 * 4, mag + ((size_t)b0 * T + t0) * 256, (size_t)T * 256 * 4, (size_t)Tc * 256 * 4,
+                                          Bc, cudaMemcpyDeviceToDevice, st));
+                net_chunk(mg, Bc, Tc, t0, t0 + Tc < T, es, NBINS, 1, st);
+                for (int b = 0; b < Bc; ++b)      // drop the DC column: [Tc][257] -> [Tc][256] of clip b0 + b
+                    CUDA_OK(cudaMemcpy2DAsync(out + ((size_t)(b0 + b) * T + t0) * 256, 256 * 4, es + (size_t)b * Tc * NBINS + 1, NBINS * 4, 256 * 4, Tc,
+                                              cudaMemcpyDeviceToDevice, st));
+            }
+        }
     }
 
     void forward_wav(const float* wav, int B, int n, float* out_wav, float* out_mag, cudaStream_t st) {
         const int T = nunet_num_frames(n);
         if (B <= 0) fail(NUNET_EINVAL, "bad batch size B=%d", B);
         if (T <= 0) fail(NUNET_EINVAL, "clip shorter than one 512-sample frame");
-        if (!offline.arena) fail(NUNET_EINVAL, "offline path disabled (max_frames = 0)");
-        if ((long long)B * T > offline.cap) fail(NUNET_ENOMEM, "B*T = %lld exceeds max_frames = %d", (long long)B * T, offline.cap);
+        const Cut c = cut_call(B, T);
         launches = 0;
-        cur_op = "framing";
         order_begin(st);
         prof_begin(st);
-        const long long frames = (long long)B * T;
         float* mag = offline.cur(o_mag, 0);
         float2* ph = reinterpret_cast<float2*>(offline.cur(o_ph, 0));
         float* est = offline.cur(o_est, 0);   // [frames][257]
         float* fr = offline.cur(o_frames, 0);
-        const int fblocks = (int)((frames + FRAMES_PER_CTA - 1) / FRAMES_PER_CTA);
-        stft_kernel<<<fblocks, 32 * FRAMES_PER_CTA, 0, st>>>(wav, tables(false), mag, ph, B, T, n);
-        check_launch("stft", frames * 4.0 * (256 + 256 + 514));
-        forward_mag(mag, B, T, est, NBINS, 1, st);
-        if (out_mag) CUDA_OK(cudaMemcpyAsync(out_mag, est, frames * NBINS * sizeof(float), cudaMemcpyDeviceToDevice, st));
-        cur_op = "framing";
-        if (out_wav) {
-            istft_frames_kernel<<<fblocks, 32 * FRAMES_PER_CTA, 0, st>>>(est, ph, tables(false), fr, frames);
-            check_launch("istft_frames", frames * 4.0 * (257 + 514 + 512));
-            const long long n_out = (long long)(T - 1) * HOP + NFFT;
-            const int blocks = (int)std::min<long long>((B * n_out + 255) / 256, 148LL * 16);
-            overlap_add_kernel<<<blocks, 256, 0, st>>>(fr, out_wav, B, T, n_out);
-            check_launch("overlap_add", frames * 4.0 * (512 + 256));
+        const long long n_out = (long long)(T - 1) * HOP + NFFT;
+        for (int b0 = 0; b0 < B; b0 += c.Bs) {
+            const int Bc = std::min(c.Bs, B - b0);
+            for (int t0 = 0; t0 < T; t0 += c.Tc) {
+                const int Tc = std::min(c.Tc, T - t0);
+                const long long frames = (long long)Bc * Tc;
+                const int fblocks = (int)((frames + FRAMES_PER_CTA - 1) / FRAMES_PER_CTA);
+                cur_op = "framing";
+                stft_kernel<<<fblocks, 32 * FRAMES_PER_CTA, 0, st>>>(wav + (size_t)b0 * n + (size_t)t0 * HOP, tables(false), mag, ph, Bc, Tc, n);
+                check_launch("stft", frames * 4.0 * (256 + 256 + 514));
+                net_chunk(mag, Bc, Tc, t0, t0 + Tc < T, est, NBINS, 1, st);
+                if (out_mag)
+                    CUDA_OK(cudaMemcpy2DAsync(out_mag + ((size_t)b0 * T + t0) * NBINS, (size_t)T * NBINS * 4, est, (size_t)Tc * NBINS * 4,
+                                              (size_t)Tc * NBINS * 4, Bc, cudaMemcpyDeviceToDevice, st));
+                cur_op = "framing";
+                if (out_wav) {
+                    istft_frames_kernel<<<fblocks, 32 * FRAMES_PER_CTA, 0, st>>>(est, ph, tables(false), fr, frames);
+                    check_launch("istft_frames", frames * 4.0 * (257 + 514 + 512));
+                    // samples [t0 * 256, (t0 + Tc) * 256 + 256) of every clip: the first hop of a later chunk adds to what the
+                    // previous chunk's last frame left there
+                    const long long span = (long long)Tc * HOP + HOP;
+                    const int blocks = (int)std::min<long long>((Bc * span + 255) / 256, 148LL * 16);
+                    overlap_add_kernel<<<blocks, 256, 0, st>>>(fr, out_wav + (size_t)b0 * n_out + (size_t)t0 * HOP, Bc, Tc, span, n_out, t0 > 0 ? 1 : 0);
+                    check_launch("overlap_add", frames * 4.0 * (512 + 256));
+                }
+            }
         }
         order_end(st);
     }
@@ -1837,17 +1967,39 @@ int nunet_forward_wav_host(nunet_engine* h, const float* wav, int B, int n_sampl
         const int T = nunet_num_frames(n_samples);
         if (B <= 0) fail(NUNET_EINVAL, "bad batch size B=%d", B);
         if (T <= 0) fail(NUNET_EINVAL, "clip shorter than one 512-sample frame");
-        const size_t n_in = (size_t)B * n_samples, n_out = (size_t)B * ((size_t)(T - 1) * HOP + NFFT);
-        if (n_in > E.h_in_cap || n_out > E.h_out_cap) fail(NUNET_ENOMEM, "host-call staging capacity exceeded");
+        // The call is staged through the handle's device buffers in sub-batches of whole clips.  The buffers are sized for
+        // max_frames frames at create time; a single clip that is longer than that (a clip cut into time chunks) makes them
+        // grow -- the one place the library allocates after nunet_create.
+        const size_t clip_in = (size_t)n_samples, clip_out = (size_t)(T - 1) * HOP + NFFT;
         cudaStream_t st = E.own_stream;
-        E.order_begin(st);
-        CUDA_OK(cudaMemcpyAsync(E.h_in, wav, n_in * sizeof(float), cudaMemcpyHostToDevice, st));
-        float* est = nullptr;
-        E.forward_wav(E.h_in, B, n_samples, out_wav ? E.h_out : nullptr, nullptr, st);
-        if (out_wav) CUDA_OK(cudaMemcpyAsync(out_wav, E.h_out, n_out * sizeof(float), cudaMemcpyDeviceToHost, st));
-        if (out_mag) {
-            est = E.offline.cur(E.o_est, 0);
-            CUDA_OK(cudaMemcpyAsync(out_mag, est, (size_t)B * T * NBINS * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (clip_in > E.h_in_cap || clip_out > E.h_out_cap) {
+            CUDA_OK(cudaStreamSynchronize(st));
+            if (E.last_done) CUDA_OK(cudaEventSynchronize(E.last_done));
+            cudaFree(E.h_in);
+            cudaFree(E.h_out);
+            E.h_in = E.h_out = nullptr;
+            E.h_in_cap = E.h_out_cap = 0;
+            CUDA_OK(cudaMalloc(&E.h_in, clip_in * sizeof(float)));
+            CUDA_OK(cudaMalloc(&E.h_out, clip_out * sizeof(float)));
+            E.h_in_cap = clip_in;
+            E.h_out_cap = clip_out;
+        }
+        const int Bh = (int)std::max<size_t>(1, std::min(E.h_in_cap / clip_in, E.h_out_cap / clip_out));
+        if (out_mag && Bh < B) fail(NUNET_EINVAL, "nunet_forward_wav_host: out_mag needs the whole call to fit the staging buffers (B <= %d here)", Bh);
+        for (int b0 = 0; b0 < B; b0 += Bh) {
+            const int Bc = std::min(Bh, B - b0);
+            E.order_begin(st);
+            CUDA_OK(cudaMemcpyAsync(E.h_in, wav + (size_t)b0 * clip_in, (size_t)Bc * clip_in * sizeof(float), cudaMemcpyHostToDevice, st));
+            const int before = E.launches;
+            E.forward_wav(E.h_in, Bc, n_samples, out_wav ? E.h_out : nullptr, nullptr, st);
+            if (b0 > 0) E.launches += before;
+            if (out_wav)
+                CUDA_OK(cudaMemcpyAsync(out_wav + (size_t)b0 * clip_out, E.h_out, (size_t)Bc * clip_out * sizeof(float), cudaMemcpyDeviceToHost, st));
+            if (out_mag) {
+                const Engine::Cut c = E.cut_call(B, T);
+                if (c.Bs < B || c.Tc < T) fail(NUNET_EINVAL, "nunet_forward_wav_host: out_mag needs the call to fit max_frames in one piece");
+                CUDA_OK(cudaMemcpyAsync(out_mag, E.offline.cur(E.o_est, 0), (size_t)B * T * NBINS * sizeof(float), cudaMemcpyDeviceToHost, st));
+            }
         }
         CUDA_OK(cudaStreamSynchronize(st));
     });
@@ -1859,7 +2011,7 @@ int nunet_forward_mag_dev(nunet_engine* h, const float* mag, int B, int T, float
         h->e.launches = 0;
         h->e.order_begin(static_cast<cudaStream_t>(stream));
         h->e.prof_begin(static_cast<cudaStream_t>(stream));
-        h->e.forward_mag(mag, B, T, out_mag, 256, 0, static_cast<cudaStream_t>(stream));
+        h->e.forward_mag(mag, B, T, out_mag, static_cast<cudaStream_t>(stream));
         h->e.order_end(static_cast<cudaStream_t>(stream));
     });
 }

@@ -135,19 +135,22 @@ __global__ void __launch_bounds__(32 * FRAMES_PER_CTA) istft_frames_kernel(const
     }
 }
 
-// overlap-add: out[b][j] = sum over the (at most two) frames covering sample j
+// overlap-add of one (time chunk of a) batch: out[b][j] (j < span, relative to the chunk's first sample, rows n_out apart) =
+// sum over the (at most two) frames of the chunk covering sample j.  add_head: the chunk continues its clips, so its first
+// hop adds to what the previous chunk's last frame already left there (0 + a + b either way: bit-identical to one pass).
 __global__ void __launch_bounds__(256) overlap_add_kernel(const float* __restrict__ frames, float* __restrict__ out,
-                                                         int B, int T, long long n_out /* per clip */) {
+                                                         int B, int T, long long span, long long n_out /* per clip */, int add_head) {
     const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long total = (long long)B * n_out;
+    const long long total = (long long)B * span;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-        const int b = (int)(idx / n_out);
-        const int j = (int)(idx - (long long)b * n_out);
+        const int b = (int)(idx / span);
+        const int j = (int)(idx - (long long)b * span);
         const int t1 = j >> 8;   // frame starting at or before j
-        float s = 0.0f;
+        float* o = out + (long long)b * n_out + j;
+        float s = (add_head && j < HOP) ? *o : 0.0f;
         if (t1 - 1 >= 0 && t1 - 1 < T) s += frames[((size_t)b * T + (t1 - 1)) * NFFT + (j - ((t1 - 1) << 8))];
         if (t1 < T) s += frames[((size_t)b * T + t1) * NFFT + (j - (t1 << 8))];
-        out[idx] = s;
+        *o = s;
     }
 }
 

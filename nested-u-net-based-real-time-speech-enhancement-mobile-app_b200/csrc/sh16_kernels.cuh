@@ -200,8 +200,10 @@ __global__ void __launch_bounds__(256) ctfa_ta_warp_sh_kernel(const uint8_t* __r
 // CTFA stage 2 (see ctfa_gate_kernel) with one WARP per frame and the MLP weights staged once per CTA: lane l owns channels
 // l and l + 32.  Same summation order (oldest row first) and MLP operation order as ctfa_gate_kernel, so the results are
 // bit-identical; no ring (offline plans and the reference's one-frame rule only).
+// Time-chunked offline calls: `hist` [clip][31][64] holds the TA rows of the 31 frames in front of this chunk (oldest first) and
+// t0 is the clip-relative index of the chunk's first frame; hist == nullptr means the chunk starts the clip (zeros before it).
 __global__ void __launch_bounds__(256) ctfa_gate_warp_kernel(const float* __restrict__ ta, MlpW fa, float* __restrict__ gate, int T,
-                                                            int mode_div32, long long frames) {
+                                                            int mode_div32, long long frames, const float* __restrict__ hist, int t0) {
     __shared__ MlpSmem w_s;
     __shared__ float avg_s[8][64];
     __shared__ float h_s[8][16];
@@ -216,11 +218,25 @@ __global__ void __launch_bounds__(256) ctfa_gate_warp_kernel(const float* __rest
             a1 = tv1 * (1.0f / CTFA_WINDOW);
         } else {
             const int t = (int)(frame % T);
-            const int n = min(t + 1, CTFA_WINDOW);
+            const float* hrow = hist ? hist + ((frame / T) * (CTFA_WINDOW - 1) + (CTFA_WINDOW - 1)) * 64 : nullptr;   // row of frame "t = 0"
+            const int n = min((hist ? t0 : 0) + t + 1, CTFA_WINDOW);
+            // all (up to) 32 rows are fetched before the first add -- one memory round trip instead of 32 -- and summed
+            // oldest first, the order of the reference's pooling window
+            float r0[CTFA_WINDOW], r1[CTFA_WINDOW];
+#pragma unroll
+            for (int d = 0; d < CTFA_WINDOW; ++d) {
+                const bool in = d < n;
+                const float* src = (d <= t) ? ta + (frame - d) * 64 : hrow + (long long)(t - d) * 64;
+                r0[d] = in ? src[lane] : 0.0f;
+                r1[d] = in ? src[32 + lane] : 0.0f;
+            }
             float s0 = 0.0f, s1 = 0.0f;
-            for (int d = n - 1; d >= 0; --d) {
-                s0 += ta[(frame - d) * 64 + lane];
-                s1 += ta[(frame - d) * 64 + 32 + lane];
+#pragma unroll
+            for (int d = CTFA_WINDOW - 1; d >= 0; --d) {
+                if (d < n) {
+                    s0 += r0[d];
+                    s1 += r1[d];
+                }
             }
             a0 = s0 * (1.0f / CTFA_WINDOW);
             a1 = s1 * (1.0f / CTFA_WINDOW);
@@ -377,6 +393,42 @@ __global__ void __launch_bounds__(128) dense_rows_sh_kernel(const void* __restri
             for (int r = 0; r < nr; ++r) Y[(r0 + r) * N + n] = acc[r];
         }
     }
+}
+
+// ---- carried state of time-chunked offline calls -------------------------------------------------------------------
+// After a chunk of T frames: hist[clip][j] (j < 31) <- row T + j of the concatenation [old hist (31 rows) | ta (T rows)],
+// i.e. the TA rows of the 31 frames in front of the next chunk.  One CTA (64 threads) per clip; all reads before any write.
+__global__ void __launch_bounds__(64) ctfa_hist_update_kernel(const float* __restrict__ ta, float* __restrict__ hist, int T, int have_hist) {
+    const long long b = blockIdx.x;
+    const int c = threadIdx.x;
+    float v[CTFA_WINDOW - 1];
+    float* h = hist + b * (CTFA_WINDOW - 1) * 64;
+#pragma unroll
+    for (int j = 0; j < CTFA_WINDOW - 1; ++j) {
+        const int i = T + j;                                   // index into the concatenation
+        v[j] = (i < CTFA_WINDOW - 1) ? (have_hist ? h[i * 64 + c] : 0.0f) : ta[(b * T + (i - (CTFA_WINDOW - 1))) * 64 + c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < CTFA_WINDOW - 1; ++j) h[j * 64 + c] = v[j];
+}
+
+// The last frame row of every tensor that feeds a causal (two time tap) conv of one nested sub-U-Net is kept for the next
+// chunk, where it is the row "t = -1" (conv_tc3: prev0 / prev1).  grid = (entries, clips).
+constexpr int CARRY_MAX = 32;
+struct CarrySave {
+    const uint8_t* src[CARRY_MAX];   // tensor base of this chunk: [clip][T][row_bytes]
+    uint8_t* dst[CARRY_MAX];         // carry base: [clip][row_bytes]
+    int row16[CARRY_MAX];            // row_bytes / 16
+    int n;
+};
+__global__ void __launch_bounds__(128) carry_save_kernel(const __grid_constant__ CarrySave cs, int T) {
+    const int e = blockIdx.x;
+    const long long b = blockIdx.y;
+    const int n16 = cs.row16[e];
+    const uint4* s = reinterpret_cast<const uint4*>(cs.src[e]) + (b * T + (T - 1)) * (long long)n16;
+    uint4* d = reinterpret_cast<uint4*>(cs.dst[e]) + b * (long long)n16;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) d[i] = __ldg(s + i);
 }
 
 }  // namespace nunet

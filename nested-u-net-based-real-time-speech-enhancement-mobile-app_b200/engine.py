@@ -50,12 +50,12 @@ class NunetEngine:
 
     def __init__(self, blob: bytes, max_frames: int = 0, max_streams: int = 0, device: int = 0,
                  ctfa_mode: str = "causal_avg32", dc_mode: str = "edge", stream_ctfa_history: bool = False,
-                 variant: int = NUNET_VARIANT_LSTM):
+                 variant: int = NUNET_VARIANT_LSTM, chunk_frames: int = 0):
         self._L = _lib.lib()
         self._h = C.c_void_p()
         self.device = torch.device("cuda", device)
         cfg = NunetConfig(variant, device, int(max_frames), int(max_streams), CTFA_MODES[ctfa_mode],
-                          DC_MODES[dc_mode], int(bool(stream_ctfa_history)), 0)
+                          DC_MODES[dc_mode], int(bool(stream_ctfa_history)), int(chunk_frames))
         self.max_frames, self.max_streams = int(max_frames), int(max_streams)
         self.ctfa_mode, self.dc_mode = ctfa_mode, dc_mode
         self.variant, self.stream_ctfa_history = int(variant), bool(stream_ctfa_history)
