@@ -1,6 +1,10 @@
-"""ctypes binding of the C ABI declared in include/nunet_b200.h (csrc/libnunet_b200.so).
+"""Bindings of the C ABI declared in include/nunet_b200.h (csrc/libnunet_b200.so).
 
-There is deliberately no fallback: if the CUDA library is missing or the device is not a B200 the
+`pyb()` is the binding the package uses: the thin pybind11 module csrc/_nunet_pybind (built by csrc/build.sh), one function
+per extern "C" entry point, addresses passed as integers.  `lib()` is the same ABI bound with ctypes -- what a maintainer of
+the reference would write without a compiler, used by the ABI tests to check every declared symbol.
+
+There is deliberately no fallback: if the CUDA library or the pybind11 module is missing, or the device is not a B200, the
 import / create call raises.  Nothing in this package computes the network on the CPU.
 """
 from __future__ import annotations
@@ -39,6 +43,27 @@ class NunetError(RuntimeError):
 
 
 _lib = None
+_pyb = None
+
+
+def pyb():
+    """The pybind11 layer over the C ABI (csrc/_nunet_pybind*.so)."""
+    global _pyb
+    if _pyb is not None:
+        return _pyb
+    import glob
+    import importlib.util
+    cands = glob.glob(os.path.join(_HERE, "csrc", "_nunet_pybind*.so"))
+    if not cands or not os.path.exists(LIB_PATH):
+        raise ImportError(f"{os.path.join(_HERE, 'csrc')}: libnunet_b200.so / _nunet_pybind*.so missing: build them with "
+                          "`python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). There is no CPU fallback.")
+    spec = importlib.util.spec_from_file_location("_nunet_pybind", cands[0])
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    if mod.abi_version() != mod.ABI_VERSION:
+        raise ImportError("nunet_b200: pybind11 module and libnunet_b200.so disagree on the ABI version")
+    _pyb = mod
+    return mod
 
 
 def lib() -> C.CDLL:
@@ -104,5 +129,5 @@ def lib() -> C.CDLL:
 
 def check(rc: int) -> int:
     if rc < 0:
-        raise NunetError(rc, lib().nunet_last_error().decode(errors="replace"))
+        raise NunetError(rc, pyb().last_error())
     return rc

@@ -71,3 +71,23 @@ def test_blob_is_parsed_and_packed_by_the_library(weights):
     b2 = pack_blob(bad)
     assert L.nunet_blob_validate(b2, len(b2), 0) == -1 and b"msfe4_de2_ta/kernel0" in L.nunet_last_error()
     assert L.nunet_blob_validate(blob, len(blob), 1) == -1          # DDB variant not built yet: says so
+
+
+def test_pybind11_layer_forwards_to_the_c_abi():
+    """The thin pybind11 module (csrc/pybind_module.cpp) is the binding the package uses; on a CPU host its host-only entry
+    points work and nunet_create fails loudly (no device) instead of falling back to anything."""
+    from nunet_b200 import _lib
+    from nunet_b200.weights import pack_blob, random_lstm_weights
+    m = _lib.pyb()
+    assert m.abi_version() == m.ABI_VERSION == _lib.lib().nunet_abi_version()
+    assert [m.num_frames(n) for n in (511, 512, 64000)] == [0, 1, 249]
+    blob = pack_blob(random_lstm_weights(0))
+    assert m.blob_validate(blob, 0) > 2_500_000
+    assert m.blob_validate(blob[:1000], 0) == -1 and "truncated" in m.last_error()
+    import torch
+    if not torch.cuda.is_available():
+        rc, h = m.create(0, 0, 8, 0, 0, 1, 0, 0, blob)
+        assert rc == -4 and h == 0 and "CUDA device" in m.last_error()
+        from nunet_b200.engine import NunetEngine
+        with pytest.raises(_lib.NunetError):
+            NunetEngine(blob, max_frames=8)
