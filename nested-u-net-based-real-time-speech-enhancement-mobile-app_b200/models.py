@@ -99,6 +99,8 @@ class _FrameModel:
     def __init__(self, opt, variant: int = NUNET_VARIANT_LSTM):
         self.opt = opt
         self._blob = None
+        self._weights = None
+        self._engine = None
         self.variant = variant
         self.device = int(getattr(opt, "device", 0))
 
@@ -112,12 +114,27 @@ class _FrameModel:
         else:
             w = dict(path_or_set)
         validate(w, expected_ddb_shapes() if ddb else expected_lstm_shapes())
+        self._weights = w
         self._blob = pack_blob(w, VARIANT_DDB if ddb else VARIANT_LSTM)
-        self._engine = NunetEngine(self._blob, max_streams=1, device=self.device, variant=self.variant)
+        self._engine = None          # created on first call: exporting needs no GPU
         return self
+
+    def convert_to_tflite(self, path: str) -> dict:
+        """The converter step on the other side of the path (converter_proposed.py:877-912: TFL_SIGNITURE around this
+        per-frame model -> saved_model -> TFLiteConverter with Optimize.DEFAULT): writes the loaded weights as the reference's
+        one-frame stateful graph with signature 'nutls_lstm_sm' and dynamic-range int8 weights (tflite_export.py).
+        Host-only; no GPU needed."""
+        if self._blob is None:
+            raise RuntimeError("load_weights() first")
+        if self.variant == NUNET_VARIANT_DDB:
+            raise ValueError("only the NUNet-TLS-LSTM graph has an exporter (the dilated-dense variant ships no float checkpoint)")
+        from .tflite_export import export_lstm_tflite
+        return export_lstm_tflite(self._weights, path)
 
     def __call__(self, x, training: bool = False):
         x = np.asarray(x, dtype=np.float32).reshape(1, 256)
+        if self._engine is None:
+            self._engine = NunetEngine(self._blob, max_streams=1, device=self.device, variant=self.variant)
         self._engine.stream_reset()
         out = self._engine.stream_step_mag(torch.from_numpy(x).to(self._engine.device))
         return out.cpu().numpy().reshape(1, 1, 256, 1)

@@ -113,53 +113,76 @@ def _tflite_role_tensors(path: str):
     return g, by_role
 
 
+def _classify_unit(role: str, tensors):
+    """[(tensor, weight-set key, layout kind)] for the constants attributed to layer `role` of a shipped .tflite.
+    kind: 'asis'; 'vec1' (scalar alpha); 'T' ([out,in] -> (in,out)); 'conv' ([Cout,kh,kw,Cin] -> (kh,kw,Cin,Cout));
+    'tconv' ([Cout,kh,kw,Cin] -> (kh,kw,Cout,Cin)); 'mlp' (1x1 conv [Cout,1,1,Cin] -> (Cin,Cout)).
+    Shared by the importer below and the exporter (tflite_export.py), which applies the inverse."""
+    res, convs, biases = [], [], {}
+    for t in tensors:
+        first = t.name.split(";")[0]
+        sub = first.split("/")[1]
+        leaf = first.split("/", 2)[2] if first.count("/") >= 2 else ""
+        nd = len(t.shape)
+        if sub.startswith("layer_normalization"):
+            if leaf == "batchnorm/mul/ReadVariableOp":
+                res.append((t, f"{role}/gamma", "asis"))
+            elif leaf == "batchnorm/ReadVariableOp":
+                res.append((t, f"{role}/beta", "asis"))
+        elif sub.startswith("p_re_lu"):
+            res.append((t, f"{role}/alpha", "vec1"))
+        elif sub.startswith("lstm_cell"):
+            if nd == 2 and tuple(t.shape) == (84, 21):      # leaf names vary (MatMul_1, MatMul_11): go by shape
+                res.append((t, f"{role}/recurrent_kernel", "T"))
+            elif nd == 2:
+                res.append((t, f"{role}/kernel", "T"))
+            elif leaf.startswith("BiasAdd"):
+                res.append((t, f"{role}/bias", "asis"))
+        elif sub == "Tensordot":                                # Dense applied to [T, 21]
+            res.append((t, f"{role}/kernel", "T"))
+        elif sub == "BiasAdd":
+            res.append((t, f"{role}/bias", "asis"))
+        elif sub.startswith("conv2d_transpose"):
+            res.append((t, f"{role}/kernel", "tconv") if nd == 4 else (t, f"{role}/bias", "asis"))
+        elif sub.startswith("conv") or sub == "Conv2D":
+            if nd == 4:
+                convs.append((_suffix(sub), t))
+            elif leaf.startswith("BiasAdd"):
+                biases[_suffix(sub)] = t
+    convs.sort(key=lambda c: c[0])
+    if role.endswith("_ta") or role.endswith("_fa"):
+        for i, (suf, t) in enumerate(convs):
+            res.append((t, f"{role}/kernel{i}", "mlp"))
+            res.append((biases[suf], f"{role}/bias{i}", "asis"))
+    elif convs:
+        suf, t = convs[0]
+        res.append((t, f"{role}/kernel", "conv"))
+        if suf in biases:
+            res.append((biases[suf], f"{role}/bias", "asis"))
+    return res
+
+
+def _to_keras_layout(w: np.ndarray, kind: str) -> np.ndarray:
+    if kind == "vec1":
+        return w.reshape(1)
+    if kind == "T":
+        return np.ascontiguousarray(w.T)
+    if kind == "conv":
+        return np.ascontiguousarray(w.transpose(1, 2, 3, 0))
+    if kind == "tconv":
+        return np.ascontiguousarray(w.transpose(1, 2, 0, 3))
+    if kind == "mlp":
+        k = np.ascontiguousarray(w.transpose(1, 2, 3, 0))
+        return k.reshape(k.shape[-2:])
+    return w
+
+
 def _unit_from_tflite(role: str, tensors, out: Dict[str, np.ndarray]) -> None:
     """Fill the `<role>/...` entries of a weight set from the constants attributed to that layer, converting
     TFLite layouts to the Keras ones: conv [Cout,kh,kw,Cin] -> (kh,kw,Cin,Cout); transpose conv
     [Cout,kh,kw,Cin] -> (kh,kw,Cout,Cin); FC [out,in] -> (in,out)."""
-    convs, biases = [], {}
-    for t in tensors:
-        sub = t.name.split(";")[0].split("/")[1]
-        leaf = t.name.split(";")[0].split("/", 2)[2] if t.name.split(";")[0].count("/") >= 2 else ""
-        w = t.dequantized()
-        if sub.startswith("layer_normalization"):
-            if leaf == "batchnorm/mul/ReadVariableOp":
-                out[f"{role}/gamma"] = w
-            elif leaf == "batchnorm/ReadVariableOp":
-                out[f"{role}/beta"] = w
-        elif sub.startswith("p_re_lu"):
-            out[f"{role}/alpha"] = w.reshape(1)
-        elif sub.startswith("lstm_cell"):
-            if w.ndim == 2 and w.shape == (84, 21):         # leaf names vary (MatMul_1, MatMul_11): go by shape
-                out[f"{role}/recurrent_kernel"] = np.ascontiguousarray(w.T)
-            elif w.ndim == 2:
-                out[f"{role}/kernel"] = np.ascontiguousarray(w.T)
-            elif leaf.startswith("BiasAdd"):
-                out[f"{role}/bias"] = w
-        elif sub == "Tensordot":                                # Dense applied to [T, 21]
-            out[f"{role}/kernel"] = np.ascontiguousarray(w.T)
-        elif sub == "BiasAdd":
-            out[f"{role}/bias"] = w
-        elif sub.startswith("conv2d_transpose"):
-            if w.ndim == 4:
-                out[f"{role}/kernel"] = np.ascontiguousarray(w.transpose(1, 2, 0, 3))
-            else:
-                out[f"{role}/bias"] = w
-        elif sub.startswith("conv") or sub == "Conv2D":
-            if w.ndim == 4:
-                convs.append((_suffix(sub), np.ascontiguousarray(w.transpose(1, 2, 3, 0))))
-            elif leaf.startswith("BiasAdd"):
-                biases[_suffix(sub)] = w
-    convs.sort(key=lambda c: c[0])
-    if role.endswith("_ta") or role.endswith("_fa"):
-        for i, (suf, k) in enumerate(convs):
-            out[f"{role}/kernel{i}"] = k.reshape(k.shape[-2:])
-            out[f"{role}/bias{i}"] = biases[suf]
-    elif convs:
-        suf, k = convs[0]
-        out[f"{role}/kernel"] = k
-        if suf in biases:
-            out[f"{role}/bias"] = biases[suf]
+    for t, key, kind in _classify_unit(role, tensors):
+        out[key] = _to_keras_layout(t.dequantized(), kind)
 
 
 def lstm_weights_from_tflite(path: str) -> Dict[str, np.ndarray]:

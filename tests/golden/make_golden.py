@@ -8,6 +8,7 @@ Fixtures:
   wav_excerpt.npz          first 1.5 s (int16) of data/40hc020i_0.wav (noisy) and data/40hc020i.wav (clean)
   o2_lstm.npz              outputs of the reference's shipped nutls_lstm.tflite executed by oracle/tflite_graph.py
   o2_ddb.npz               the same for nutls.tflite (dilated-dense baseline)
+  reference_artifacts.json SHA-256 / size of the reference's shipped .tflite / .h5 files (exporter golden values)
   oracle_io_lstm.npz       oracle outputs with the reference .h5 weights on seeded inputs (regression pin +
                            expected values for the GPU parity tests)
 """
@@ -119,6 +120,19 @@ def oracle_io():
     np.savez_compressed(f"{HERE}/oracle_io_lstm.npz", **out)
 
 
+def reference_artifacts():
+    """SHA-256 / size of the reference's shipped artefacts: the exporter tests reproduce nutls_lstm.tflite byte for byte."""
+    import hashlib
+    out = {}
+    for name, rel in (("nutls_lstm.tflite", "dnn_model/tflite/nutls_lstm.tflite"), ("nutls.tflite", "dnn_model/tflite/nutls.tflite"),
+                      ("nutls_lstm.h5", "dnn_model/log/saved_model/nutls_lstm.h5")):
+        b = open(f"{REF}/{rel}", "rb").read()
+        out[name] = {"sha256": hashlib.sha256(b).hexdigest(), "bytes": len(b)}
+    json.dump(out, open(f"{HERE}/reference_artifacts.json", "w"), indent=1)
+    from nunet_b200.tflite_export import build_skeleton
+    build_skeleton()          # nunet_b200/data/nutls_lstm_skeleton.tflite.gz: the shipped graph with weights and scales zeroed
+
+
 if __name__ == "__main__":
     java_windows()
     state_tables()
@@ -126,4 +140,5 @@ if __name__ == "__main__":
     oracle_io()
     graph_oracle_io()
     graph_oracle_ddb_io()
+    reference_artifacts()
     print("fixtures written to", HERE)
