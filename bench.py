@@ -278,7 +278,8 @@ def streaming_record(ctx: Ctx, blob: bytes, variant: str, S: int, steps: int, wa
     from nunet_b200.synth import synth_clips
     dev = ctx.dev
     eng = NunetEngine(blob, max_streams=S, device=ctx.local_rank, ctfa_mode="frame_div32", dc_mode="edge",
-                      variant=1 if variant == "ddb" else 0)
+                      variant={"lstm": 0, "ddb": 1, "hybrid": 2}[variant])
+    variant = "lstm" if variant == "hybrid" else variant       # same graph, same algorithmic bytes
     W = max(warmup, 4)       # 2 plain steps + one CUDA-graph capture per step parity happen before the timed region
     nh = min(W + steps + 4, 260)
     pool = synth_clips(min(S, 32), 256 * nh, first_clip=1000 * ctx.rank)
@@ -433,6 +434,17 @@ def main():
                 extra["configs[2]"] = dict(config=streaming_config("lstm", args.streams), metric=METRIC, unit=UNIT, **sr)
             except Exception as e:
                 extra["configs[2]"] = {"error": repr(e)}
+            try:
+                # not a BASELINE config: the same streaming workload with the arithmetic of the DEPLOYED int8 dynamic-range graph
+                # (engine variant 2; FP32 / dp4a SIMT kernels, every hybrid operator's input quantised per stream and call)
+                from nunet_b200.tflite_export import hybrid_weight_set
+                hs = min(args.streams, 256)
+                hr = streaming_record(ctx, pack_blob(hybrid_weight_set(weights), 2), "hybrid", hs, max(args.steps, 20), args.warmup)
+                cfg_h = streaming_config("lstm", hs)
+                cfg_h["workload"] = cfg_h["workload"].replace("configs[2]", "deployed int8-hybrid arithmetic (SURVEY 8(f)3)")
+                extra["int8_hybrid_streaming"] = dict(config=cfg_h, metric=METRIC, unit=UNIT, **hr)
+            except Exception as e:
+                extra["int8_hybrid_streaming"] = {"error": repr(e)}
             try:
                 dw = load_weights_or_die("ddb")
                 dr = offline_record(ctx, pack_blob(dw, 1), "ddb", args.batch, n_samples, args.steps, args.warmup, profile=True)

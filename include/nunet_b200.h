@@ -47,7 +47,13 @@ enum {
 
 /* variant: which bottleneck block the nested U-Net uses */
 enum { NUNET_VARIANT_LSTM = 0,   /* models/proposed.py   NUTLS_LSTM  */
-       NUNET_VARIANT_DDB = 1 };  /* models/nunet_tls.py  NUTLS (dilated dense block) */
+       NUNET_VARIANT_DDB = 1,    /* models/nunet_tls.py  NUTLS (dilated dense block) */
+       NUNET_VARIANT_LSTM_HYBRID = 2 };
+       /* NUTLS_LSTM with the arithmetic of the DEPLOYED artefact: the dynamic-range-quantised one-frame .tflite
+          (converter_proposed.py:901 Optimize.DEFAULT) as the TFLite runtime executes it -- int8 weights, every hybrid
+          CONV_2D / FULLY_CONNECTED input quantised to int8 per call, int32 accumulation (interpreter_proposed.py:374-380,
+          RTSE_NUTLS_LSTM.java:571).  Streaming entry points only (the reference has no offline int8 graph); the blob carries
+          the int8 tensors and their scales (nunet_b200.weights.hybrid_weight_set). */
 
 /* CTFA time pooling */
 enum { NUNET_CTFA_CAUSAL_AVG32 = 0,  /* offline graph: models/proposed.py:125 `ctfa` (mean of last 32 TA) */

@@ -15,7 +15,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libnunet_b200.so")
 
-NUNET_VARIANT_LSTM, NUNET_VARIANT_DDB = 0, 1
+NUNET_VARIANT_LSTM, NUNET_VARIANT_DDB, NUNET_VARIANT_LSTM_HYBRID = 0, 1, 2
 NUNET_CTFA_CAUSAL_AVG32, NUNET_CTFA_FRAME_DIV32 = 0, 1
 NUNET_DC_ZERO, NUNET_DC_EDGE = 0, 1
 

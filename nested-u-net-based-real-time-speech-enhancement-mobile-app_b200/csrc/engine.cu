@@ -33,6 +33,7 @@
 #include "sh16_kernels.cuh"
 #include "lstm_kernels.cuh"
 #include "ddb_kernels.cuh"
+#include "hybrid_kernels.cuh"
 
 namespace nunet {
 
@@ -155,6 +156,20 @@ struct DdbLayer {   // one dilated dense block: float offsets into the pool
     int C = 0;
     size_t w_in, b_in, a_in, w_out, b_out, a_out;
     size_t w0[6], b0[6], w1[6], b1[6], gamma[6], beta[6], alpha[6];
+};
+// int8-hybrid variant (hybrid_kernels.cuh): float offsets into the pool; int8 / int32 data is stored as raw bytes
+struct HqConvLayer {
+    size_t w = 0, wtap = 0, wscale = 0, bias = 0, gamma = 0, beta = 0, alpha = 0;
+    int Ct = 0, Cout = 0, KT = 1, KF = 1, padl = 0, stride = 1, epi = HQ_BIAS;
+};
+struct HqMlpLayer {
+    size_t k0, k1, s0, s1, b0, b1;
+};
+struct HqLstmLayer {
+    size_t wk, wr, wd, wd_f, bk, bd;
+    float sk, sr, sd;
+    bool dense_q;
+    int D;
 };
 struct VecLayer {   // input_layer / out_conv
     size_t w, b, gamma, beta, alpha;
@@ -374,6 +389,11 @@ struct Engine {
     std::map<std::string, LstmLayer> lstms;
     std::map<std::string, DdbLayer> ddbs;
     VecLayer in_layer{}, out_layer{};
+    std::map<std::string, HqConvLayer> hconvs;
+    std::map<std::string, HqMlpLayer> hmlps;
+    std::map<std::string, HqLstmLayer> hlstms;
+    std::map<std::string, std::pair<size_t, size_t>> hups;   // up_sampling: dequantised kernel [k][ci][co], bias
+    Ten *hq_qbuf = nullptr, *hq_qp = nullptr;
     size_t tw_off = 0, win_off = 0, win_stream_off = 0, inv_win_off = 0;
 
     Plan offline, stream;
@@ -577,10 +597,134 @@ struct Engine {
         ddbs[role] = d;
     }
     bool is_ddb() const { return cfg.variant == NUNET_VARIANT_DDB; }
+    bool is_hybrid() const { return cfg.variant == NUNET_VARIANT_LSTM_HYBRID; }
+
+    // ---- int8-hybrid variant: int8 weights (stored in the blob as exact float values, TFLite layouts) + scales
+    size_t add_bytes(const std::vector<int8_t>& v) {
+        std::vector<float> raw((v.size() + 3) / 4, 0.0f);
+        memcpy(raw.data(), v.data(), v.size());
+        return pool.add(raw);
+    }
+    size_t add_ints(const std::vector<int>& v) {
+        std::vector<float> raw(v.size());
+        memcpy(raw.data(), v.data(), v.size() * 4);
+        return pool.add(raw);
+    }
+    static int8_t q8(float f) {
+        if (f != std::floor(f) || f < -128.f || f > 127.f) fail(NUNET_EINVAL, "weight blob: a quantised tensor holds %g", f);
+        return (int8_t)f;
+    }
+    // role/kernel_q [Cout][KT][KF][Ct] + role/kernel_scale [Cout]
+    void add_hq_conv(const std::string& role, int Ct, int Cout, int KT, int KF, int padl, int stride, int epi) {
+        const Arr& q = blob.get(role + "/kernel_q", {Cout, KT, KF, Ct});
+        HqConvLayer L;
+        L.Ct = Ct; L.Cout = Cout; L.KT = KT; L.KF = KF; L.padl = padl; L.stride = stride; L.epi = epi;
+        const int taps = KT * KF, C4 = Ct / 4;
+        std::vector<int8_t> w((size_t)taps * Ct * Cout);
+        std::vector<int> wtap((size_t)taps * Cout, 0);
+        for (int c = 0; c < Cout; ++c)
+            for (int t = 0; t < taps; ++t)
+                for (int ci = 0; ci < Ct; ++ci) {
+                    const int8_t v = q8(q.data[((size_t)c * taps + t) * Ct + ci]);
+                    w[(((size_t)t * C4 + ci / 4) * Cout + c) * 4 + (ci & 3)] = v;       // word (tap, ci/4, c), byte ci % 4
+                    wtap[(size_t)t * Cout + c] += v;
+                }
+        L.w = add_bytes(w);
+        L.wtap = add_ints(wtap);
+        L.wscale = add_arr(role + "/kernel_scale", {Cout});
+        L.bias = add_arr(role + "/bias", {Cout});
+        if (epi != HQ_BIAS) {
+            const int cln = (epi == HQ_LN) ? Cout : Cout / 2;
+            L.gamma = add_arr(role + "/gamma", {cln});
+            L.beta = add_arr(role + "/beta", {cln});
+            L.alpha = add_arr(role + "/alpha", {1});
+        }
+        hconvs[role] = L;
+    }
+    void add_hq_mlp(const std::string& role) {
+        HqMlpLayer m;
+        auto bytes = [&](const std::string& n, int co, int ci) {
+            const Arr& q = blob.get(n, {co, 1, 1, ci});
+            std::vector<int8_t> v(q.n);
+            for (size_t i = 0; i < q.n; ++i) v[i] = q8(q.data[i]);
+            return add_bytes(v);
+        };
+        m.k0 = bytes(role + "/kernel0_q", 16, 64);
+        m.k1 = bytes(role + "/kernel1_q", 64, 16);
+        m.s0 = add_arr(role + "/kernel0_scale", {16});
+        m.s1 = add_arr(role + "/kernel1_scale", {64});
+        m.b0 = add_arr(role + "/bias0", {16});
+        m.b1 = add_arr(role + "/bias1", {64});
+        hmlps[role] = m;
+    }
+    void add_hq_lstm(const std::string& lstm, const std::string& dense, int D) {
+        HqLstmLayer l{};
+        l.D = D;
+        auto bytes = [&](const std::string& n, int a, int b) {
+            const Arr& q = blob.get(n, {a, b});
+            std::vector<int8_t> v(q.n);
+            for (size_t i = 0; i < q.n; ++i) v[i] = q8(q.data[i]);
+            return add_bytes(v);
+        };
+        l.wk = bytes(lstm + "/kernel_q", LSTM_GATES, D);
+        l.wr = bytes(lstm + "/recurrent_kernel_q", LSTM_GATES, LSTM_UNITS);
+        l.sk = blob.get(lstm + "/kernel_scale", {1}).data[0];
+        l.sr = blob.get(lstm + "/recurrent_kernel_scale", {1}).data[0];
+        l.bk = add_arr(lstm + "/bias", {LSTM_GATES});
+        l.bd = add_arr(dense + "/bias", {D});
+        l.dense_q = blob.m.count(dense + "/kernel_q") != 0;
+        if (l.dense_q) {
+            l.wd = bytes(dense + "/kernel_q", D, LSTM_UNITS);
+            l.sd = blob.get(dense + "/kernel_scale", {1}).data[0];
+        } else {
+            l.wd_f = add_arr(dense + "/kernel", {LSTM_UNITS, D});
+        }
+        hlstms[lstm] = l;
+    }
+    void add_hq_up(const std::string& up) {
+        const Arr& ku = blob.get(up + "/kernel", {1, 3, 128, 128});      // (kh, kw, Cout, Cin), dequantised
+        std::vector<float> w((size_t)3 * 128 * 128);
+        for (int k = 0; k < 3; ++k)
+            for (int co = 0; co < 128; ++co)
+                for (int ci = 0; ci < 128; ++ci) w[((size_t)k * 128 + ci) * 128 + co] = ku.data[((size_t)k * 128 + co) * 128 + ci];
+        const size_t wo = pool.add(w);
+        hups[up] = {wo, add_arr(up + "/bias", {128})};
+    }
+    void pack_params_hybrid() {
+        in_layer.w = add_arr("input_layer/kernel", {1, 1, 1, 64});
+        in_layer.b = add_arr("input_layer/bias", {64});
+        in_layer.gamma = add_arr("input_layer/gamma", {64});
+        in_layer.beta = add_arr("input_layer/beta", {64});
+        in_layer.alpha = add_arr("input_layer/alpha", {1});
+        out_layer.w = add_arr("out_conv/kernel", {1, 1, 64, 1});
+        out_layer.b = add_arr("out_conv/bias", {1});
+        for (int side = 0; side < 2; ++side)
+            for (int i = 0; i < 6; ++i) {
+                const std::string blk = side ? DEC_NAMES[i] : ENC_NAMES[i];
+                const int n = side ? DEC_N[i] : ENC_N[i];
+                const int F0 = side ? DEC_F0[i] : ENC_F0[i];
+                add_hq_conv(blk + "_in", side ? 128 : 64, 64, 1, 1, 0, 1, HQ_LN);
+                if (side) add_hq_up(UP_NAMES[i]);
+                for (int k = 1; k <= n; ++k) add_hq_conv(blk + "_conv" + std::to_string(k), ((k == 1) ? 64 : 32) * (side ? 2 : 1), 32, 2, 3, 1, 2, HQ_LN);
+                add_hq_lstm(blk + "_lstm", blk + "_dense", (F0 >> n) * 32);
+                for (int k = 1; k <= n; ++k)
+                    add_hq_conv(blk + "_spconv" + std::to_string(k), 64, (k == n) ? 128 : 64, 2, 3, 1, 1, (k == n) ? HQ_SHUF64 : HQ_SHUF32);
+                add_hq_mlp(blk + "_ta");
+                add_hq_mlp(blk + "_fa");
+                if (side == 0) add_hq_conv(DOWN_NAMES[i], 64, 64, 1, 3, 0, 2, HQ_BIAS);
+            }
+        add_hq_lstm("lstm", "dense", 256);
+        pack_framing_tables();
+    }
 
     void pack_params() {
-        if (blob.variant != cfg.variant || (cfg.variant != NUNET_VARIANT_LSTM && cfg.variant != NUNET_VARIANT_DDB))
+        if (blob.variant != cfg.variant ||
+            (cfg.variant != NUNET_VARIANT_LSTM && cfg.variant != NUNET_VARIANT_DDB && cfg.variant != NUNET_VARIANT_LSTM_HYBRID))
             fail(NUNET_EINVAL, "weight blob variant %d does not match the requested variant %d", blob.variant, cfg.variant);
+        if (is_hybrid()) {
+            pack_params_hybrid();
+            return;
+        }
         in_layer.w = add_arr("input_layer/kernel", {1, 1, 1, 64});
         in_layer.b = add_arr("input_layer/bias", {64});
         in_layer.gamma = add_arr("input_layer/gamma", {64});
@@ -615,6 +759,10 @@ struct Engine {
         if (is_ddb()) add_ddb("ddb", 64);
         else add_lstm("lstm", "dense", 256);
 
+        pack_framing_tables();
+    }
+
+    void pack_framing_tables() {
         // framing tables (tf.signal.hann_window periodic; inverse_stft_window_fn(256); interpreter_proposed.py:21-26)
         std::vector<float> tw(512), win(512), wins(512), inv(512);
         const double PI = 3.14159265358979323846;
@@ -1385,11 +1533,175 @@ struct Engine {
         });
     }
 
+    // ---- int8-hybrid variant: the one-frame graph operator by operator (hybrid_kernels.cuh), fp32 tensors, streaming only
+    Ten* hq_conv_op(Plan& P, const std::string& role, Ten* a, Ten* b, const std::string& out_name) {
+        const HqConvLayer L = hconvs.at(role);
+        if (a->C + (b ? b->C : 0) != L.Ct || (b && b->F != a->F)) fail(NUNET_EINVAL, "plan: %s wiring", role.c_str());
+        const int F_in = a->F;
+        const int F_conv = (L.stride == 2) ? F_in / 2 : F_in;
+        const bool shuf = (L.epi == HQ_SHUF32 || L.epi == HQ_SHUF64);
+        Ten* o = P.make(out_name, shuf ? 2 * F_conv : F_conv, shuf ? L.Cout / 2 : L.Cout, true);
+        Plan* pp = &P;
+        P.ops.push_back([=](Engine& E, const Run& r) {
+            E.cur_op = out_name;
+            int8_t* qb = reinterpret_cast<int8_t*>(pp->cur(E.hq_qbuf, 0));
+            HqParams* qp = reinterpret_cast<HqParams*>(pp->cur(E.hq_qp, 0));
+            hq_quantize_kernel<<<r.B, 256, 0, r.st>>>(pp->prev(a, r.parity), pp->cur(a, r.parity), b ? pp->prev(b, r.parity) : nullptr,
+                                                      b ? pp->cur(b, r.parity) : nullptr, F_in, a->C, b ? b->C : 0, L.KT, qb, qp);
+            E.check_launch("hq_quantize", 0.0);
+            HqConv c{};
+            c.q = qb; c.qp = qp;
+            c.w = reinterpret_cast<const int*>(E.pool.at(L.w));
+            c.wtap = reinterpret_cast<const int*>(E.pool.at(L.wtap));
+            c.wscale = E.pool.at(L.wscale); c.bias = E.pool.at(L.bias);
+            c.gamma = E.pool.at(L.gamma); c.beta = E.pool.at(L.beta); c.alpha = E.pool.at(L.alpha);
+            c.out = pp->cur(o, r.parity);
+            c.F_in = F_in; c.Ct = L.Ct; c.Cout = L.Cout; c.KT = L.KT; c.KF = L.KF; c.padl = L.padl; c.stride = L.stride; c.F_conv = F_conv; c.epi = L.epi;
+            const int PT = 128 / L.Cout;
+            hq_conv_kernel<<<dim3(r.B, (F_conv + PT - 1) / PT), 128, 128 * sizeof(float), r.st>>>(c);
+            E.check_launch("hq_conv", (double)r.B * (F_in * L.Ct * L.KT + 4.0 * o->numel()));
+        });
+        return o;
+    }
+
+    Ten* hq_lstm_op(Plan& P, const std::string& lstm, Ten* x, const std::string& out_name, const std::string& state_name) {
+        const HqLstmLayer L = hlstms.at(lstm);
+        const int D = x->F * x->C;
+        if (D != L.D) fail(NUNET_EINVAL, "plan: %s width", lstm.c_str());
+        Ten* hst = P.make("", 1, LSTM_UNITS, true, false);
+        Ten* cst = P.make("", 1, LSTM_UNITS, true, false);
+        Plan::StateRef sh, sc;
+        sh.name = state_name + "_h"; sh.is_lstm = true; sh.a = hst;
+        sc.name = state_name + "_c"; sc.is_lstm = true; sc.a = cst;
+        P.states.push_back(sh);
+        P.states.push_back(sc);
+        Ten* o = P.make(out_name, x->F, x->C, true);
+        Plan* pp = &P;
+        P.ops.push_back([=](Engine& E, const Run& r) {
+            E.cur_op = out_name;
+            HqLstm l{};
+            l.x = pp->cur(x, r.parity); l.y = pp->cur(o, r.parity);
+            l.h = pp->cur(hst, 0); l.c = pp->cur(cst, 0);
+            l.wk = reinterpret_cast<const int8_t*>(E.pool.at(L.wk));
+            l.wr = reinterpret_cast<const int8_t*>(E.pool.at(L.wr));
+            l.wd = L.dense_q ? reinterpret_cast<const int8_t*>(E.pool.at(L.wd)) : nullptr;
+            l.wd_f = L.dense_q ? nullptr : E.pool.at(L.wd_f);
+            l.bk = E.pool.at(L.bk); l.bd = E.pool.at(L.bd);
+            l.sk = L.sk; l.sr = L.sr; l.sd = L.sd; l.D = D;
+            hq_lstm_kernel<<<r.B, 128, 0, r.st>>>(l);
+            E.check_launch("hq_lstm", (double)r.B * 8.0 * D);
+        });
+        return o;
+    }
+
+    HqMlp hq_mlp_of(const HqMlpLayer& m) const {
+        HqMlp o;
+        o.k0 = reinterpret_cast<const int8_t*>(pool.at(m.k0)); o.k1 = reinterpret_cast<const int8_t*>(pool.at(m.k1));
+        o.s0 = pool.at(m.s0); o.s1 = pool.at(m.s1); o.b0 = pool.at(m.b0); o.b1 = pool.at(m.b1);
+        return o;
+    }
+
+    Ten* hq_msfe(Plan& P, const std::string& blk, int n, Ten* en_in, Ten* const* skips, Ten** des_out) {
+        std::string pc, ps;
+        state_prefixes(blk, pc, ps);
+        std::vector<Ten*> ens;
+        Ten* cur = en_in;
+        for (int k = 1; k <= n; ++k) {
+            Ten* sk = skips ? skips[k - 1] : nullptr;
+            Plan::StateRef st;
+            st.name = pc + "_" + std::to_string(k); st.a = cur; st.b = sk;
+            P.states.push_back(st);
+            cur = hq_conv_op(P, blk + "_conv" + std::to_string(k), cur, sk, blk + "_conv" + std::to_string(k));
+            ens.push_back(cur);
+        }
+        cur = hq_lstm_op(P, blk + "_lstm", cur, blk + "_bb", blk);
+        std::vector<Ten*> des;
+        for (int k = 1; k <= n; ++k) {
+            Ten* sk = ens[n - k];
+            Plan::StateRef st;
+            st.name = ps + "_" + std::to_string(k); st.a = cur; st.b = sk;
+            P.states.push_back(st);
+            cur = hq_conv_op(P, blk + "_spconv" + std::to_string(k), cur, sk, blk + "_spconv" + std::to_string(k));
+            des.push_back(cur);
+        }
+        if (des_out)
+            for (int k = 1; k <= n; ++k) des_out[k - 1] = des[n - k];
+        Ten* x = cur;
+        Ten* out = P.make(blk + "_out", x->F, 64, true);
+        const HqMlpLayer mta = hmlps.at(blk + "_ta"), mfa = hmlps.at(blk + "_fa");
+        const int F0 = x->F;
+        Plan* pp = &P;
+        P.ops.push_back([=](Engine& E, const Run& r) {
+            E.cur_op = blk;
+            hq_ctfa_kernel<<<r.B, 64, 0, r.st>>>(pp->cur(x, r.parity), pp->cur(en_in, r.parity), E.hq_mlp_of(mta), E.hq_mlp_of(mfa),
+                                                 pp->cur(out, r.parity), F0);
+            E.check_launch("hq_ctfa", (double)r.B * 4.0 * 3 * F0 * 64);
+        });
+        return out;
+    }
+
+    void build_hybrid_plan(Plan& P) {
+        Plan* pp = &P;
+        hq_qbuf = P.make("", 1, 2 * 256 * 128 / 4, true, false);      // int8 [rows 2][F 256][C 128] at most
+        hq_qp = P.make("", 1, 64, true, false);
+        Ten* x0 = P.make("input_layer", 256, 64, true);
+        P.ops.push_back([=](Engine& E, const Run& r) {
+            E.cur_op = "input_layer";
+            const long long npix = (long long)r.B * 256;
+            const VecLayer& v = E.in_layer;
+            input_layer_kernel<<<(int)((npix * 8 + 255) / 256), 256, 0, r.st>>>(r.mag_in, E.pool.at(v.w), E.pool.at(v.b), E.pool.at(v.gamma),
+                                                                              E.pool.at(v.beta), E.pool.at(v.alpha), pp->cur(x0, r.parity), npix);
+            E.check_launch("input_layer", npix * 4.0 * 65);
+        });
+        Ten* x = x0;
+        Ten* enc_des[6][6] = {};
+        Ten* enc_out[6] = {};
+        for (int i = 0; i < 6; ++i) {
+            const std::string blk = ENC_NAMES[i];
+            Ten* en_in = hq_conv_op(P, blk + "_in", x, nullptr, blk + "_in");
+            Ten* out = hq_msfe(P, blk, ENC_N[i], en_in, nullptr, enc_des[i]);
+            x = hq_conv_op(P, DOWN_NAMES[i], out, nullptr, DOWN_NAMES[i]);
+            enc_out[i] = x;
+        }
+        Ten* y = hq_lstm_op(P, "lstm", x, "bb_main", "state");
+        for (int i = 0; i < 6; ++i) {
+            const std::string blk = DEC_NAMES[i];
+            const int j = 5 - i;
+            // up_sampling(cat[y, enc_out]): float transpose conv on the dequantised kernel, then the hybrid 1x1 inconv
+            Ten* a = y;
+            Ten* b = enc_out[j];
+            Ten* u = P.make(std::string(UP_NAMES[i]), 2 * a->F, 128, true);
+            const auto up = hups.at(UP_NAMES[i]);
+            const int F_in = a->F;
+            const std::string un = UP_NAMES[i];
+            P.ops.push_back([=](Engine& E, const Run& r) {
+                E.cur_op = un;
+                hq_upsample_kernel<<<dim3(r.B, 2 * F_in), 128, 0, r.st>>>(pp->cur(a, r.parity), pp->cur(b, r.parity), E.pool.at(up.first),
+                                                                         E.pool.at(up.second), pp->cur(u, r.parity), F_in);
+                E.check_launch("hq_upsample", (double)r.B * 4.0 * 3 * F_in * 128);
+            });
+            Ten* en_in = hq_conv_op(P, blk + "_in", u, nullptr, blk + "_in");
+            y = hq_msfe(P, blk, DEC_N[i], en_in, enc_des[j], nullptr);
+        }
+        P.ops.push_back([=](Engine& E, const Run& r) {
+            E.cur_op = "out_conv";
+            const long long npix = (long long)r.B * 256;
+            out_conv_kernel<<<(int)((npix * 16 + 255) / 256), 256, 0, r.st>>>(pp->cur(y, r.parity), E.pool.at(E.out_layer.w), E.pool.at(E.out_layer.b),
+                                                                             r.est_out, npix, 256, r.est_stride, r.est_off);
+            E.check_launch("out_conv", npix * 4.0 * 65);
+        });
+    }
+
     void alloc_plan(Plan& P, int cap, bool streaming) {
         P.streaming = streaming;
-        P.sh16 = use_tc && (!streaming || stream_tc3);
+        P.sh16 = use_tc && (!streaming || stream_tc3) && !is_hybrid();
         P.cap = cap;
-        build_plan(P);
+        if (is_hybrid()) {
+            if (!streaming) fail(NUNET_EINVAL, "the int8-hybrid variant is the deployed ONE-FRAME graph: streaming entry points only (max_frames must be 0)");
+            build_hybrid_plan(P);
+        } else {
+            build_plan(P);
+        }
         if (streaming) {
             s_mag = P.make("", 1, 256, true, false);
             s_ph = P.make("", 1, 2 * NBINS, true, false);

@@ -106,7 +106,11 @@ class Interpreter:
     baseline with signature key 'nutls' (interpreter_nunet_tls.py:543-549); a role-named weight set goes in `weights=`."""
 
     def __init__(self, model_path: Optional[str] = None, weights: Optional[dict] = None, device: int = 0,
-                 num_threads: Optional[int] = None, variant: Optional[str] = None):
+                 num_threads: Optional[int] = None, variant: Optional[str] = None, arithmetic: str = "float"):
+        """arithmetic="float": float32 on the (dequantised) weights -- the graph as trained (default).
+        arithmetic="int8-hybrid" (LSTM variant): what the TFLite runtime actually computes on the reference's shipped
+        dynamic-range-quantised file: int8 weights, per-call int8 quantisation of every hybrid operator's input, int32
+        accumulation (engine variant NUNET_VARIANT_LSTM_HYBRID)."""
         if variant is None:
             variant = "ddb" if (model_path or "").endswith("nutls.tflite") else "lstm"
         self._ddb = variant == "ddb"
@@ -120,7 +124,17 @@ class Interpreter:
             else:
                 weights = lstm_weights_from_h5(model_path)
         validate(weights, expected_ddb_shapes() if self._ddb else expected_lstm_shapes())
-        self._blob = pack_blob(weights, VARIANT_DDB if self._ddb else 0)
+        if arithmetic not in ("float", "int8-hybrid"):
+            raise ValueError("arithmetic must be 'float' or 'int8-hybrid'")
+        self._hybrid = arithmetic == "int8-hybrid"
+        if self._hybrid:
+            if self._ddb:
+                raise ValueError("int8-hybrid arithmetic is implemented for the NUNet-TLS-LSTM graph")
+            from .tflite_export import hybrid_weight_set
+            from .weights import VARIANT_LSTM_HYBRID
+            self._blob = pack_blob(hybrid_weight_set(weights), VARIANT_LSTM_HYBRID)
+        else:
+            self._blob = pack_blob(weights, VARIANT_DDB if self._ddb else 0)
         self._device = device
         self._engine: Optional[NunetEngine] = None
         self._cached_runner: Optional[SignatureRunner] = None
@@ -128,8 +142,10 @@ class Interpreter:
 
     def allocate_tensors(self):
         if self._engine is None:
+            from ._lib import NUNET_VARIANT_LSTM_HYBRID
             self._engine = NunetEngine(self._blob, max_streams=1, device=self._device, dc_mode="edge",
-                                       variant=NUNET_VARIANT_DDB if self._ddb else NUNET_VARIANT_LSTM)
+                                       variant=NUNET_VARIANT_LSTM_HYBRID if self._hybrid
+                                       else (NUNET_VARIANT_DDB if self._ddb else NUNET_VARIANT_LSTM))
             self._engine.stream_reset()
 
     def _runner(self) -> SignatureRunner:

@@ -137,3 +137,26 @@ def ensure_skeleton() -> str:
     if not os.path.exists(SKELETON_LSTM) and os.path.exists(REFERENCE_TFLITE_LSTM):
         build_skeleton()
     return SKELETON_LSTM
+
+
+def hybrid_weight_set(weights: Dict[str, np.ndarray], skeleton: str = SKELETON_LSTM) -> Dict[str, np.ndarray]:
+    """The weight set of the DEPLOYED arithmetic (engine variant NUNET_VARIANT_LSTM_HYBRID): every tensor that is int8 in the
+    reference's graph is quantised exactly as the exporter writes it, and goes into the set three times -- `<key>` dequantised
+    (q * scale; what float operators such as the transpose convolution see after DEQUANTIZE), `<key>_q` the int8 values in the
+    TFLite layout ([Cout,kh,kw,Cin] / [out,in]; stored as exact floats) and `<key>_scale` (per output channel for convolutions,
+    one value for fully-connected kernels).  Float tensors are passed through.  Quantising the reference's float checkpoint
+    this way gives precisely the int8 tensors of the reference's shipped nutls_lstm.tflite."""
+    if not os.path.exists(skeleton):
+        raise FileNotFoundError(f"{skeleton} missing (made by tflite_export.build_skeleton from the reference's shipped graph)")
+    from .weights import _to_keras_layout
+    out: Dict[str, np.ndarray] = {k: np.asarray(v, np.float32) for k, v in weights.items()}
+    for t, key, kind, _boff, _bn, _soff, sn in _layout(gzip.open(skeleton, "rb").read()):
+        if t.dtype != np.int8 or key not in weights:
+            continue
+        w = _from_keras_layout(weights[key], kind, t.shape)
+        q, scale = quantize_symmetric(w, per_channel=sn > 1)
+        deq = q.astype(np.float32) * (scale.reshape((-1,) + (1,) * (q.ndim - 1)) if sn > 1 else scale[0])
+        out[key] = _to_keras_layout(deq.astype(np.float32), kind)
+        out[key + "_q"] = q.astype(np.float32)
+        out[key + "_scale"] = scale.astype(np.float32)
+    return out

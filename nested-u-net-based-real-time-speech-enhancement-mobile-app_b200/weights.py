@@ -23,6 +23,7 @@ from .h5_reader import read_h5
 MAGIC = b"NUNETW01"
 VARIANT_LSTM = 0
 VARIANT_DDB = 1
+VARIANT_LSTM_HYBRID = 2     # NUNet-TLS-LSTM with the deployed int8 dynamic-range arithmetic (tflite_export.hybrid_weight_set)
 _ENTRY = struct.Struct("<64sI4IQ4x")  # name, ndim, dims[4], offset (floats), pad -> 96 bytes
 assert _ENTRY.size == 96
 
