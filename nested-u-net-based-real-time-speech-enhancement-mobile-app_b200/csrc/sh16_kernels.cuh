@@ -220,23 +220,12 @@ __global__ void __launch_bounds__(256) ctfa_gate_warp_kernel(const float* __rest
             const int t = (int)(frame % T);
             const float* hrow = hist ? hist + ((frame / T) * (CTFA_WINDOW - 1) + (CTFA_WINDOW - 1)) * 64 : nullptr;   // row of frame "t = 0"
             const int n = min((hist ? t0 : 0) + t + 1, CTFA_WINDOW);
-            // all (up to) 32 rows are fetched before the first add -- one memory round trip instead of 32 -- and summed
-            // oldest first, the order of the reference's pooling window
-            float r0[CTFA_WINDOW], r1[CTFA_WINDOW];
-#pragma unroll
-            for (int d = 0; d < CTFA_WINDOW; ++d) {
-                const bool in = d < n;
-                const float* src = (d <= t) ? ta + (frame - d) * 64 : hrow + (long long)(t - d) * 64;
-                r0[d] = in ? src[lane] : 0.0f;
-                r1[d] = in ? src[32 + lane] : 0.0f;
-            }
+            // oldest row first: the order of the reference's pooling window (and of the streaming ring)
             float s0 = 0.0f, s1 = 0.0f;
-#pragma unroll
-            for (int d = CTFA_WINDOW - 1; d >= 0; --d) {
-                if (d < n) {
-                    s0 += r0[d];
-                    s1 += r1[d];
-                }
+            for (int d = n - 1; d >= 0; --d) {
+                const float* src = (d <= t) ? ta + (frame - d) * 64 : hrow + (long long)(t - d) * 64;
+                s0 += src[lane];
+                s1 += src[32 + lane];
             }
             a0 = s0 * (1.0f / CTFA_WINDOW);
             a1 = s1 * (1.0f / CTFA_WINDOW);
