@@ -624,7 +624,15 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
         const float rcpP = 1.0f / (float)p.P, rcpTp = 1.0f / (float)Tp;
         long long tl_table = 0, tl_wait = 0, tl_fence = 0, tl_issue = 0;   // per-role cycle counters (Tc3Params::timing)
         const long long tl_begin = clock64();
-        asm volatile("griddepcontrol.wait;" ::: "memory");   // our sources are the previous kernels' outputs
+        // Our sources are the previous kernels' outputs: wait for them (programmatic dependent launch) -- but only right before
+        // the first copy, so that the slot table of the first tile is built while the previous kernel drains.
+        bool dep_waited = false;
+        auto dep_wait = [&]() {
+            if (!dep_waited) {
+                asm volatile("griddepcontrol.wait;" ::: "memory");
+                dep_waited = true;
+            }
+        };
         int buf = 0, round = 0;        // ring position of phase g and the parity of its use count
         int g = 0;
         for (int it = 0; it < my_tiles; ++it) {
@@ -636,6 +644,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
                 const int peer_box = PAIR ? t3_tile_geo(tile_q(it, half ^ 1) - p.lead, p.P, Tp, p.padrow, p.slots,
                                                           max(p.tm_delta[0], p.tm_delta[1]), p.tm_dmin, p.prev_rows).box : 1;
                 if (tg.box && peer_box) {
+                    dep_wait();
                     // one box per image into this warp's plane; 32 arrivals per warp keep the barrier count of the fallback
                     for (int ph = 0; ph < p.nphase; ++ph, ++g) {
                         const long long tl1 = clock64();
@@ -731,6 +740,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
                 }
             }
             tl_table += clock64() - tl0;
+            dep_wait();
             for (int ph = 0; ph < p.nphase; ++ph, ++g) {
                 const long long tl1 = clock64();
                 if (g >= NB) mbar_wait_relaxed(&a_empty[buf], round ^ 1);

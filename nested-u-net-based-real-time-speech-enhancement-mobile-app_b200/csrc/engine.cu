@@ -34,6 +34,7 @@
 #include "lstm_kernels.cuh"
 #include "ddb_kernels.cuh"
 #include "hybrid_kernels.cuh"
+#include "fused_tail.cuh"
 
 namespace nunet {
 
@@ -142,6 +143,7 @@ struct ConvLayer {
     int CA = 0, CB = 0, COUT = 0, KT = 1, KF = 1, padl = 0, stride = 1, epi = EPI_LN;
     // split-half tensor-core path (conv_tc3.cuh): fp16 hi/lo weights, columns in output-channel order
     size_t w3 = 0, b3 = 0;   // float offsets into the pool (w3 holds raw halves)
+    size_t wfz = 0;          // the same scaled hi / lo weights in mma.sync fragment order (fused_tail.cuh)
     int N3 = 0, PC3 = 0, nhalf3 = 1;
     float wscale_inv = 1.0f;
 };
@@ -225,6 +227,49 @@ static std::vector<float> pack_tc3(const std::vector<float>& k, int taps, int Ci
             }
     std::vector<float> raw(out.size() / 2);
     memcpy(raw.data(), out.data(), out.size() * sizeof(__half));
+    return raw;
+}
+
+// logical [taps][Cin][COUT] -> B fragments of mma.sync.m16n8k16 for fused_tail.cuh: [k-step = (tap, 16-channel group)][8-column tile]
+// [lane] x {b_hi k 2q..2q+1, b_hi k 2q+8..9, b_lo same} with n = 8 tile + lane / 4, q = lane % 4; columns in the packed order of
+// tc3_col_to_channel (all COUT columns: the two 64-column halves of a 128-channel unit follow each other); same power-of-two scale
+// as pack_tc3.
+static std::vector<float> pack_fz(const std::vector<float>& k, int taps, int Cin, int COUT, int epi, float scale_inv) {
+    const float scale = 1.0f / scale_inv;
+    const int cgn = Cin / 16, NT = COUT / 8, nhalf = (COUT == 128) ? 2 : 1, Nh = COUT / nhalf;
+    std::vector<uint32_t> out((size_t)taps * cgn * NT * 32 * 4);
+    auto halves = [&](int tap, int ci, int n, __half& hi, __half& lo) {
+        const int co = tc3_col_to_channel(epi, n / Nh, n % Nh);
+        const float w = k[((size_t)tap * Cin + ci) * COUT + co] * scale;
+        hi = __float2half_rn(w);
+        lo = __float2half_rn(w - __half2float(hi));
+    };
+    auto pack2 = [](__half a, __half b) {
+        uint16_t x, y;
+        memcpy(&x, &a, 2);
+        memcpy(&y, &b, 2);
+        return (uint32_t)x | ((uint32_t)y << 16);
+    };
+    // LayerNorm groups (the PC channels of one output pixel) are stored one after the other so that a group -- or a run of
+    // groups -- is one contiguous weight chunk for the kernel's shared-memory staging
+    const int PC = (epi == EPI_SHUF32) ? 32 : (epi == EPI_SHUF64) ? 64 : COUT, NTG = PC / 8;
+    for (int tap = 0; tap < taps; ++tap)
+        for (int cg = 0; cg < cgn; ++cg)
+            for (int nt = 0; nt < NT; ++nt)
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int n = nt * 8 + (lane >> 2), q = lane & 3;
+                    __half h[4], l[4];
+                    const int kk[4] = {2 * q, 2 * q + 1, 2 * q + 8, 2 * q + 9};
+                    for (int i = 0; i < 4; ++i) halves(tap, cg * 16 + kk[i], n, h[i], l[i]);
+                    const int px = nt / NTG, ntl = nt % NTG;
+                    uint32_t* o = &out[(((((size_t)px * taps + tap) * cgn + cg) * NTG + ntl) * 32 + lane) * 4];
+                    o[0] = pack2(h[0], h[1]);
+                    o[1] = pack2(h[2], h[3]);
+                    o[2] = pack2(l[0], l[1]);
+                    o[3] = pack2(l[2], l[3]);
+                }
+    std::vector<float> raw(out.size());
+    memcpy(raw.data(), out.data(), out.size() * 4);
     return raw;
 }
 
@@ -394,6 +439,17 @@ struct Engine {
     std::map<std::string, HqLstmLayer> hlstms;
     std::map<std::string, std::pair<size_t, size_t>> hups;   // up_sampling: dequantised kernel [k][ci][co], bias
     Ten *hq_qbuf = nullptr, *hq_qp = nullptr;
+    // streaming plans: the layers of a nested sub-U-Net that work on <= 32 bins are collected into one fused_tail_kernel launch
+    struct FzGroup {
+        std::vector<std::function<void(Engine&, const Run&, FzLayer&)>> fill;
+        double alg_bytes = 0.0;
+    };
+    std::unique_ptr<FzGroup> fz_open;     // group being collected while the plan is built
+    int fz_dbg = 0;                       // NUNET_FZ_DBG (experiments)
+    int stream_fuse = 0;                  // NUNET_STREAM_FUSE=1 (debug knob): fused_tail_kernel for the <= 32-bin layers.  Off by default:
+                                          // measured at 1 .. 2048 streams it is 0-15 % SLOWER than one conv_tc3 launch per layer (94 vs 174
+                                          // launches per step) -- legacy mma.sync sustains ~290 FMA/clk/SM on B200, 28x below tcgen05, so the
+                                          // fused chain is bound by the tensor path it uses (profiles/r2_fused_tail_*.txt)
     size_t tw_off = 0, win_off = 0, win_stream_off = 0, inv_win_off = 0;
 
     Plan offline, stream;
@@ -498,6 +554,7 @@ struct Engine {
         for (int h = 0; h < L.nhalf3; ++h)
             for (int n = 0; n < L.N3; ++n) b3[(size_t)h * L.N3 + n] = bias[tc3_col_to_channel(L.epi, h, n)];
         L.b3 = pool.add(b3);
+        if (cfg.max_streams > 0 && (L.CA + L.CB) % 16 == 0) L.wfz = pool.add(pack_fz(kv, L.KT * L.KF, L.CA + L.CB, L.COUT, L.epi, L.wscale_inv));
     }
 
     // up_sampling (Conv2DTranspose (1,3) stride (1,2) 'same', models/proposed.py:260) followed by the decoder
@@ -1197,6 +1254,26 @@ struct Engine {
             a_coff = P.want_carry(a);
             if (b) b_coff = P.want_carry(b);
         }
+        if (fz_open) {
+            if (!L.wfz) fail(NUNET_EINVAL, "plan: %s has no fused-kernel weights", role.c_str());
+            fz_open->alg_bytes += 4.0 * ((double)F_in * (L.CA + L.CB) * L.KT + (double)o->numel());
+            fz_open->fill.push_back([=](Engine& E, const Run& r, FzLayer& f) {
+                f.kind = FZ_CONV;
+                f.a_cur = reinterpret_cast<const uint8_t*>(pp->cur(a, r.parity));
+                f.a_prev = reinterpret_cast<const uint8_t*>(pp->prev(a, r.parity));
+                f.b_cur = b ? reinterpret_cast<const uint8_t*>(pp->cur(b, r.parity)) : nullptr;
+                f.b_prev = b ? reinterpret_cast<const uint8_t*>(pp->prev(b, r.parity)) : nullptr;
+                f.out = reinterpret_cast<uint8_t*>(pp->cur(o, r.parity));
+                f.w = reinterpret_cast<const uint4*>(E.pool.at(L.wfz));
+                f.bias = E.pool.at(L.b3); f.gamma = E.pool.at(L.gamma); f.beta = E.pool.at(L.beta); f.alpha = E.pool.at(L.alpha);
+                f.wscale_inv = L.wscale_inv;
+                f.F_in = F_in; f.Ca = L.CA; f.Cb = L.CB; f.F_conv = F_conv; f.N = L.COUT; f.KT = L.KT; f.KF = L.KF; f.padl = L.padl;
+                f.stride = L.stride;
+                f.epi = L.epi == EPI_LN ? FZE_LN : L.epi == EPI_SHUF32 ? FZE_SHUF32 : L.epi == EPI_SHUF64 ? FZE_SHUF64 : FZE_BIAS;
+                f.in_eo = src_eo ? 1 : 0; f.out_eo = dst_eo ? 1 : 0;
+            });
+            return o;
+        }
         P.ops.push_back([=](Engine& E, const Run& r) {
             E.cur_op = out_name;
             if (pp->sh16) {
@@ -1236,6 +1313,19 @@ struct Engine {
         o->sh = P.sh16;
         Plan* pp = &P;
         const size_t hc_off = P.streaming ? 0 : P.carry_alloc(2 * 32);     // offline: h | c carried between time chunks, 32 floats each
+        if (fz_open) {
+            const int xC = x->C;
+            fz_open->alg_bytes += 8.0 * D;
+            fz_open->fill.push_back([=](Engine& E, const Run& r, FzLayer& f) {
+                f.kind = FZ_LSTM;
+                f.a_cur = reinterpret_cast<const uint8_t*>(pp->cur(x, r.parity));
+                f.out = reinterpret_cast<uint8_t*>(pp->cur(o, r.parity));
+                f.wk = E.pool.at(L.wk); f.wr = E.pool.at(L.wr); f.bk = E.pool.at(L.wb); f.wd = E.pool.at(L.dk); f.bd = E.pool.at(L.db);
+                f.h = pp->cur(hst, 0); f.c = pp->cur(cst, 0);
+                f.D = D; f.C = xC;
+            });
+            return o;
+        }
         P.ops.push_back([=](Engine& E, const Run& r) {
             E.cur_op = out_name;
             const long long rows = (long long)r.B * r.T;
@@ -1362,11 +1452,37 @@ struct Engine {
                 s.b = sk;
                 P.states.push_back(s);
             }
+            // streaming: from the first conv whose input has <= 32 bins on, the layers of this sub-U-Net are collected into one
+            // fused_tail_kernel launch (closed below after the last sub-pixel conv that still writes <= 32 bins)
+            if (P.streaming && P.sh16 && stream_fuse && !is_ddb() && !fz_open && cur->F <= 32) fz_open.reset(new FzGroup());
             cur = op_conv(P, blk + "_conv" + std::to_string(k), cur, sk, blk + "_conv" + std::to_string(k), false);
             ens.push_back(cur);
         }
         Ten* bb = is_ddb() ? op_ddb(P, blk + "_ddb", cur, blk + "_bb", false) : op_lstm(P, blk + "_lstm", cur, blk + "_bb", blk, false);
         cur = bb;
+        auto fz_close = [&]() {
+            if (!fz_open) return;
+            std::shared_ptr<FzGroup> grp(fz_open.release());
+            if ((int)grp->fill.size() > FZ_MAXL) fail(NUNET_EINVAL, "plan: %s fuses %zu layers", blk.c_str(), grp->fill.size());
+            Plan* pq = &P;
+            P.ops.push_back([=](Engine& E, const Run& r) {
+                E.cur_op = blk + "_tail";
+                FzParams fp{};
+                fp.nl = (int)grp->fill.size();
+                for (int i = 0; i < fp.nl; ++i) grp->fill[i](E, r, fp.L[i]);
+                fp.S = r.B;
+                fp.dbg = E.fz_dbg;
+                fp.G = std::max(1, (r.B + FZ_CTAS_PER_SM * E.num_sms - 1) / (FZ_CTAS_PER_SM * E.num_sms));
+                (void)pq;
+                static bool attr_set = false;
+                if (!attr_set) {
+                    CUDA_OK(cudaFuncSetAttribute(fused_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FZ_SMEM));
+                    attr_set = true;
+                }
+                fused_tail_kernel<<<(r.B + fp.G - 1) / fp.G, FZ_THREADS, FZ_SMEM, r.st>>>(fp);
+                E.check_launch("fused_tail", (double)r.B * grp->alg_bytes);
+            });
+        };
         std::vector<Ten*> des;
         for (int k = 1; k <= n; ++k) {
             Ten* sk = ens[n - k];
@@ -1377,10 +1493,12 @@ struct Engine {
                 s.b = sk;
                 P.states.push_back(s);
             }
+            if (fz_open && cur->F > 16) fz_close();        // this sub-pixel conv would write more than 32 bins: it runs on its own
             cur = op_conv(P, blk + "_spconv" + std::to_string(k), cur, sk, blk + "_spconv" + std::to_string(k), des_persistent,
                           /*out_eo=*/k == n);
             des.push_back(cur);
         }
+        fz_close();
         if (des_out)
             for (int k = 1; k <= n; ++k) des_out[k - 1] = des[n - k];
         // CTFA + residual
@@ -2223,6 +2341,8 @@ int nunet_create(const nunet_config* cfg, const void* blob, size_t blob_bytes, n
         if (const char* c = knob("NUNET_TC3_PAIR")) E.tc3_pair = atoi(c);
         if (const char* c = knob("NUNET_TC3_ROW_TILES")) E.tc3_row_tiles = atoi(c);
         if (const char* c = knob("NUNET_STREAM_GRAPH")) E.stream_graphs = atoi(c);
+        if (const char* c = knob("NUNET_STREAM_FUSE")) E.stream_fuse = atoi(c);
+        if (const char* c = knob("NUNET_FZ_DBG")) E.fz_dbg = atoi(c);
         if (const char* c = knob("NUNET_STREAM_SPLIT")) E.stream_split = std::max(1, std::min(4, atoi(c)));
         if (const char* c = knob("NUNET_TC3_PAIR_MINF")) E.tc3_pair_minf = atoi(c);
         if (const char* c = knob("NUNET_TC3_BOX_STRIDED")) E.tc3_box_strided = atoi(c);
