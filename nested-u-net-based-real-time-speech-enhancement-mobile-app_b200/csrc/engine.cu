@@ -35,6 +35,7 @@
 #include "ddb_kernels.cuh"
 #include "hybrid_kernels.cuh"
 #include "fused_tail.cuh"
+#include "ddb_fused.cuh"
 
 namespace nunet {
 
@@ -1380,58 +1381,114 @@ struct Engine {
         }
         Plan* pp = &P;
         const bool sh = P.sh16;
+        // offline: history of a time chunk -- 32 frames of out_0..out_5, one row of the block input (fp32) and of out_6, per clip
+        size_t hist_off[8] = {};
+        if (!P.streaming) {
+            for (int i = 0; i < 6; ++i) hist_off[i] = P.carry_alloc((size_t)DDB_HIST * F * h);
+            hist_off[6] = P.carry_alloc((size_t)F * C);
+            hist_off[7] = P.carry_alloc((size_t)F * h);
+        }
         P.ops.push_back([=](Engine& E, const Run& r) {
             E.cur_op = out_name;
-            if (r.use_carry || r.save_carry)
-                fail(NUNET_EINVAL, "time chunking is not available for the dilated-dense variant: a clip must fit max_frames (T <= %d)", pp->cap);
             const long long units = (long long)r.B * r.T;
-            const long long nin = units * F * h;
-            DdbGeom g{pp->streaming ? 1 : 0, r.step & (DDB_RING - 1), r.T};
-            float* m[7];
-            for (int i = 0; i < 6; ++i) m[i] = pp->cur(mid[i], 0);
-            m[6] = pp->cur(mid[6], r.parity);
-            const void* xin = pp->cur(x, r.parity);
-            const void* xprev = pp->prev(x, r.parity);
-            {
-                const int blocks = (int)((units * F + 31) / 32);
-                const size_t smem = (size_t)(6 * C * h + 6 * C * 32) * sizeof(float);
-                auto go = [&](auto kfn) {
-                    CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
-                    kfn<<<blocks, 128, smem, r.st>>>(xin, xprev, E.pool.at(L.w_in), E.pool.at(L.b_in), E.pool.at(L.a_in), m[0], units, g, F);
-                };
-                if (C == 64) { if (sh) go(ddb_conv23_kernel<64, 32, true, false, true>); else go(ddb_conv23_kernel<64, 32, true, false, false>); }
-                else { if (sh) go(ddb_conv23_kernel<32, 16, true, false, true>); else go(ddb_conv23_kernel<32, 16, true, false, false>); }
+            const bool chunked = !pp->streaming && (r.use_carry || r.save_carry);
+            if (chunked && !pp->carry) fail(NUNET_EINVAL, "time chunking needs the carry arena");
+            if (!pp->streaming && !chunked) {
+                // Whole clips offline: one launch per layer (in, six dilated layers, out).  Measured at 256 clips x 249 frames the
+                // one-CTA-per-clip kernel below takes 12.4 ms per step against 8.8 ms for these eight grid-wide launches per block:
+                // a clip's 996 pixels are too few threads to hide the L2 latency of the dense block's gather.  The fused kernel
+                // serves streaming (13 instead of 104 launches per step) and time-chunked calls (it reads the carried history);
+                // both paths evaluate every output with the same operation sequence (bit-identical, tests/test_gpu_chunking.py).
+                const long long nin = units * F * h;
+                DdbGeom g{pp->streaming ? 1 : 0, r.step & (DDB_RING - 1), r.T};
+                float* m[7];
+                for (int i = 0; i < 6; ++i) m[i] = pp->cur(mid[i], 0);
+                m[6] = pp->cur(mid[6], r.parity);
+                const void* xin = pp->cur(x, r.parity);
+                const void* xprev = pp->prev(x, r.parity);
+                {
+                    const int blocks = (int)((units * F + 31) / 32);
+                    const size_t smem = (size_t)(6 * C * h + 6 * C * 32) * sizeof(float);
+                    auto go = [&](auto kfn) {
+                        CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+                        kfn<<<blocks, 128, smem, r.st>>>(xin, xprev, E.pool.at(L.w_in), E.pool.at(L.b_in), E.pool.at(L.a_in), m[0], units, g, F);
+                    };
+                    if (C == 64) { if (sh) go(ddb_conv23_kernel<64, 32, true, false, true>); else go(ddb_conv23_kernel<64, 32, true, false, false>); }
+                    else { if (sh) go(ddb_conv23_kernel<32, 16, true, false, true>); else go(ddb_conv23_kernel<32, 16, true, false, false>); }
+                }
+                E.check_launch("ddb_in", units * 4.0 * F * (C + h));
+                DdbOuts src{};
+                for (int i = 0; i < 6; ++i) src.o[i] = m[i];
+                for (int k = 1; k <= 6; ++k) {
+                    const int d = 1 << (k - 1);
+                    const int blocks = (int)((nin + 127) / 128);
+                    const int ring_out = (pp->streaming && k < 6) ? 1 : 0;
+                    if (h == 16)
+                        ddb_layer_kernel<16><<<blocks, 128, 0, r.st>>>(src, k, d, E.pool.at(L.w0[k - 1]), E.pool.at(L.b0[k - 1]), E.pool.at(L.w1[k - 1]),
+                                                                      E.pool.at(L.b1[k - 1]), E.pool.at(L.gamma[k - 1]), E.pool.at(L.beta[k - 1]),
+                                                                      E.pool.at(L.alpha[k - 1]), m[k], ring_out, units, g, F);
+                    else
+                        ddb_layer_kernel<32><<<blocks, 128, 0, r.st>>>(src, k, d, E.pool.at(L.w0[k - 1]), E.pool.at(L.b0[k - 1]), E.pool.at(L.w1[k - 1]),
+                                                                      E.pool.at(L.b1[k - 1]), E.pool.at(L.gamma[k - 1]), E.pool.at(L.beta[k - 1]),
+                                                                      E.pool.at(L.alpha[k - 1]), m[k], ring_out, units, g, F);
+                    E.check_launch("ddb_layer", units * 4.0 * F * h * (k + 1));
+                }
+                void* yo = pp->cur(o, r.parity);
+                const float* o6prev = pp->prev(mid[6], r.parity);
+                {
+                    const int blocks = (int)((units * F + 31) / 32);
+                    const size_t smem = (size_t)(6 * h * C + 6 * h * 32) * sizeof(float);
+                    auto go = [&](auto kfn) {
+                        CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+                        kfn<<<blocks, 128, smem, r.st>>>(m[6], o6prev, E.pool.at(L.w_out), E.pool.at(L.b_out), E.pool.at(L.a_out), yo, units, g, F);
+                    };
+                    if (C == 64) { if (sh) go(ddb_conv23_kernel<32, 64, false, true, true>); else go(ddb_conv23_kernel<32, 64, false, true, false>); }
+                    else { if (sh) go(ddb_conv23_kernel<16, 32, false, true, true>); else go(ddb_conv23_kernel<16, 32, false, true, false>); }
+                }
+                E.check_launch("ddb_out", units * 4.0 * F * (C + h));
+                return;
             }
-            E.check_launch("ddb_in", units * 4.0 * F * (C + h));
-            DdbOuts src{};
-            for (int i = 0; i < 6; ++i) src.o[i] = m[i];
-            for (int k = 1; k <= 6; ++k) {
-                const int d = 1 << (k - 1);
-                const int blocks = (int)((nin + 127) / 128);
-                const int ring_out = (pp->streaming && k < 6) ? 1 : 0;
-                if (h == 16)
-                    ddb_layer_kernel<16><<<blocks, 128, 0, r.st>>>(src, k, d, E.pool.at(L.w0[k - 1]), E.pool.at(L.b0[k - 1]), E.pool.at(L.w1[k - 1]),
-                                                                  E.pool.at(L.b1[k - 1]), E.pool.at(L.gamma[k - 1]), E.pool.at(L.beta[k - 1]),
-                                                                  E.pool.at(L.alpha[k - 1]), m[k], ring_out, units, g, F);
-                else
-                    ddb_layer_kernel<32><<<blocks, 128, 0, r.st>>>(src, k, d, E.pool.at(L.w0[k - 1]), E.pool.at(L.b0[k - 1]), E.pool.at(L.w1[k - 1]),
-                                                                  E.pool.at(L.b1[k - 1]), E.pool.at(L.gamma[k - 1]), E.pool.at(L.beta[k - 1]),
-                                                                  E.pool.at(L.alpha[k - 1]), m[k], ring_out, units, g, F);
-                E.check_launch("ddb_layer", units * 4.0 * F * h * (k + 1));
+            DdbFused f{};
+            f.g = DdbGeom{pp->streaming ? 1 : 0, r.step & (DDB_RING - 1), r.T};
+            f.x = pp->cur(x, r.parity);
+            f.x_prev = pp->prev(x, r.parity);
+            f.y = pp->cur(o, r.parity);
+            for (int i = 0; i < 6; ++i) f.mid[i] = pp->cur(mid[i], 0);
+            f.mid[6] = pp->cur(mid[6], r.parity);
+            f.mid6_prev = pp->prev(mid[6], r.parity);
+            if (!pp->streaming && r.use_carry) {
+                for (int i = 0; i < 6; ++i) f.hist_mid[i] = pp->carry_at(hist_off[i]);
+                f.hist_x = pp->carry_at(hist_off[6]);
+                f.hist_mid6 = pp->carry_at(hist_off[7]);
             }
-            void* yo = pp->cur(o, r.parity);
-            const float* o6prev = pp->prev(mid[6], r.parity);
-            {
-                const int blocks = (int)((units * F + 31) / 32);
-                const size_t smem = (size_t)(6 * h * C + 6 * h * 32) * sizeof(float);
-                auto go = [&](auto kfn) {
-                    CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
-                    kfn<<<blocks, 128, smem, r.st>>>(m[6], o6prev, E.pool.at(L.w_out), E.pool.at(L.b_out), E.pool.at(L.a_out), yo, units, g, F);
-                };
-                if (C == 64) { if (sh) go(ddb_conv23_kernel<32, 64, false, true, true>); else go(ddb_conv23_kernel<32, 64, false, true, false>); }
-                else { if (sh) go(ddb_conv23_kernel<16, 32, false, true, true>); else go(ddb_conv23_kernel<16, 32, false, true, false>); }
+            f.w_in = E.pool.at(L.w_in); f.b_in = E.pool.at(L.b_in); f.a_in = E.pool.at(L.a_in);
+            f.w_out = E.pool.at(L.w_out); f.b_out = E.pool.at(L.b_out); f.a_out = E.pool.at(L.a_out);
+            for (int k = 0; k < 6; ++k) {
+                f.w0[k] = E.pool.at(L.w0[k]); f.b0[k] = E.pool.at(L.b0[k]); f.w1[k] = E.pool.at(L.w1[k]); f.b1[k] = E.pool.at(L.b1[k]);
+                f.gamma[k] = E.pool.at(L.gamma[k]); f.beta[k] = E.pool.at(L.beta[k]); f.alpha[k] = E.pool.at(L.alpha[k]);
             }
-            E.check_launch("ddb_out", units * 4.0 * F * (C + h));
+            f.F = F;
+            f.units = units;
+            f.units_per_cta = pp->streaming ? 8 : r.T;          // one clip per CTA offline (its layers depend only on its own frames)
+            const int grid = (int)((units + f.units_per_cta - 1) / f.units_per_cta);
+            const int NG = (C == 32) ? 4 : 2;
+            const size_t smem = (size_t)(6 * C * h + NG * 6 * C * 32) * sizeof(float);
+            auto go = [&](auto kfn) {
+                CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+                kfn<<<grid, DDBF_THREADS, smem, r.st>>>(f);
+            };
+            if (C == 64) { if (sh) go(ddb_block_kernel<64, true>); else go(ddb_block_kernel<64, false>); }
+            else { if (sh) go(ddb_block_kernel<32, true>); else go(ddb_block_kernel<32, false>); }
+            E.check_launch("ddb_block", units * 4.0 * F * (2.0 * C + 2.0 * h * 7 + 21.0 * h));
+            if (!pp->streaming && r.save_carry) {
+                DdbHistW hw{};
+                for (int i = 0; i < 6; ++i) hw.mid[i] = pp->carry_at(hist_off[i]);
+                hw.x = pp->carry_at(hist_off[6]);
+                hw.mid6 = pp->carry_at(hist_off[7]);
+                if (sh) ddb_hist_update_kernel<true><<<dim3(r.B, 7), 256, 0, r.st>>>(f, hw, C, r.use_carry ? 1 : 0);
+                else ddb_hist_update_kernel<false><<<dim3(r.B, 7), 256, 0, r.st>>>(f, hw, C, r.use_carry ? 1 : 0);
+                E.check_launch("ddb_hist", 0.0);
+            }
         });
         return o;
     }

@@ -112,17 +112,22 @@ def test_8192_clips_on_one_gpu(blob):
     assert torch.equal(y[:16], y[-16:]) and torch.equal(y[:16], y[4000:4016])
 
 
-def test_ddb_variant_sub_batches_but_refuses_time_chunks(ddb_weights):
-    from nunet_b200._lib import NUNET_VARIANT_DDB, NunetError
+def test_ddb_variant_sub_batches_and_time_chunks(ddb_weights):
+    """Dilated-dense variant: sub-batches of whole clips, and time chunks whose history is the last 32 frames of every dilated
+    layer's input (the deepest dilation) plus one row for the two causal (2,3) convs of each block -- bit-identical to one pass.
+    Chunks of 5 and 20 frames are shorter than that history, 48 longer."""
+    from nunet_b200._lib import NUNET_VARIANT_DDB
     from nunet_b200.engine import NunetEngine
     from nunet_b200.synth import synth_clips
     from nunet_b200.weights import VARIANT_DDB, pack_blob
     blob = pack_blob(ddb_weights, VARIANT_DDB)
-    B, T = 4, 50
+    B, T = 4, 100
     wav = torch.from_numpy(synth_clips(B, 512 + 256 * (T - 1), first_clip=600)).cuda()
     y0, e0 = NunetEngine(blob, max_frames=B * T, variant=NUNET_VARIANT_DDB).forward_wav(wav)
     y1, e1 = NunetEngine(blob, max_frames=T + 3, variant=NUNET_VARIANT_DDB).forward_wav(wav)     # one clip per sub-batch
     assert torch.equal(e0, e1) and torch.equal(y0, y1)
-    with pytest.raises(NunetError) as ei:
-        NunetEngine(blob, max_frames=T - 1, variant=NUNET_VARIANT_DDB).forward_wav(wav)
-    assert "dilated-dense" in str(ei.value)
+    for chunk in (5, 20, 48):
+        y2, e2 = NunetEngine(blob, max_frames=B * T, variant=NUNET_VARIANT_DDB, chunk_frames=chunk).forward_wav(wav)
+        assert torch.equal(e0, e2) and torch.equal(y0, y2), chunk
+    y3, e3 = NunetEngine(blob, max_frames=64, variant=NUNET_VARIANT_DDB).forward_wav(wav)        # clip longer than the arena
+    assert torch.equal(e0, e3) and torch.equal(y0, y3)
