@@ -875,11 +875,11 @@ struct Engine {
 
     template <int COUT, int CN, int PM, int NT, int EPI>
     void launch_conv_t(const ConvParams& p, int grid, size_t smem, cudaStream_t st) {
-        static bool attr_set = false;
+        static unsigned long long attr_set = 0;     // bit d: attribute set on device d (function attributes are per device)
         auto kfn = conv_unit_kernel<COUT, CN, PM, NT, EPI>;
-        if (!attr_set) {
+        if (!((attr_set >> cfg.device) & 1ull)) {
             CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-            attr_set = true;
+            attr_set |= 1ull << cfg.device;
         }
         kfn<<<grid, NT, smem, st>>>(p);
         const double frames = (double)p.B * p.T;
@@ -941,11 +941,11 @@ struct Engine {
 
     template <int N, int PC, bool LN, bool PAIR = false>
     void launch_tc3_t(const Tc3Params& p, int grid, size_t smem, cudaStream_t st) {
-        static bool attr_set = false;
+        static unsigned long long attr_set = 0;     // bit d: attribute set on device d (function attributes are per device)
         auto kfn = conv_tc3_kernel<N, PC, LN, PAIR>;
-        if (!attr_set) {
+        if (!((attr_set >> cfg.device) & 1ull)) {
             CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            attr_set = true;
+            attr_set |= 1ull << cfg.device;
         }
         cudaLaunchConfig_t lc{};
         lc.gridDim = dim3((unsigned)grid);
@@ -1531,10 +1531,10 @@ struct Engine {
                 fp.dbg = E.fz_dbg;
                 fp.G = std::max(1, (r.B + FZ_CTAS_PER_SM * E.num_sms - 1) / (FZ_CTAS_PER_SM * E.num_sms));
                 (void)pq;
-                static bool attr_set = false;
-                if (!attr_set) {
+                static unsigned long long attr_set = 0;
+                if (!((attr_set >> E.cfg.device) & 1ull)) {
                     CUDA_OK(cudaFuncSetAttribute(fused_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FZ_SMEM));
-                    attr_set = true;
+                    attr_set |= 1ull << E.cfg.device;
                 }
                 fused_tail_kernel<<<(r.B + fp.G - 1) / fp.G, FZ_THREADS, FZ_SMEM, r.st>>>(fp);
                 E.check_launch("fused_tail", (double)r.B * grp->alg_bytes);
