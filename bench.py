@@ -59,6 +59,15 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_tensor_peak():
+    """sustained dense bf16 / fp16 TFLOP/s (the step is long: the sustained figure applies)"""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j.get("bf16_tflops_sustained", j.get("bf16_tflops", 1410.0))), "measured (MEASURED_PEAKS.json, sustained)"
+    return 1410.0, "fallback (B200_PROFILING.md)"
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
 
@@ -235,6 +244,11 @@ def offline_record(ctx: Ctx, blob: bytes, variant: str, B: int, n_samples: int, 
                     "unit": "GB/s", "frac": path_gbs / peak, "traffic": traffic, "traffic_source": traffic_src,
                     "peak_source": peak_src, "b_alg_bytes_per_frame": b_alg, "algorithmic_bytes": b_alg * B * T,
                     "fp32_equiv_tflops": value / ctx.world * FLOP_PER_FRAME[variant] / 1e12}
+        # second roofline of the path: fp32-grade results cost three fp16 tensor products per multiply-add
+        tpeak, tsrc = measured_tensor_peak()
+        t3 = 3.0 * value / ctx.world * FLOP_PER_FRAME[variant] / 1e12
+        roofline["tensor_3product"] = {"bound": "tensor", "achieved": t3, "peak": tpeak, "unit": "TFLOP/s", "frac": t3 / tpeak, "peak_source": tsrc,
+                                       "note": "issued fp16 tensor FLOP/s = 3 x the model's FLOPs (split-half hi/lo products)"}
         if profile:
             # per-launch CUDA events (one extra step) -> the launch with the largest share of the step
             eng.profile(True)
