@@ -179,83 +179,6 @@ __global__ void __launch_bounds__(256) gate_residual_kernel(const float4* __rest
     }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// Small dense: Y[r][n] = b[n] + sum_k X[r][k] W[k][n].  Used for the LSTM input projection
-// (K = F_b*C, N = 84) and the Dense after the LSTM (K = 21, N = F_b*C)  (models/proposed.py:305-309).
-constexpr int DENSE_RB = 16;
-__global__ void __launch_bounds__(128) dense_rows_kernel(const float* __restrict__ X, const float* __restrict__ W,
-                                                        const float* __restrict__ bias, float* __restrict__ Y,
-                                                        long long rows, int K, int N) {
-    extern __shared__ float xs[];   // [DENSE_RB][K]
-    const long long r0 = (long long)blockIdx.x * DENSE_RB;
-    const int nr = (int)min((long long)DENSE_RB, rows - r0);
-    for (int i = threadIdx.x; i < DENSE_RB * K; i += blockDim.x) {
-        const int r = i / K;
-        xs[i] = (r < nr) ? __ldg(X + r0 * K + i) : 0.0f;
-    }
-    __syncthreads();
-    for (int n = threadIdx.x; n < N; n += blockDim.x) {
-        float acc[DENSE_RB];
-        const float bv = __ldg(bias + n);
-#pragma unroll
-        for (int r = 0; r < DENSE_RB; ++r) acc[r] = bv;
-        for (int k = 0; k < K; ++k) {
-            const float wv = __ldg(W + (size_t)k * N + n);
-#pragma unroll
-            for (int r = 0; r < DENSE_RB; ++r) acc[r] = fmaf(xs[r * K + k], wv, acc[r]);
-        }
-        for (int r = 0; r < nr; ++r) Y[(r0 + r) * N + n] = acc[r];
-    }
-}
-
-// LSTM(21, return_sequences=True) recurrence, Keras gate order i, f, c, o (models/proposed.py:26-63).
-// One CTA (96 threads, 84 active gate lanes) per clip / stream.  xw = x.kernel + bias precomputed.
-// h0/c0: carried state [B][21] (streaming: read and overwritten; offline: nullptr = zeros).
-__global__ void __launch_bounds__(96) lstm_recur_kernel(const float* __restrict__ xw,   // [B][T][84]
-                                                       const float* __restrict__ Wr,   // [21][84]
-                                                       float* __restrict__ h_state, float* __restrict__ c_state,
-                                                       float* __restrict__ hs,          // [B][T][21]
-                                                       int T) {
-    __shared__ float h_s[LSTM_UNITS + 3];
-    __shared__ float z_s[LSTM_GATES];
-    const int b = blockIdx.x;
-    const int j = threadIdx.x;
-    float wr[LSTM_UNITS];
-#pragma unroll
-    for (int k = 0; k < LSTM_UNITS; ++k) wr[k] = (j < LSTM_GATES) ? __ldg(Wr + k * LSTM_GATES + j) : 0.0f;
-    float c = 0.0f;
-    if (j < LSTM_UNITS) {
-        h_s[j] = h_state ? h_state[b * LSTM_UNITS + j] : 0.0f;
-        c = c_state ? c_state[b * LSTM_UNITS + j] : 0.0f;
-    }
-    const float* xb = xw + (size_t)b * T * LSTM_GATES;
-    float* hb = hs + (size_t)b * T * LSTM_UNITS;
-    float xnext = (j < LSTM_GATES) ? __ldg(xb + j) : 0.0f;
-    __syncthreads();
-    float hlast = 0.0f;
-    for (int t = 0; t < T; ++t) {
-        float z = xnext;
-        if (t + 1 < T && j < LSTM_GATES) xnext = __ldg(xb + (size_t)(t + 1) * LSTM_GATES + j);
-#pragma unroll
-        for (int k = 0; k < LSTM_UNITS; ++k) z = fmaf(h_s[k], wr[k], z);
-        if (j < LSTM_GATES) z_s[j] = z;
-        __syncthreads();
-        if (j < LSTM_UNITS) {
-            const float gi = sigmoidf_(z_s[j]);
-            const float gf = sigmoidf_(z_s[LSTM_UNITS + j]);
-            const float gc = tanhf(z_s[2 * LSTM_UNITS + j]);
-            const float go = sigmoidf_(z_s[3 * LSTM_UNITS + j]);
-            c = fmaf(gf, c, gi * gc);
-            hlast = go * tanhf(c);
-            h_s[j] = hlast;
-            hb[(size_t)t * LSTM_UNITS + j] = hlast;
-        }
-        __syncthreads();
-    }
-    if (j < LSTM_UNITS && h_state) {
-        h_state[b * LSTM_UNITS + j] = hlast;
-        c_state[b * LSTM_UNITS + j] = c;
-    }
-}
+// (the LSTM bottleneck -- input projection, recurrence, Dense -- lives in lstm_kernels.cuh)
 
 }  // namespace nunet

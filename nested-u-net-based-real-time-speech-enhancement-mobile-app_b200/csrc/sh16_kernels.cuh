@@ -327,63 +327,6 @@ __device__ __forceinline__ int sh16_half_index(int F, int C, int part, int f, in
     return (((part * (C >> 3) + (c >> 3)) * F + f) << 3) + (c & 7);
 }
 
-// Small dense Y[r][n] = b[n] + sum_k X[r][k] W[k][n] (LSTM input projection / Dense after the LSTM,
-// models/proposed.py:305-309) where X and / or Y rows are sh16 frame rows [F_b][C] with k (or n) = f*C + c.
-template <bool IN_SH, bool OUT_SH>
-__global__ void __launch_bounds__(128) dense_rows_sh_kernel(const void* __restrict__ Xv, const float* __restrict__ W,
-                                                           const float* __restrict__ bias, void* __restrict__ Yv, long long rows,
-                                                           int K, int N, int C /*channels per sh16 pixel*/) {
-    extern __shared__ float xs[];   // [DENSE_RB][K]
-    const long long r0 = (long long)blockIdx.x * DENSE_RB;
-    const int nr = (int)min((long long)DENSE_RB, rows - r0);
-    if (IN_SH) {
-        const uint8_t* X = reinterpret_cast<const uint8_t*>(Xv);
-        const int F = K / C, K8 = K >> 3, C8 = C >> 3;
-        for (int i = threadIdx.x; i < DENSE_RB * K8; i += blockDim.x) {      // item = 8 channels of one bin
-            const int r = i / K8, k8 = i - r * K8;
-            const int f = k8 / C8, c8 = k8 - f * C8;
-            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (r < nr) sh16_load8(X + (r0 + r) * (long long)K * 4, F, C, f, c8, v);
-            float4* dst = reinterpret_cast<float4*>(xs + r * K + f * C + c8 * 8);
-            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-        }
-    } else {
-        const float* X = reinterpret_cast<const float*>(Xv);
-        for (int i = threadIdx.x; i < DENSE_RB * K; i += blockDim.x) {
-            const int r = i / K;
-            xs[i] = (r < nr) ? __ldg(X + r0 * K + i) : 0.0f;
-        }
-    }
-    __syncthreads();
-    for (int n = threadIdx.x; n < N; n += blockDim.x) {
-        float acc[DENSE_RB];
-        const float bv = __ldg(bias + n);
-#pragma unroll
-        for (int r = 0; r < DENSE_RB; ++r) acc[r] = bv;
-        for (int k = 0; k < K; ++k) {
-            const float wv = __ldg(W + (size_t)k * N + n);
-#pragma unroll
-            for (int r = 0; r < DENSE_RB; ++r) acc[r] = fmaf(xs[r * K + k], wv, acc[r]);
-        }
-        if (OUT_SH) {
-            __half* Y = reinterpret_cast<__half*>(Yv);
-            const int F = N / C;
-            const int f = n / C, c = n - f * C;
-            const int ih = sh16_half_index(F, C, 0, f, c), il = sh16_half_index(F, C, 1, f, c);
-            for (int r = 0; r < nr; ++r) {
-                __half* row = Y + (r0 + r) * (long long)N * 2;
-                const __half h = __float2half_rn(acc[r]);
-                row[ih] = h;
-                row[il] = __float2half_rn(acc[r] - __half2float(h));
-            }
-        } else {
-            float* Y = reinterpret_cast<float*>(Yv);
-            for (int r = 0; r < nr; ++r) Y[(r0 + r) * N + n] = acc[r];
-        }
-    }
-}
-
 // ---- carried state of time-chunked offline calls -------------------------------------------------------------------
 // After a chunk of T frames: hist[clip][j] (j < 31) <- row T + j of the concatenation [old hist (31 rows) | ta (T rows)],
 // i.e. the TA rows of the 31 frames in front of the next chunk.  One CTA (64 threads) per clip; all reads before any write.
