@@ -468,7 +468,7 @@ struct Engine {
     int launches = 0;
     int last_B = 0, last_T = 0;
     int num_sms = 148;
-    bool no_recycle = false; // NUNET_NO_RECYCLE (tools/layer_report.py): every offline tensor keeps its own storage
+    bool no_recycle = false; // NUNET_NO_RECYCLE (tests/layer_report.py): every offline tensor keeps its own storage
     bool use_tc = true;     // NUNET_CONV=simt forces the FP32 SIMT units everywhere
     int tc3_fence_mode = 0;  // NUNET_TC3_FENCE
     int tc3_dbg = 0;         // NUNET_TC3_DBG (experiments)
@@ -1687,7 +1687,7 @@ struct Engine {
             const size_t m = P.mark();
             Ten* en_in = op_conv(P, blk + "_in", y, enc_out[j], blk + "_in", false, /*out_eo=*/true);
             // the last block's gate + residual also applies out_conv (sh16 plans; kept apart when every tensor is retained
-            // for tools/layer_report.py)
+            // for tests/layer_report.py)
             const bool fuse = (i == 5) && P.sh16 && !no_recycle;
             y = op_msfe(P, blk, DEC_N[i], en_in, enc_des[j], nullptr, false, true, /*out_eo=*/false, fuse);
             if (recycle) P.release(m);

@@ -1,5 +1,5 @@
 """GPU debugging aid: runs the offline engine without scratch recycling and compares EVERY intermediate tensor
-with the CPU oracle's taps.  Writes gpurun_out/layer_report.txt.   usage: python tools/layer_report.py [B T]"""
+with the CPU oracle's taps.  Writes gpurun_out/layer_report.txt.   usage: python tests/layer_report.py [B T]"""
 import os
 import sys
 
