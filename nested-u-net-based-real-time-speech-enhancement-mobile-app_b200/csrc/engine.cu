@@ -1584,6 +1584,14 @@ struct Engine {
         P.ops.push_back([=](Engine& E, const Run& r) {
             E.cur_op = blk;
             const int frames = r.B * r.T;
+            if (pp->streaming && pp->sh16 && !ring && !fuse_out_conv) {
+                // one-frame graph: mean, both MLPs, gate and residual of a stream in one launch
+                ctfa_stream_sh_kernel<<<r.B, 256, 0, r.st>>>(reinterpret_cast<const uint8_t*>(pp->cur(x, r.parity)),
+                                                            reinterpret_cast<const uint8_t*>(pp->cur(en_in, r.parity)), E.mlpw(mta), E.mlpw(mfa),
+                                                            reinterpret_cast<uint8_t*>(pp->cur(out, r.parity)), F0, in_eo, o_eo);
+                E.check_launch("ctfa_stream", frames * 4.0 * (3.0 * F0 * 64));
+                return;
+            }
             if (pp->sh16 && F0 <= 64)
                 ctfa_ta_warp_sh_kernel<<<std::min((frames + 7) / 8, E.num_sms * 8), 256, 0, r.st>>>(
                     reinterpret_cast<const uint8_t*>(pp->cur(x, r.parity)), E.mlpw(mta), pp->cur(ta, 0), F0, (long long)frames);

@@ -283,6 +283,59 @@ __global__ void __launch_bounds__(256) gate_residual_sh_kernel(const uint8_t* __
     }
 }
 
+// Streaming step: the whole CTFA of one block -- frequency mean, TA MLP, FA MLP on TA / 32 (the one-frame graph's rule,
+// models/proposed.py:162-196), gate and `x * gate + residual` (:319) -- for one stream per CTA (256 threads), one launch instead of
+// three (ctfa_ta*, ctfa_gate*, gate_residual_sh).  Operation order of every sum as in those kernels (ctfa_ta_sh_kernel's reduction,
+// ctfa_mlp, gate_residual_sh_kernel's fused multiply-add).
+__global__ void __launch_bounds__(256) ctfa_stream_sh_kernel(const uint8_t* __restrict__ x, const uint8_t* __restrict__ res, MlpW ta, MlpW fa,
+                                                            uint8_t* __restrict__ out, int F, int in_eo, int out_eo) {
+    __shared__ float v_s[64], h_s[16], t_s[64], g_s[64];
+    const long long s = blockIdx.x;
+    const int tid = threadIdx.x, c8 = tid >> 5, lane = tid & 31;
+    const uint8_t* xrow = x + s * (long long)F * 256;
+    float sum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int f = lane; f < F; f += 32) {           // storage positions: the mean does not care about the bin order
+        float v[8];
+        sh16_load8(xrow, F, 64, f, c8, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sum[e] += v[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) sum[e] += __shfl_xor_sync(0xffffffffu, sum[e], m);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v_s[c8 * 8 + e] = sum[e] / (float)F;
+    }
+    __syncthreads();
+    if (tid < 64) {
+        const float t = ctfa_mlp(v_s, h_s, ta, tid, 1);
+        t_s[tid] = t;
+        asm volatile("bar.sync 1, 64;" ::: "memory");      // everyone is done reading v_s / h_s
+        v_s[tid] = t * (1.0f / CTFA_WINDOW);                // 31 zero rows + this frame, average-pooled over 32
+        asm volatile("bar.sync 1, 64;" ::: "memory");
+        const float g = ctfa_mlp(v_s, h_s, fa, tid, 1);
+        g_s[tid] = g * t;
+    }
+    __syncthreads();
+    const uint8_t* rrow = res + s * (long long)F * 256;
+    uint8_t* orow = out + s * (long long)F * 256;
+    for (int i = tid; i < F * 8; i += 256) {
+        const int c = i / F, po = i - c * F;                 // chunk, output storage position
+        const int f = out_eo ? ((po < (F >> 1)) ? 2 * po : 2 * (po - (F >> 1)) + 1) : po;
+        const int pi = sh16_pos(f, F, in_eo);
+        float xv[8], rv[8], o[8];
+        sh16_load8(xrow, F, 64, pi, c, xv);
+        sh16_load8(rrow, F, 64, pi, c, rv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = fmaf(xv[e], g_s[c * 8 + e], rv[e]);
+        sh16_store8(orow, F, 64, po, c, o);
+    }
+}
+
 // Last decoder block: out_conv (Conv2D 1x1, 64 -> 1, models/proposed.py:615) applied to x * gate + res without ever
 // writing the 64-channel block output.  One thread per bin; lanes = consecutive bins, so every 16-byte load of a warp
 // is contiguous.  x and res share the [even | odd] order (in_eo); the estimate goes to bin order.
