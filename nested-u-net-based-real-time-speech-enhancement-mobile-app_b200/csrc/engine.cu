@@ -555,7 +555,7 @@ struct Engine {
         for (int h = 0; h < L.nhalf3; ++h)
             for (int n = 0; n < L.N3; ++n) b3[(size_t)h * L.N3 + n] = bias[tc3_col_to_channel(L.epi, h, n)];
         L.b3 = pool.add(b3);
-        if (cfg.max_streams > 0 && (L.CA + L.CB) % 16 == 0) L.wfz = pool.add(pack_fz(kv, L.KT * L.KF, L.CA + L.CB, L.COUT, L.epi, L.wscale_inv));
+        if (stream_fuse && cfg.max_streams > 0 && (L.CA + L.CB) % 16 == 0) L.wfz = pool.add(pack_fz(kv, L.KT * L.KF, L.CA + L.CB, L.COUT, L.epi, L.wscale_inv));
     }
 
     // up_sampling (Conv2DTranspose (1,3) stride (1,2) 'same', models/proposed.py:260) followed by the decoder
