@@ -93,6 +93,7 @@ struct Tc3Params {
     const float* beta;
     const float* alpha;
     uint8_t* out;          // sh16 [frames][F_out][PC], F_out = F_conv * nhalf * N / PC
+    uint8_t* out2;         // optional second copy of the output with its bins stored [even | odd] (read by a stride-2 unit), or null
     int F_out;
     float wscale_inv;      // undoes the power-of-two weight scale
     int C0, C1;
@@ -569,10 +570,12 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
             // output bins of this conv pixel: obin0 + g (g < NPX); storage position inside a plane of the frame row
             const int ohalf = PAIR ? eg : half;       // channel half (= output pixel group) this thread finishes
             const int obin0 = (x - p.xlo) * npx + ohalf * NPX;
-            const int opos0 = p.out_eo ? (obin0 & 1) * (p.F_out >> 1) + (obin0 >> 1) : obin0;
-            uint8_t* orow = p.out + ((long long)b * p.T + t) * out_rs + (long long)opos0 * 16;
-            if (valid && !(p.dbg & 2)) {
-                if (NPX == 2 && !p.out_eo) {
+            // one copy in the order the flags ask for; units whose output also feeds a stride-2 unit write a second,
+            // [even | odd] copy (Tc3Params::out2) so that consumer moves whole plane rows instead of 16-byte pieces
+            auto emit = [&](uint8_t* base, const int eo) {
+                const int opos0 = eo ? (obin0 & 1) * (p.F_out >> 1) + (obin0 >> 1) : obin0;
+                uint8_t* orow = base + ((long long)b * p.T + t) * out_rs + (long long)opos0 * 16;
+                if (NPX == 2 && !eo) {
                     // two neighbouring output bins per thread: one 32-byte store per chunk (whole sectors)
 #pragma unroll
                     for (int c = 0; c < CPP; ++c) {
@@ -586,7 +589,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
 #pragma unroll
                     for (int g = 0; g < NPX; ++g) {
                         // with [even | odd] storage the second bin of a pair lives half a plane further
-                        uint8_t* o = orow + (p.out_eo ? (long long)g * (p.F_out >> 1) * 16 : (long long)g * 16);
+                        uint8_t* o = orow + (eo ? (long long)g * (p.F_out >> 1) * 16 : (long long)g * 16);
 #pragma unroll
                         for (int c = 0; c < CPP; ++c) {
                             uint4 hi, lo;
@@ -596,6 +599,10 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
                         }
                     }
                 }
+            };
+            if (valid && !(p.dbg & 2)) {
+                emit(p.out, p.out_eo);
+                if (!PAIR && p.out2) emit(p.out2, 1);
             }
         }
         if (p.timing && blockIdx.x == 0 && threadIdx.x == 0) {

@@ -282,6 +282,7 @@ struct Ten {
     bool pingpong = false;    // streaming: two copies selected by step parity
     bool sh = false;          // holds split-half records (sh16 plans) rather than floats
     bool eo = false;          // sh16: bins stored [even | odd] inside every plane
+    Ten* twin = nullptr;      // offline sh16: a second copy in [even | odd] order written by the same producer, for stride-2 readers
     std::string name;
     size_t numel() const { return (size_t)F * C; }
 };
@@ -468,6 +469,7 @@ struct Engine {
     int launches = 0;
     int last_B = 0, last_T = 0;
     int num_sms = 148;
+    bool tc3_twin = true;    // NUNET_TC3_TWIN=0: no [even | odd] twins (stride-2 units then use strided boxes over bin-ordered sources)
     bool no_recycle = false; // NUNET_NO_RECYCLE (tests/layer_report.py): every offline tensor keeps its own storage
     bool use_tc = true;     // NUNET_CONV=simt forces the FP32 SIMT units everywhere
     int tc3_fence_mode = 0;  // NUNET_TC3_FENCE
@@ -997,8 +999,9 @@ struct Engine {
     // Split-half tensor-core path (offline plans with sh16 tensors): every conv unit of the topology is eligible.
     void launch_conv_tc3(const ConvLayer& L, const float* a_cur, const float* b_cur, const float* a_prev, const float* b_prev,
                          float* out, int B, int T, int F_in, bool src_eo, bool out_eo, cudaStream_t st, bool allow_box = true,
-                         bool* probe_two = nullptr) {
+                         bool* probe_two = nullptr, float* out2 = nullptr) {
         Tc3Params p{};
+        p.out2 = reinterpret_cast<uint8_t*>(out2);
         p.prev0 = (L.KT == 2) ? reinterpret_cast<const uint8_t*>(a_prev) : nullptr;
         p.prev1 = (L.KT == 2) ? reinterpret_cast<const uint8_t*>(b_prev) : nullptr;
         p.src_eo = src_eo ? 1 : 0;
@@ -1149,7 +1152,7 @@ struct Engine {
             bool two_rows = false;
             launch_conv_tc3(L, a_cur, b_cur, a_prev, b_prev, out, B, T, F_in, src_eo, out_eo, st, false, &two_rows);
             if (two_rows) {
-                launch_conv_tc3(L, a_cur, b_cur, a_prev, b_prev, out, B, T, F_in, src_eo, out_eo, st, false);
+                launch_conv_tc3(L, a_cur, b_cur, a_prev, b_prev, out, B, T, F_in, src_eo, out_eo, st, false, nullptr, out2);
                 return;
             }
         }
@@ -1238,8 +1241,14 @@ struct Engine {
     // -------------------------------------------------------------------------------- topology -> plan
     // conv unit reading one or two tensors
     Ten* op_conv(Plan& P, const std::string& role, Ten* a, Ten* b, const std::string& out_name, bool persistent,
-                 bool out_eo = false) {
+                 bool out_eo = false, bool want_twin = false) {
         const ConvLayer& L = convs.at(role);
+        // a stride-2 unit reads the [even | odd] copies of its sources when their producers wrote one: its tile images are
+        // then whole plane rows per tensor-map box instead of a box of 16-byte pieces (traversal stride two)
+        if (L.stride == 2 && a->twin && !a->eo && (!b || (b->twin && !b->eo))) {
+            a = a->twin;
+            if (b) b = b->twin;
+        }
         if (a->C != L.CA || (b ? b->C : 0) != L.CB || (b && b->F != a->F)) fail(NUNET_EINVAL, "plan: %s wiring", role.c_str());
         const int F_in = a->F;
         const int F_conv = (L.stride == 2) ? F_in / 2 : F_in;
@@ -1247,6 +1256,13 @@ struct Engine {
         Ten* o = P.make(out_name, shuf ? 2 * F_conv : F_conv, shuf ? L.COUT / 2 : L.COUT, persistent);
         o->sh = P.sh16;
         o->eo = P.sh16 && out_eo;
+        Ten* o2 = nullptr;
+        if (want_twin && tc3_twin && !P.streaming && P.sh16 && !o->eo && !fz_open && (o->F % 2) == 0) {
+            o2 = P.make("", o->F, o->C, persistent);
+            o2->sh = true;
+            o2->eo = true;
+            o->twin = o2;
+        }
         if (b && b->eo != a->eo) fail(NUNET_EINVAL, "plan: %s sources disagree on the bin order", role.c_str());
         const bool src_eo = a->eo, dst_eo = o->eo;
         Plan* pp = &P;
@@ -1285,7 +1301,7 @@ struct Engine {
                     bp = b ? pp->carry_at(b_coff) : nullptr;
                 }
                 E.launch_conv_tc3(L, pp->cur(a, r.parity), b ? pp->cur(b, r.parity) : nullptr, ap, bp, pp->cur(o, r.parity), r.B, r.T, F_in,
-                                  src_eo, dst_eo, r.st);
+                                  src_eo, dst_eo, r.st, true, nullptr, o2 ? pp->cur(o2, r.parity) : nullptr);
                 return;
             }
             E.launch_conv(L, pp->cur(a, r.parity), pp->prev(a, r.parity), b ? pp->cur(b, r.parity) : nullptr,
@@ -1512,7 +1528,8 @@ struct Engine {
             // streaming: from the first conv whose input has <= 32 bins on, the layers of this sub-U-Net are collected into one
             // fused_tail_kernel launch (closed below after the last sub-pixel conv that still writes <= 32 bins)
             if (P.streaming && P.sh16 && stream_fuse && !is_ddb() && !fz_open && cur->F <= 32) fz_open.reset(new FzGroup());
-            cur = op_conv(P, blk + "_conv" + std::to_string(k), cur, sk, blk + "_conv" + std::to_string(k), false);
+            // (its output feeds the next stride-2 conv and, in bin order, the sub-pixel conv of the way up)
+            cur = op_conv(P, blk + "_conv" + std::to_string(k), cur, sk, blk + "_conv" + std::to_string(k), false, false, /*want_twin=*/k < n);
             ens.push_back(cur);
         }
         Ten* bb = is_ddb() ? op_ddb(P, blk + "_ddb", cur, blk + "_bb", false) : op_lstm(P, blk + "_lstm", cur, blk + "_bb", blk, false);
@@ -1551,8 +1568,9 @@ struct Engine {
                 P.states.push_back(s);
             }
             if (fz_open && cur->F > 16) fz_close();        // this sub-pixel conv would write more than 32 bins: it runs on its own
+            // (second-level skips de_2 .. de_n of an encoder block are read by the stride-2 convs of the paired decoder block)
             cur = op_conv(P, blk + "_spconv" + std::to_string(k), cur, sk, blk + "_spconv" + std::to_string(k), des_persistent,
-                          /*out_eo=*/k == n);
+                          /*out_eo=*/k == n, /*want_twin=*/des_out != nullptr && des_persistent && k < n);
             des.push_back(cur);
         }
         fz_close();
@@ -2391,6 +2409,7 @@ int nunet_create(const nunet_config* cfg, const void* blob, size_t blob_bytes, n
         const bool knobs = getenv("NUNET_DEBUG_KNOBS") && atoi(getenv("NUNET_DEBUG_KNOBS")) != 0;
         auto knob = [&](const char* name) -> const char* { return knobs ? getenv(name) : nullptr; };
         E.no_recycle = knob("NUNET_NO_RECYCLE") != nullptr;
+        if (const char* v = knob("NUNET_TC3_TWIN")) E.tc3_twin = atoi(v) != 0;
         if (const char* c = knob("NUNET_CONV")) {
             E.use_tc = strcmp(c, "simt") != 0;
         }
