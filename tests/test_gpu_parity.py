@@ -455,6 +455,36 @@ def test_streaming_graph_with_parallel_chains_equals_plain_launches(blob, ddb_we
         assert np.isfinite(g).all() and np.abs(a - g).max() <= 1e-6
 
 
+@pytest.mark.parametrize("variant", ["lstm", "ddb"])
+def test_even_odd_twins_do_not_change_results(blob, ddb_weights, variant, monkeypatch):
+    """Inner stride-2 convs read an [even | odd] copy of their inputs that the producers write next to the bin-ordered one
+    (Tc3Params::out2).  That is a change of data movement only: with the twins switched off (NUNET_TC3_TWIN=0, strided
+    tensor-map boxes over the bin-ordered tensors) every output is bit-identical -- whole clips and time chunks."""
+    from nunet_b200._lib import NUNET_VARIANT_DDB, NUNET_VARIANT_LSTM
+    from nunet_b200.engine import NunetEngine
+    from nunet_b200.synth import synth_clips
+    from nunet_b200.weights import VARIANT_DDB, pack_blob
+    if variant == "ddb":
+        b, v = pack_blob(ddb_weights, VARIANT_DDB), NUNET_VARIANT_DDB
+    else:
+        b, v = blob, NUNET_VARIANT_LSTM
+    B, T = 5, 45
+    wav = torch.from_numpy(synth_clips(B, 512 + 256 * (T - 1), first_clip=300)).cuda()
+    outs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("NUNET_DEBUG_KNOBS", "1")
+        monkeypatch.setenv("NUNET_TC3_TWIN", mode)
+        eng = NunetEngine(b, max_frames=B * T, variant=v)
+        y, est = eng.forward_wav(wav)
+        cut = NunetEngine(b, max_frames=B * T, variant=v, chunk_frames=16)
+        y2, est2 = cut.forward_wav(wav)
+        outs[mode] = [t.cpu().numpy().copy() for t in (y, est, y2, est2)]
+        eng.close()
+        cut.close()
+    for a, g in zip(outs["1"], outs["0"]):
+        assert np.isfinite(a).all() and np.array_equal(a, g)
+
+
 def test_full_size_batch_properties(blob, oracles):
     """BASELINE configs[1] at FULL size (256 clips x 4 s = 63 744 frames, the bench workload), checked through properties
     that do not need an oracle run of that size: (a) copies of one clip anywhere in the batch come out bit-identical
