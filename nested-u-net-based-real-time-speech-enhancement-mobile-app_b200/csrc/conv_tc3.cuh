@@ -6,7 +6,7 @@
 // issued as TWO kind::f16 MMAs per K step:  a_hi x [b_hi | b_lo]  (2N accumulator columns) and  a_lo x b_hi
 // (into the first N columns); the epilogue adds the two column blocks.  Sharing the a_hi read between two products
 // matters because at M = 128 the shared-memory read of A, not the tensor pipe, bounds an N <= 64 MMA.
-// That is the accuracy of the 3xTF32 scheme of conv_tc.cuh at twice the tensor rate and half the shared-memory
+// That is the accuracy of a 3xTF32 scheme (the first kernel of this repo, since removed) at twice the tensor rate and half the shared-memory
 // operand traffic, and -- the point of the format -- the split is done ONCE by the producer's epilogue, so the
 // consumer's loaders are pure 16-byte cp.async copies (no conversion pass: the old kernel was bound by it).
 //
@@ -22,7 +22,7 @@
 // Weights are pre-split on the host and scaled by a power of two per layer so that their lo parts stay normal
 // halves (undone in the epilogue).
 //
-// Geometry: the "flat padded implicit GEMM" of conv_tc.cuh -- output positions of the whole batch on one flat
+// Geometry: a "flat padded implicit GEMM" -- output positions of the whole batch on one flat
 // axis q = rho*P + x with zero pad rows / columns, every tap a constant shift of q, so all taps read the SAME
 // shared-memory image through K-major no-swizzle UMMA descriptors (rows 16 B apart, 8-channel K chunks in planes):
 //      buffer[hi|lo][chunk 2][img][slot][8 halves],   one image buffer = 16 input channels = one K=16 MMA step.
@@ -36,7 +36,8 @@
 // CTAs' images and weight halves -- see Tc3Params::pair.  (Fallback NUNET_TC3_PAIR=0: CTA 2c / 2c+1 take half 0 / 1
 // of the same tiles independently.)
 //
-// CTA = 13 warps, persistent over tiles of mt*128 positions:
+// CTA = 16 warps (13 working + 3 idle ones that only balance the register file, see T3_WARPS), persistent over tiles of
+// mt*128 positions:
 //   warps 0-7   epilogue  two groups of four warps (two warps share every SM sub-partition and hide each other's
 //                         latencies): TMEM -> registers (one thread = one position, all its channels: LayerNorm is
 //                         thread-local) -> bias / two-pass LN / PReLU -> hi/lo split -> 16/32-byte stores, coalesced
