@@ -4,6 +4,8 @@ import ctypes
 import os
 import re
 
+import numpy as np
+
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -91,3 +93,63 @@ def test_pybind11_layer_forwards_to_the_c_abi():
         from nunet_b200.engine import NunetEngine
         with pytest.raises(_lib.NunetError):
             NunetEngine(blob, max_frames=8)
+
+
+def test_blob_parser_survives_corrupted_tables():
+    """nunet_create / nunet_blob_validate take bytes from outside: a damaged table (count, rank, dimensions, offsets, names) must
+    end in an error code with a message -- never in a crash, an out-of-bounds read or a wrap-around of the size arithmetic."""
+    from nunet_b200 import _lib
+    from nunet_b200.weights import pack_blob, random_lstm_weights
+    m = _lib.pyb()
+    blob = pack_blob(random_lstm_weights(0))
+    cnt = int.from_bytes(blob[8:12], "little")
+    assert m.blob_validate(blob, 0) > 0
+
+    def patched(pos, value, width):
+        b = bytearray(blob)
+        b[pos:pos + width] = int(value).to_bytes(width, "little")
+        return bytes(b)
+
+    e0 = 16                                    # first table entry: name[64] | ndim u32 | dims u32[4] | offset u64 (floats)
+    targeted = [
+        (patched(8, 0xFFFFFFFF, 4), "truncated"),                      # count
+        (patched(8, cnt + 1, 4), None),                                # table runs into the data
+        (patched(e0 + 64, 5, 4), "rank"),                              # ndim
+        (patched(e0 + 68, 0xFFFFFFFF, 4), "dimension"),                # one huge dimension
+        (patched(e0 + 84, 2 ** 64 - 1, 8), "out of range"),            # offset + size would wrap
+        (patched(e0 + 84, (len(blob) - 16 - cnt * 96) // 4, 8), "out of range"),   # starts at the very end
+        (blob[:8] + b"\xff" * 8 + blob[16:], None),
+        (b"NUNETW02" + blob[8:], "magic"),
+        (blob[:16 + cnt * 96 - 1], "truncated"),
+        (b"", "magic"),
+    ]
+    for b, word in targeted:
+        assert m.blob_validate(b, 0) == -1
+        assert word is None or word in m.last_error(), (word, m.last_error())
+    # all four dimensions large: the element count must not wrap around 64 bits
+    b = bytearray(blob)
+    b[e0 + 64:e0 + 68] = (4).to_bytes(4, "little")
+    for k in range(4):
+        b[e0 + 68 + 4 * k:e0 + 72 + 4 * k] = (0x7FFFFFFF).to_bytes(4, "little")
+    assert m.blob_validate(bytes(b), 0) == -1 and "out of range" in m.last_error()
+    rng = np.random.default_rng(7)
+    errors = 0
+    for _ in range(60):
+        b = bytearray(blob)
+        base = 16 + int(rng.integers(cnt)) * 96
+        field = int(rng.integers(4))
+        if field == 0:
+            b[base + int(rng.integers(64))] ^= 0xFF
+        elif field == 1:
+            b[base + 64:base + 68] = int(rng.integers(0, 2 ** 32)).to_bytes(4, "little")
+        elif field == 2:
+            k = int(rng.integers(4))
+            b[base + 68 + 4 * k:base + 72 + 4 * k] = int(rng.integers(0, 2 ** 32)).to_bytes(4, "little")
+        else:
+            b[base + 84:base + 92] = int(rng.integers(0, 2 ** 63)).to_bytes(8, "little")
+        r = m.blob_validate(bytes(b), 0)
+        assert r == -1 or r > 0
+        if r == -1:
+            errors += 1
+            assert len(m.last_error()) > 0
+    assert errors > 20
