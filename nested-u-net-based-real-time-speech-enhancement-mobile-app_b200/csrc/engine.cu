@@ -469,6 +469,7 @@ struct Engine {
     int launches = 0;
     int last_B = 0, last_T = 0;
     int num_sms = 148;
+    bool ctfa_gate4 = true;  // NUNET_CTFA_GATE4=0 (experiments): the one-frame-per-warp gate kernel
     bool tc3_twin = true;    // NUNET_TC3_TWIN=0: no [even | odd] twins (stride-2 units then use strided boxes over bin-ordered sources)
     bool no_recycle = false; // NUNET_NO_RECYCLE (tests/layer_report.py): every offline tensor keeps its own storage
     bool use_tc = true;     // NUNET_CONV=simt forces the FP32 SIMT units everywhere
@@ -1634,6 +1635,10 @@ struct Engine {
             }
             const float* hist = (!pp->streaming && r.use_carry && !div32) ? pp->carry_at(hist_off) : nullptr;
             if (!ring && (frames >= 64 || !pp->streaming))
+                if (E.ctfa_gate4)
+                    ctfa_gate_warp4_kernel<<<std::min((frames + 31) / 32, E.num_sms * 4), 256, 0, r.st>>>(pp->cur(ta, 0), E.mlpw(mfa), pp->cur(gate, 0),
+                                                                                                         r.T, div32, (long long)frames, hist, r.t0);
+                else
                 ctfa_gate_warp_kernel<<<std::min((frames + 7) / 8, E.num_sms * 8), 256, 0, r.st>>>(pp->cur(ta, 0), E.mlpw(mfa), pp->cur(gate, 0),
                                                                                                     r.T, div32, (long long)frames, hist, r.t0);
             else
@@ -2410,6 +2415,7 @@ int nunet_create(const nunet_config* cfg, const void* blob, size_t blob_bytes, n
         auto knob = [&](const char* name) -> const char* { return knobs ? getenv(name) : nullptr; };
         E.no_recycle = knob("NUNET_NO_RECYCLE") != nullptr;
         if (const char* v = knob("NUNET_TC3_TWIN")) E.tc3_twin = atoi(v) != 0;
+        if (const char* v = knob("NUNET_CTFA_GATE4")) E.ctfa_gate4 = atoi(v) != 0;
         if (const char* c = knob("NUNET_CONV")) {
             E.use_tc = strcmp(c, "simt") != 0;
         }

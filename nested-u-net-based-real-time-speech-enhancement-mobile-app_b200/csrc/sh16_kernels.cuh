@@ -158,6 +158,8 @@ __global__ void __launch_bounds__(256) ctfa_ta_warp_sh_kernel(const uint8_t* __r
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c8 = lane & 7, fq = lane >> 3;
+    const bool pow2F = (F & (F - 1)) == 0;
+    const float invF = 1.0f / (float)F;
     for (long long frame = (long long)blockIdx.x * 8 + warp; frame < frames; frame += (long long)gridDim.x * 8) {
         const uint8_t* row = x + (size_t)frame * F * 256;
         float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -174,8 +176,10 @@ __global__ void __launch_bounds__(256) ctfa_ta_warp_sh_kernel(const uint8_t* __r
             s[e] += __shfl_xor_sync(0xffffffffu, s[e], 16);
         }
         if (fq == 0) {
+            // F is a power of two in every block of the topology: multiplying by the (exact) reciprocal is the same rounding as the
+            // division of the reference's mean and a tenth of its instructions
 #pragma unroll
-            for (int e = 0; e < 8; ++e) mean_s[warp][c8 * 8 + e] = s[e] / (float)F;
+            for (int e = 0; e < 8; ++e) mean_s[warp][c8 * 8 + e] = pow2F ? s[e] * invF : s[e] / (float)F;
         }
         __syncwarp();
         if (lane < 16) {
@@ -195,6 +199,39 @@ __global__ void __launch_bounds__(256) ctfa_ta_warp_sh_kernel(const uint8_t* __r
         }
         __syncwarp();
     }
+}
+
+// The CTFA MLP (64 -> 16 relu -> 64, pre-sigmoid) of FOUR frames by one warp, as packed fp32x2 FMAs over frame pairs: layer 1 on
+// lane = (hidden unit j, frame pair p), layer 2 on lane = channels 2 lane, 2 lane + 1 of all four frames.  v_s [64][4] holds the
+// inputs (channel-major), h_s [16][4] is scratch; every sum runs in the order of mlp_apply / ctfa_mlp (k and j ascending from the
+// bias), so the results equal the one-frame kernels' bit for bit.  ox / oy [4]: outputs of the two channels per frame.
+__device__ __forceinline__ void mlp4_warp(const MlpSmem& m, const float (*v_s)[4], float (*h_s)[4], int lane, float* ox, float* oy) {
+    __syncwarp();
+    {
+        const int j = lane & 15, p = lane >> 4;
+        float2 acc = make_float2(m.b0[j], m.b0[j]);
+#pragma unroll 16
+        for (int k = 0; k < 64; ++k) {
+            const float2 av = *reinterpret_cast<const float2*>(&v_s[k][2 * p]);
+            const float w = m.k0[k * 16 + j];
+            acc = __ffma2_rn(av, make_float2(w, w), acc);
+        }
+        *reinterpret_cast<float2*>(&h_s[j][2 * p]) = make_float2(fmaxf(acc.x, 0.0f), fmaxf(acc.y, 0.0f));
+    }
+    __syncwarp();
+    const float2 b1 = *reinterpret_cast<const float2*>(&m.b1[2 * lane]);
+    float2 x01 = make_float2(b1.x, b1.x), x23 = x01, y01 = make_float2(b1.y, b1.y), y23 = y01;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float4 hv = *reinterpret_cast<const float4*>(&h_s[j][0]);
+        const float2 w2 = *reinterpret_cast<const float2*>(&m.k1[j * 64 + 2 * lane]);
+        x01 = __ffma2_rn(make_float2(hv.x, hv.y), make_float2(w2.x, w2.x), x01);
+        x23 = __ffma2_rn(make_float2(hv.z, hv.w), make_float2(w2.x, w2.x), x23);
+        y01 = __ffma2_rn(make_float2(hv.x, hv.y), make_float2(w2.y, w2.y), y01);
+        y23 = __ffma2_rn(make_float2(hv.z, hv.w), make_float2(w2.y, w2.y), y23);
+    }
+    ox[0] = x01.x; ox[1] = x01.y; ox[2] = x23.x; ox[3] = x23.y;
+    oy[0] = y01.x; oy[1] = y01.y; oy[2] = y23.x; oy[3] = y23.y;
 }
 
 // CTFA stage 2 (see ctfa_gate_kernel) with one WARP per frame and the MLP weights staged once per CTA: lane l owns channels
@@ -248,6 +285,102 @@ __global__ void __launch_bounds__(256) ctfa_gate_warp_kernel(const float* __rest
         }
         gate[frame * 64 + lane] = sigmoidf_(o0) * tv0;
         gate[frame * 64 + 32 + lane] = sigmoidf_(o1) * tv1;
+        __syncwarp();
+    }
+}
+
+// The same stage, FOUR consecutive frames per warp iteration (the default).  ctfa_gate_warp_kernel is instruction-bound
+// (ncu: ~860 warp instructions per frame, two thirds of them address arithmetic of the window loop, and an MLP that keeps 16
+// lanes busy); here lane l owns channels 2l, 2l+1 (one 8-byte load per TA row), the 35 rows that the four windows share are
+// read once and added into each window oldest row first -- the order of ctfa_gate_kernel, so results stay bit-identical --
+// and the MLP runs as packed fp32x2 FMAs over frame pairs: layer 1 on (hidden unit j, frame pair) = all 32 lanes, layer 2 on
+// (2 channels x 4 frames) per lane.  Groups that straddle two clips (and the last, partial one) take the per-frame sums below.
+__device__ __forceinline__ float2 ctfa_window_sum2(const float* __restrict__ ta, const float* __restrict__ hist, long long frame, int T,
+                                                   int t0, int lane) {
+    const int t = (int)(frame % T);
+    const float* hrow = hist ? hist + ((frame / T) * (CTFA_WINDOW - 1) + (CTFA_WINDOW - 1)) * 64 : nullptr;   // row of frame "t = 0"
+    const int n = min((hist ? t0 : 0) + t + 1, CTFA_WINDOW);
+    // all 32 candidate rows, eight loads in flight at a time; rows in front of the window (d >= n, the OLDEST ones) count as +0,
+    // which leaves every partial sum what the n-row loop of ctfa_gate_warp_kernel makes it
+    float2 s = make_float2(0.0f, 0.0f);
+#pragma unroll
+    for (int db = CTFA_WINDOW - 1; db >= 0; db -= 8) {
+        float2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int d = db - u;
+            const float* src = (d <= t) ? ta + (frame - d) * 64 : hrow + (long long)(t - d) * 64;
+            v[u] = (d < n) ? *reinterpret_cast<const float2*>(src + 2 * lane) : make_float2(0.0f, 0.0f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s = __fadd2_rn(s, v[u]);
+    }
+    return s;
+}
+__global__ void __launch_bounds__(256) ctfa_gate_warp4_kernel(const float* __restrict__ ta, MlpW fa, float* __restrict__ gate, int T,
+                                                             int mode_div32, long long frames, const float* __restrict__ hist, int t0) {
+    __shared__ MlpSmem w_s;
+    __shared__ __align__(16) float avg_s[8][64][4];   // [warp][channel][frame of the group]
+    __shared__ __align__(16) float h_s[8][16][4];
+    mlp_stage(w_s, fa);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long groups = (frames + 3) >> 2;
+    for (long long g = (long long)blockIdx.x * 8 + warp; g < groups; g += (long long)gridDim.x * 8) {
+        const long long frame0 = g * 4;
+        const int nf = (int)min((long long)4, frames - frame0);
+        float2 tv[4], a[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            tv[i] = (i < nf) ? *reinterpret_cast<const float2*>(ta + (frame0 + i) * 64 + 2 * lane) : make_float2(0.0f, 0.0f);
+        const int tf = (int)(frame0 % T);
+        if (mode_div32) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = make_float2(tv[i].x * (1.0f / CTFA_WINDOW), tv[i].y * (1.0f / CTFA_WINDOW));
+        } else if (nf == 4 && tf + 3 < T) {
+            // four frames of one clip: their windows share the 35 rows t = tf - 31 .. tf + 3.  Rows in front of the clip come from
+            // the carried history (time-chunked calls) or, in front of what exists (t < -t0), count as +0 -- they are the OLDEST
+            // terms of a window, so every partial sum is what the n-row loop makes it.
+            const int base = hist ? t0 : 0;
+            const float* hrow = hist ? hist + ((frame0 / T) * (CTFA_WINDOW - 1) + (CTFA_WINDOW - 1)) * 64 : nullptr;   // row of "t = 0"
+            const float* trow = ta + (frame0 - tf) * 64;                                                             // row of t = 0
+            float2 s[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) s[i] = make_float2(0.0f, 0.0f);
+#pragma unroll
+            for (int rb = 0; rb < CTFA_WINDOW + 3; rb += 7) {
+                float2 v[7];
+#pragma unroll
+                for (int u = 0; u < 7; ++u) {
+                    const int tr = tf - (CTFA_WINDOW - 1) + rb + u;
+                    const float* src = (tr >= 0 ? trow : hrow) + (long long)tr * 64;
+                    v[u] = (tr >= -base) ? *reinterpret_cast<const float2*>(src + 2 * lane) : make_float2(0.0f, 0.0f);
+                }
+#pragma unroll
+                for (int u = 0; u < 7; ++u)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (rb + u >= i && rb + u <= i + CTFA_WINDOW - 1) s[i] = __fadd2_rn(s[i], v[u]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = make_float2(s[i].x * (1.0f / CTFA_WINDOW), s[i].y * (1.0f / CTFA_WINDOW));
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float2 s = make_float2(0.0f, 0.0f);
+                if (i < nf) s = ctfa_window_sum2(ta, hist, frame0 + i, T, t0, lane);
+                a[i] = make_float2(s.x * (1.0f / CTFA_WINDOW), s.y * (1.0f / CTFA_WINDOW));
+            }
+        }
+        *reinterpret_cast<float4*>(&avg_s[warp][2 * lane][0]) = make_float4(a[0].x, a[1].x, a[2].x, a[3].x);
+        *reinterpret_cast<float4*>(&avg_s[warp][2 * lane + 1][0]) = make_float4(a[0].y, a[1].y, a[2].y, a[3].y);
+        __syncwarp();
+        float ox[4], oy[4];
+        mlp4_warp(w_s, avg_s[warp], h_s[warp], lane, ox, oy);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (i < nf)
+                *reinterpret_cast<float2*>(gate + (frame0 + i) * 64 + 2 * lane) = make_float2(sigmoidf_(ox[i]) * tv[i].x, sigmoidf_(oy[i]) * tv[i].y);
         __syncwarp();
     }
 }

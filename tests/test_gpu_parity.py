@@ -455,11 +455,14 @@ def test_streaming_graph_with_parallel_chains_equals_plain_launches(blob, ddb_we
         assert np.isfinite(g).all() and np.abs(a - g).max() <= 1e-6
 
 
+@pytest.mark.parametrize("knob", ["NUNET_TC3_TWIN", "NUNET_CTFA_GATE4"])
 @pytest.mark.parametrize("variant", ["lstm", "ddb"])
-def test_even_odd_twins_do_not_change_results(blob, ddb_weights, variant, monkeypatch):
-    """Inner stride-2 convs read an [even | odd] copy of their inputs that the producers write next to the bin-ordered one
-    (Tc3Params::out2).  That is a change of data movement only: with the twins switched off (NUNET_TC3_TWIN=0, strided
-    tensor-map boxes over the bin-ordered tensors) every output is bit-identical -- whole clips and time chunks."""
+def test_kernel_variants_do_not_change_results(blob, ddb_weights, variant, knob, monkeypatch):
+    """Two round-2 changes are pure re-arrangements and must not move a bit -- whole clips and time chunks:
+    NUNET_TC3_TWIN: inner stride-2 convs read an [even | odd] copy of their inputs that the producers write next to the
+    bin-ordered one (Tc3Params::out2); switched off they read the bin-ordered tensors through strided tensor-map boxes.
+    NUNET_CTFA_GATE4: the CTFA gate kernel handles four frames per warp with packed fp32x2 arithmetic in the summation order of
+    the one-frame-per-warp kernel it replaces."""
     from nunet_b200._lib import NUNET_VARIANT_DDB, NUNET_VARIANT_LSTM
     from nunet_b200.engine import NunetEngine
     from nunet_b200.synth import synth_clips
@@ -473,7 +476,7 @@ def test_even_odd_twins_do_not_change_results(blob, ddb_weights, variant, monkey
     outs = {}
     for mode in ("1", "0"):
         monkeypatch.setenv("NUNET_DEBUG_KNOBS", "1")
-        monkeypatch.setenv("NUNET_TC3_TWIN", mode)
+        monkeypatch.setenv(knob, mode)
         eng = NunetEngine(b, max_frames=B * T, variant=v)
         y, est = eng.forward_wav(wav)
         cut = NunetEngine(b, max_frames=B * T, variant=v, chunk_frames=16)
