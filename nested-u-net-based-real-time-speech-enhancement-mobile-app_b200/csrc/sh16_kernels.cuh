@@ -144,63 +144,6 @@ __global__ void __launch_bounds__(256) ctfa_ta_sh_kernel(const uint8_t* __restri
     if (frame < frames) ta_out[frame * 64 + (threadIdx.x & 63)] = t;
 }
 
-// CTFA stage 1 for blocks with few bins (F <= 64): one WARP per frame, eight frames per CTA iteration, grid-stride.  Lane
-// (c8 = lane & 7, fq = lane >> 3) sums chunk c8 over the bins f = fq, fq + 4, ..: one load instruction of the warp reads
-// four neighbouring positions (64 contiguous bytes) of each of the eight planes.  The per-frame MLP runs inside the warp
-// (same operation order as mlp_apply).  The CTA-per-four-frames kernel above spends ~10 us of fixed latency per CTA, which
-// is all there is at F <= 32 (0.24 ms per launch whatever the size); this one does not.
-__global__ void __launch_bounds__(256) ctfa_ta_warp_sh_kernel(const uint8_t* __restrict__ x, MlpW ta, float* __restrict__ ta_out, int F,
-                                                             long long frames) {
-    __shared__ MlpSmem w_s;
-    __shared__ float mean_s[8][64];
-    __shared__ float h_s[8][16];
-    mlp_stage(w_s, ta);
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int c8 = lane & 7, fq = lane >> 3;
-    const bool pow2F = (F & (F - 1)) == 0;
-    const float invF = 1.0f / (float)F;
-    for (long long frame = (long long)blockIdx.x * 8 + warp; frame < frames; frame += (long long)gridDim.x * 8) {
-        const uint8_t* row = x + (size_t)frame * F * 256;
-        float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-        for (int f = fq; f < F; f += 4) {
-            float v[8];
-            sh16_load8(row, F, 64, f, c8, v);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) s[e] += v[e];
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            s[e] += __shfl_xor_sync(0xffffffffu, s[e], 8);
-            s[e] += __shfl_xor_sync(0xffffffffu, s[e], 16);
-        }
-        if (fq == 0) {
-            // F is a power of two in every block of the topology: multiplying by the (exact) reciprocal is the same rounding as the
-            // division of the reference's mean and a tenth of its instructions
-#pragma unroll
-            for (int e = 0; e < 8; ++e) mean_s[warp][c8 * 8 + e] = pow2F ? s[e] * invF : s[e] / (float)F;
-        }
-        __syncwarp();
-        if (lane < 16) {
-            float a = w_s.b0[lane];
-#pragma unroll 16
-            for (int k = 0; k < 64; ++k) a = fmaf(mean_s[warp][k], w_s.k0[k * 16 + lane], a);
-            h_s[warp][lane] = fmaxf(a, 0.0f);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-            const int c = lane + 32 * hf;
-            float o = w_s.b1[c];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) o = fmaf(h_s[warp][j], w_s.k1[j * 64 + c], o);
-            ta_out[frame * 64 + c] = sigmoidf_(o);
-        }
-        __syncwarp();
-    }
-}
-
 // The CTFA MLP (64 -> 16 relu -> 64, pre-sigmoid) of FOUR frames by one warp, as packed fp32x2 FMAs over frame pairs: layer 1 on
 // lane = (hidden unit j, frame pair p), layer 2 on lane = channels 2 lane, 2 lane + 1 of all four frames.  v_s [64][4] holds the
 // inputs (channel-major), h_s [16][4] is scratch; every sum runs in the order of mlp_apply / ctfa_mlp (k and j ascending from the
@@ -232,6 +175,60 @@ __device__ __forceinline__ void mlp4_warp(const MlpSmem& m, const float (*v_s)[4
     }
     ox[0] = x01.x; ox[1] = x01.y; ox[2] = x23.x; ox[3] = x23.y;
     oy[0] = y01.x; oy[1] = y01.y; oy[2] = y23.x; oy[3] = y23.y;
+}
+
+// CTFA stage 1 for blocks with few bins (F <= 64): one WARP per group of four frames, grid-stride.  Lane (c8 = lane & 7,
+// fq = lane >> 3) sums chunk c8 over the bins f = fq, fq + 4, ..: one load instruction of the warp reads four neighbouring
+// positions (64 contiguous bytes) of each of the eight planes; the four frames of a group go one after the other, then their
+// MLPs run together (mlp4_warp: a per-frame MLP keeps 16 lanes busy and was a third of this kernel's instructions).  The
+// CTA-per-four-frames kernel above spends ~10 us of fixed latency per CTA, which is all there is at F <= 32; this one does not.
+__global__ void __launch_bounds__(256) ctfa_ta_warp_sh_kernel(const uint8_t* __restrict__ x, MlpW ta, float* __restrict__ ta_out, int F,
+                                                             long long frames) {
+    __shared__ MlpSmem w_s;
+    __shared__ __align__(16) float mean_s[8][64][4];
+    __shared__ __align__(16) float h_s[8][16][4];
+    mlp_stage(w_s, ta);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c8 = lane & 7, fq = lane >> 3;
+    // F is a power of two in every block of the topology: multiplying by the (exact) reciprocal is the same rounding as the
+    // division of the reference's mean and a tenth of its instructions
+    const bool pow2F = (F & (F - 1)) == 0;
+    const float invF = 1.0f / (float)F;
+    const long long groups = (frames + 3) >> 2;
+    for (long long g = (long long)blockIdx.x * 8 + warp; g < groups; g += (long long)gridDim.x * 8) {
+        const long long frame0 = g * 4;
+        const int nf = (int)min((long long)4, frames - frame0);
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) {
+            float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (i < nf) {
+                const uint8_t* row = x + (size_t)(frame0 + i) * F * 256;
+#pragma unroll 4
+                for (int f = fq; f < F; f += 4) {
+                    float v[8];
+                    sh16_load8(row, F, 64, f, c8, v);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) s[e] += v[e];
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                s[e] += __shfl_xor_sync(0xffffffffu, s[e], 8);
+                s[e] += __shfl_xor_sync(0xffffffffu, s[e], 16);
+            }
+            if (fq == 0) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) mean_s[warp][c8 * 8 + e][i] = pow2F ? s[e] * invF : s[e] / (float)F;
+            }
+        }
+        float ox[4], oy[4];
+        mlp4_warp(w_s, mean_s[warp], h_s[warp], lane, ox, oy);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (i < nf) *reinterpret_cast<float2*>(ta_out + (frame0 + i) * 64 + 2 * lane) = make_float2(sigmoidf_(ox[i]), sigmoidf_(oy[i]));
+        __syncwarp();
+    }
 }
 
 // CTFA stage 2 (see ctfa_gate_kernel) with one WARP per frame and the MLP weights staged once per CTA: lane l owns channels
