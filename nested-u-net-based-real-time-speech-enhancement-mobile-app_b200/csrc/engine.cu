@@ -1612,7 +1612,7 @@ struct Engine {
                 return;
             }
             if (pp->sh16 && F0 <= 64)
-                ctfa_ta_warp_sh_kernel<<<std::min((frames + 31) / 32, E.num_sms * 4), 256, 0, r.st>>>(
+                ctfa_ta_warp_sh_kernel<<<std::min((frames + 31) / 32, E.num_sms * 3), 256, 0, r.st>>>(
                     reinterpret_cast<const uint8_t*>(pp->cur(x, r.parity)), E.mlpw(mta), pp->cur(ta, 0), F0, (long long)frames);
             else if (pp->sh16)
                 ctfa_ta_sh_kernel<<<(frames + CTFA_FPB - 1) / CTFA_FPB, 256, 0, r.st>>>(

@@ -177,9 +177,9 @@ __device__ __forceinline__ void mlp4_warp(const MlpSmem& m, const float (*v_s)[4
     oy[0] = y01.x; oy[1] = y01.y; oy[2] = y23.x; oy[3] = y23.y;
 }
 
-// CTFA stage 1 for blocks with few bins (F <= 64): one WARP per group of four frames, grid-stride.  Lane (c8 = lane & 7,
-// fq = lane >> 3) sums chunk c8 over the bins f = fq, fq + 4, ..: one load instruction of the warp reads four neighbouring
-// positions (64 contiguous bytes) of each of the eight planes; the four frames of a group go one after the other, then their
+// CTFA stage 1 for blocks with few bins (F <= 64): one WARP per group of four frames, grid-stride.  Lane (c4 = lane >> 3,
+// fq = lane & 7) sums chunks c4 and c4 + 4 over the bins f = fq, fq + 8, ..: one load instruction of the warp reads eight
+// neighbouring positions (128 contiguous bytes) of four planes; the four frames of a group go one after the other, then their
 // MLPs run together (mlp4_warp: a per-frame MLP keeps 16 lanes busy and was a third of this kernel's instructions).  The
 // CTA-per-four-frames kernel above spends ~10 us of fixed latency per CTA, which is all there is at F <= 32; this one does not.
 __global__ void __launch_bounds__(256) ctfa_ta_warp_sh_kernel(const uint8_t* __restrict__ x, MlpW ta, float* __restrict__ ta_out, int F,
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(256) ctfa_ta_warp_sh_kernel(const uint8_t* __r
     mlp_stage(w_s, ta);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int c8 = lane & 7, fq = lane >> 3;
+    const int c4 = lane >> 3, fq = lane & 7;
     // F is a power of two in every block of the topology: multiplying by the (exact) reciprocal is the same rounding as the
     // division of the reference's mean and a tenth of its instructions
     const bool pow2F = (F & (F - 1)) == 0;
@@ -201,25 +201,37 @@ __global__ void __launch_bounds__(256) ctfa_ta_warp_sh_kernel(const uint8_t* __r
         const int nf = (int)min((long long)4, frames - frame0);
 #pragma unroll 1
         for (int i = 0; i < 4; ++i) {
-            float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            float s[2][8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s[0][e] = s[1][e] = 0.0f;
             if (i < nf) {
                 const uint8_t* row = x + (size_t)(frame0 + i) * F * 256;
-#pragma unroll 4
-                for (int f = fq; f < F; f += 4) {
-                    float v[8];
-                    sh16_load8(row, F, 64, f, c8, v);
+#pragma unroll 2
+                for (int f = fq; f < F; f += 8) {
+                    float v0[8], v1[8];
+                    sh16_load8(row, F, 64, f, c4, v0);
+                    sh16_load8(row, F, 64, f, c4 + 4, v1);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) s[e] += v[e];
+                    for (int e = 0; e < 8; ++e) {
+                        s[0][e] += v0[e];
+                        s[1][e] += v1[e];
+                    }
                 }
             }
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                s[e] += __shfl_xor_sync(0xffffffffu, s[e], 8);
-                s[e] += __shfl_xor_sync(0xffffffffu, s[e], 16);
-            }
+            for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    s[hh][e] += __shfl_xor_sync(0xffffffffu, s[hh][e], 1);
+                    s[hh][e] += __shfl_xor_sync(0xffffffffu, s[hh][e], 2);
+                    s[hh][e] += __shfl_xor_sync(0xffffffffu, s[hh][e], 4);
+                }
             if (fq == 0) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) mean_s[warp][c8 * 8 + e][i] = pow2F ? s[e] * invF : s[e] / (float)F;
+                for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        mean_s[warp][(c4 + 4 * hh) * 8 + e][i] = pow2F ? s[hh][e] * invF : s[hh][e] / (float)F;
             }
         }
         float ox[4], oy[4];
