@@ -469,6 +469,7 @@ struct Engine {
     int launches = 0;
     int last_B = 0, last_T = 0;
     int num_sms = 148;
+    bool lstm_stream = true; // NUNET_LSTM_STREAM=0 (experiments): streaming steps on lstm_block_kernel (one CTA per stream)
     bool ctfa_gate4 = true;  // NUNET_CTFA_GATE4=0 (experiments): the one-frame-per-warp gate kernel
     bool tc3_twin = true;    // NUNET_TC3_TWIN=0: no [even | odd] twins (stride-2 units then use strided boxes over bin-ordered sources)
     bool no_recycle = false; // NUNET_NO_RECYCLE (tests/layer_report.py): every offline tensor keeps its own storage
@@ -1356,6 +1357,19 @@ struct Engine {
                 hp = pp->carry_at(hc_off);
                 cp = hp + (size_t)pp->carry_cap * LSTM_UNITS;
                 zero_init = r.use_carry ? 0 : 1;
+            }
+            if (pp->streaming && r.T == 1 && hp && E.lstm_stream) {
+                // a streaming step: groups of 16 streams per CTA share the weight reads
+                const size_t sm2 = (size_t)LSTM_TB * (D + LSTM_GATES + 24) * sizeof(float);
+                const int grid = (r.B + LSTM_TB - 1) / LSTM_TB;
+                if (pp->sh16)
+                    lstm_stream_kernel<true><<<grid, LSTM_THREADS, sm2, r.st>>>(pp->cur(x, r.parity), E.pool.at(L.wk4), E.pool.at(L.wr), E.pool.at(L.wb),
+                                                                           E.pool.at(L.dk), E.pool.at(L.db), hp, cp, pp->cur(o, r.parity), r.B, D, xC);
+                else
+                    lstm_stream_kernel<false><<<grid, LSTM_THREADS, sm2, r.st>>>(pp->cur(x, r.parity), E.pool.at(L.wk4), E.pool.at(L.wr), E.pool.at(L.wb),
+                                                                            E.pool.at(L.dk), E.pool.at(L.db), hp, cp, pp->cur(o, r.parity), r.B, D, xC);
+                E.check_launch("lstm", rows * 4.0 * (2.0 * D + 2 * LSTM_UNITS));
+                return;
             }
             // one CTA per clip / stream: projection, recurrence and Dense in one kernel (lstm_kernels.cuh)
             if (pp->sh16)
@@ -2416,6 +2430,7 @@ int nunet_create(const nunet_config* cfg, const void* blob, size_t blob_bytes, n
         E.no_recycle = knob("NUNET_NO_RECYCLE") != nullptr;
         if (const char* v = knob("NUNET_TC3_TWIN")) E.tc3_twin = atoi(v) != 0;
         if (const char* v = knob("NUNET_CTFA_GATE4")) E.ctfa_gate4 = atoi(v) != 0;
+        if (const char* v = knob("NUNET_LSTM_STREAM")) E.lstm_stream = atoi(v) != 0;
         if (const char* c = knob("NUNET_CONV")) {
             E.use_tc = strcmp(c, "simt") != 0;
         }

@@ -249,4 +249,148 @@ __global__ void __launch_bounds__(LSTM_THREADS, 2) lstm_block_kernel(const void*
     }
 }
 
+// Streaming step (T = 1): one CTA per group of LSTM_TB STREAMS.  lstm_block_kernel with T = 1 is one CTA per stream, each
+// reading the whole input kernel (D x 84 floats: 1024 streams x 43..86 KB from L2 per launch) for 28 working threads; here the
+// sixteen streams of a group share every weight read and all 256 threads work in each of the four phases (stage, project,
+// one recurrence step, Dense).  Every sum is formed exactly as in lstm_block_kernel (k ascending from the bias; three partial
+// sums per gate in the recurrence; j ascending in the Dense), so a stream's frames equal the offline kernel's bit for bit.
+template <bool SH>
+__global__ void __launch_bounds__(LSTM_THREADS) lstm_stream_kernel(const void* __restrict__ xv, const float* __restrict__ Wk4,
+                                                                  const float* __restrict__ Wr /*[21][84]*/, const float* __restrict__ bk /*[84]*/,
+                                                                  const float* __restrict__ Wd /*[21][D]*/, const float* __restrict__ bd /*[D]*/,
+                                                                  float* __restrict__ h_state, float* __restrict__ c_state /*[S][21]*/,
+                                                                  void* __restrict__ yv, int S, int D, int C) {
+    extern __shared__ __align__(16) float smem[];
+    float* xs = smem;                                  // [D][LSTM_TB]  (k-major)
+    float* xw = xs + LSTM_TB * D;                      // [LSTM_TB][84]
+    float* hs = xw + LSTM_TB * LSTM_GATES;             // [LSTM_TB][24]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int s0 = blockIdx.x * LSTM_TB, ns = min(LSTM_TB, S - s0);
+    const int Fb = D / C, D8 = D >> 3, C8 = C >> 3;
+    // ---- stage: x rows of the group -> fp32, k-major
+    if (SH) {
+        const uint8_t* xsh = reinterpret_cast<const uint8_t*>(xv) + (size_t)s0 * D * 4;
+        for (int it = tid; it < LSTM_TB * D8; it += LSTM_THREADS) {
+            const int r = it % LSTM_TB, k8 = it / LSTM_TB;
+            const int f = k8 / C8, c8 = k8 - f * C8;
+            float v[8];
+            if (r < ns) {
+                sh16_load8(xsh + (size_t)r * D * 4, Fb, C, f, c8, v);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = 0.0f;
+            }
+            float* dst = xs + (f * C + c8 * 8) * LSTM_TB + r;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) dst[e * LSTM_TB] = v[e];
+        }
+    } else {
+        const float* xf = reinterpret_cast<const float*>(xv) + (size_t)s0 * D;
+        for (int it = tid; it < LSTM_TB * (D >> 2); it += LSTM_THREADS) {
+            const int r = it % LSTM_TB, k4 = it / LSTM_TB;
+            const float4 v = (r < ns) ? __ldg(reinterpret_cast<const float4*>(xf + (size_t)r * D) + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float* dst = xs + (k4 * 4) * LSTM_TB + r;
+            dst[0] = v.x; dst[LSTM_TB] = v.y; dst[2 * LSTM_TB] = v.z; dst[3 * LSTM_TB] = v.w;
+        }
+    }
+    __syncthreads();
+    // ---- project: thread = (gate triple gg, stream pair sp), the pair packed in fp32x2
+    if (tid < 28 * (LSTM_TB / 2)) {
+        const int gg = tid % 28, sp = tid / 28;
+        float2 acc[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float bj = __ldg(bk + 3 * gg + j);
+            acc[j] = make_float2(bj, bj);
+        }
+        const float2* xr = reinterpret_cast<const float2*>(xs) + sp;                  // [k][8 stream pairs]
+        const float4* wp = reinterpret_cast<const float4*>(Wk4) + 3 * gg;
+        const int D4 = D >> 2;
+#pragma unroll 2
+        for (int k4 = 0; k4 < D4; ++k4) {
+            const float4 w0 = __ldg(wp + k4 * LSTM_GATES), w1 = __ldg(wp + k4 * LSTM_GATES + 1), w2 = __ldg(wp + k4 * LSTM_GATES + 2);
+            const float wv[3][4] = {{w0.x, w0.y, w0.z, w0.w}, {w1.x, w1.y, w1.z, w1.w}, {w2.x, w2.y, w2.z, w2.w}};
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const float2 x2 = xr[(k4 * 4 + kk) * (LSTM_TB / 2)];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) acc[j] = __ffma2_rn(x2, make_float2(wv[j][kk], wv[j][kk]), acc[j]);
+            }
+        }
+        float* dst = xw + (2 * sp) * LSTM_GATES + 3 * gg;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            dst[j] = acc[j].x;
+            dst[LSTM_GATES + j] = acc[j].y;
+        }
+    }
+    __syncthreads();
+    // ---- one recurrence step: warp w takes streams 2w and 2w + 1, lane u < 21 owns unit u
+    {
+        const int u = (lane < LSTM_UNITS) ? lane : 0;
+        float2 wif[LSTM_UNITS], wco[LSTM_UNITS];
+#pragma unroll
+        for (int k = 0; k < LSTM_UNITS; ++k) {
+            wif[k] = make_float2(__ldg(Wr + k * LSTM_GATES + u), __ldg(Wr + k * LSTM_GATES + LSTM_UNITS + u));
+            wco[k] = make_float2(__ldg(Wr + k * LSTM_GATES + 2 * LSTM_UNITS + u), __ldg(Wr + k * LSTM_GATES + 3 * LSTM_UNITS + u));
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int r = 2 * warp + q;
+            const bool live = r < ns && lane < LSTM_UNITS;
+            float h = 0.0f, c = 0.0f;
+            if (live) {
+                h = h_state[(size_t)(s0 + r) * LSTM_UNITS + lane];
+                c = c_state[(size_t)(s0 + r) * LSTM_UNITS + lane];
+            }
+            float2 zif[3], zco[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) zif[j] = zco[j] = make_float2(0.0f, 0.0f);
+#pragma unroll
+            for (int k = 0; k < LSTM_UNITS; ++k) {
+                const float hk = __shfl_sync(0xffffffffu, h, k);
+                const float2 hh = make_float2(hk, hk);
+                zif[k % 3] = __ffma2_rn(hh, wif[k], zif[k % 3]);
+                zco[k % 3] = __ffma2_rn(hh, wco[k], zco[k % 3]);
+            }
+            const float2 sif = __fadd2_rn(__fadd2_rn(zif[0], zif[1]), zif[2]), sco = __fadd2_rn(__fadd2_rn(zco[0], zco[1]), zco[2]);
+            const float* xg = xw + r * LSTM_GATES + u;
+            const float z0 = xg[0] + sif.x, z1 = xg[LSTM_UNITS] + sif.y, z2 = xg[2 * LSTM_UNITS] + sco.x, z3 = xg[3 * LSTM_UNITS] + sco.y;
+            const float gi = fast_sigmoid(z0), gf = fast_sigmoid(z1), gc = fast_tanh(z2), go = fast_sigmoid(z3);
+            c = fmaf(gf, c, gi * gc);
+            h = go * fast_tanh(c);
+            if (live) {
+                hs[r * 24 + lane] = h;
+                h_state[(size_t)(s0 + r) * LSTM_UNITS + lane] = h;
+                c_state[(size_t)(s0 + r) * LSTM_UNITS + lane] = c;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- Dense: item = 8 consecutive outputs of one stream
+    for (int it = tid; it < ns * D8; it += LSTM_THREADS) {
+        const int r = it / D8, k8 = it - r * D8;
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = __ldg(bd + k8 * 8 + e);
+        const float* hr = hs + r * 24;
+#pragma unroll
+        for (int j = 0; j < LSTM_UNITS; ++j) {
+            const float hj = hr[j];
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(Wd + (size_t)j * D + k8 * 8));
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(Wd + (size_t)j * D + k8 * 8) + 1);
+            o[0] = fmaf(hj, w0.x, o[0]); o[1] = fmaf(hj, w0.y, o[1]); o[2] = fmaf(hj, w0.z, o[2]); o[3] = fmaf(hj, w0.w, o[3]);
+            o[4] = fmaf(hj, w1.x, o[4]); o[5] = fmaf(hj, w1.y, o[5]); o[6] = fmaf(hj, w1.z, o[6]); o[7] = fmaf(hj, w1.w, o[7]);
+        }
+        if (SH) {
+            const int f = k8 / C8, c8 = k8 - f * C8;
+            sh16_store8(reinterpret_cast<uint8_t*>(yv) + (size_t)(s0 + r) * D * 4, Fb, C, f, c8, o);
+        } else {
+            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(yv) + (size_t)(s0 + r) * D + k8 * 8);
+            dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+            dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+        }
+    }
+}
+
 }  // namespace nunet

@@ -488,6 +488,26 @@ def test_kernel_variants_do_not_change_results(blob, ddb_weights, variant, knob,
         assert np.isfinite(a).all() and np.array_equal(a, g)
 
 
+def test_streaming_lstm_group_kernel_equals_per_stream_kernel(blob, monkeypatch):
+    """A streaming step runs the LSTM bottlenecks on lstm_stream_kernel (16 streams per CTA share the weight reads); every sum
+    is formed as in lstm_block_kernel (one CTA per stream, NUNET_LSTM_STREAM=0), so the two agree bit for bit -- 37 streams
+    (two full groups and a partial one), 6 hops, states carried."""
+    from nunet_b200.engine import NunetEngine
+    from nunet_b200.synth import synth_clips
+    S, steps = 37, 6
+    wav = synth_clips(S, 256 * steps, first_clip=410)
+    outs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("NUNET_DEBUG_KNOBS", "1")
+        monkeypatch.setenv("NUNET_LSTM_STREAM", mode)
+        eng = NunetEngine(blob, max_streams=S)
+        eng.stream_reset()
+        outs[mode] = [eng.stream_step_wav(torch.from_numpy(wav[:, 256 * t:256 * (t + 1)]).cuda()).cpu().numpy().copy() for t in range(steps)]
+        eng.close()
+    for a, g in zip(outs["1"], outs["0"]):
+        assert np.isfinite(a).all() and np.array_equal(a, g)
+
+
 def test_full_size_batch_properties(blob, oracles):
     """BASELINE configs[1] at FULL size (256 clips x 4 s = 63 744 frames, the bench workload), checked through properties
     that do not need an oracle run of that size: (a) copies of one clip anywhere in the batch come out bit-identical
