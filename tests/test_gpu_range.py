@@ -270,3 +270,40 @@ def test_signature_runner_detects_foreign_steps_resets_and_edits(weights, oracle
 def _shapes(run):
     """signature input name -> shape ('msfe6_ee_prev1' has the shape of 'msfe6_ee_cur1'; LSTM states keep their name)"""
     return {n: run._shapes[n.replace("_prev", "_cur")] for n in run.input_names() if n != "input"}
+
+
+def test_unaligned_wav_and_hop_pointers(blob):
+    """The framing kernels move samples as 8-byte pairs when they can; a clip whose length is odd puts every second clip of a
+    batch on a 4-byte boundary, and a caller may hand over a hop buffer that is a view at an odd offset.  Both take the scalar
+    path and must give what the aligned call gives, bit for bit."""
+    from nunet_b200.engine import NunetEngine
+    from nunet_b200.synth import synth_clips
+    B, T = 3, 10
+    N = 512 + 256 * (T - 1) + 1                                   # odd: the last sample belongs to no frame
+    wav = torch.from_numpy(synth_clips(B, N, first_clip=520)).cuda()
+    eng = NunetEngine(blob, max_frames=B * T, max_streams=4)
+    y, est = eng.forward_wav(wav)
+    for b in range(B):
+        y1, est1 = eng.forward_wav(wav[b:b + 1].clone())
+        assert torch.equal(y1[0], y[b]) and torch.equal(est1[0], est[b]), b
+    S, steps = 4, 3
+    hops = torch.from_numpy(synth_clips(S, 256 * steps, first_clip=530)).cuda()
+    outs = []
+    for mode in ("aligned", "odd"):
+        eng.stream_reset()
+        ys = []
+        for t in range(steps):
+            hop = hops[:, 256 * t:256 * (t + 1)].contiguous()
+            if mode == "odd":
+                raw_in = torch.zeros(S * 256 + 1, device="cuda")
+                raw_out = torch.zeros(S * 256 + 1, device="cuda")
+                hin, hout = raw_in[1:].view(S, 256), raw_out[1:].view(S, 256)
+                assert hin.data_ptr() % 8 == 4 and hout.data_ptr() % 8 == 4
+                hin.copy_(hop)
+                eng.stream_step_wav(hin, hout)
+                ys.append(hout.clone())
+            else:
+                ys.append(eng.stream_step_wav(hop).clone())
+        outs.append(torch.stack(ys))
+    assert torch.isfinite(outs[0]).all() and torch.equal(outs[0], outs[1])
+    eng.close()
