@@ -142,7 +142,8 @@ struct Tc3Params {
     int tm_box_bytes;      // tm_rows * P * 16
     alignas(64) CUtensorMap tm_map[2];   // src0 / src1
     unsigned long long* timing;   // experiments: CTA 0 writes per-role cycle counters here (null = off)
-    int dbg;               // experiments only: 1 = no loads, 2 = no stores, 4 = no MMAs, 8 = no LN/split math
+    int dbg;               // experiments only: 1 = no loads, 2 = no stores, 8 = no LN/split math (the MMA-side switches of round 1
+                           // are gone: their tests sat in the issue loop, whose instruction count is on the critical path)
 };
 
 // mbarrier wait for warps that are NOT on the critical path (epilogue, loaders): the try_wait carries a suspend-time
@@ -272,6 +273,72 @@ __device__ __forceinline__ void tc_mma_f16_w(uint32_t d_tmem, uint32_t a_low, ui
         "setp.ne.b32 p, %6, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
         "}" ::"r"(d_tmem), "r"(a_low), "r"(a_high), "r"(b_low), "r"(b_high), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// All MMAs of ONE tap in one asm block.  The issuing thread's instruction stream is on the critical path of the small-N units
+// (a tap's MMAs keep the tensor pipe busy for ~100 cycles and the pipe queues only a few of them), so the descriptors are
+// assembled with the fewest instructions: one predicate, one B descriptor, the A descriptors by 32-bit adds on the low word.
+//   one tile:   a_hi x [b_hi | b_lo] -> d0 (2N columns),  a_lo x b_hi -> d0 (N columns)
+//   two tiles:  the same for the second tile (a + t2 -> d1), interleaved so that back-to-back MMAs never chain on one accumulator
+__device__ __forceinline__ void tc_mma_tap1(uint32_t d0, uint32_t a_low, uint32_t a_lo_delta, uint32_t a_high, uint32_t b_low,
+                                            uint32_t b_high, uint32_t idesc_2n, uint32_t idesc_n, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 al;\n\t"
+        ".reg .b64 da, dl, db;\n\t"
+        "setp.ne.b32 p, %8, 0;\n\t"
+        "mov.b64 db, {%4, %5};\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "add.u32 al, %1, %2;\n\t"
+        "mov.b64 dl, {al, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %6, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], dl, db, %7, 1;\n\t"
+        "}" ::"r"(d0), "r"(a_low), "r"(a_lo_delta), "r"(a_high), "r"(b_low), "r"(b_high), "r"(idesc_2n), "r"(idesc_n), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_tap2(uint32_t d0, uint32_t d1, uint32_t a_low, uint32_t t2, uint32_t a_lo_delta, uint32_t a_high,
+                                            uint32_t b_low, uint32_t b_high, uint32_t idesc_2n, uint32_t idesc_n, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 a1, al0, al1;\n\t"
+        ".reg .b64 da0, da1, dl0, dl1, db;\n\t"
+        "setp.ne.b32 p, %10, 0;\n\t"
+        "mov.b64 db, {%6, %7};\n\t"
+        "add.u32 a1, %2, %3;\n\t"
+        "add.u32 al0, %2, %4;\n\t"
+        "add.u32 al1, a1, %4;\n\t"
+        "mov.b64 da0, {%2, %5};\n\t"
+        "mov.b64 da1, {a1, %5};\n\t"
+        "mov.b64 dl0, {al0, %5};\n\t"
+        "mov.b64 dl1, {al1, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da0, db, %8, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], da1, db, %8, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], dl0, db, %9, 1;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], dl1, db, %9, 1;\n\t"
+        "}" ::"r"(d0), "r"(d1), "r"(a_low), "r"(t2), "r"(a_lo_delta), "r"(a_high), "r"(b_low), "r"(b_high), "r"(idesc_2n), "r"(idesc_n),
+        "r"(accumulate)
+        : "memory");
+}
+// pair mode: a_hi x [b_hi | b_lo] of both halves -> d0 (4N columns), a_lo x b_hi of both halves -> d0 + N (2N columns)
+__device__ __forceinline__ void tc_mma_tap_pair(uint32_t d0, uint32_t d0n, uint32_t a_low, uint32_t a_lo_delta, uint32_t a_high, uint32_t b_low,
+                                                uint32_t b_high, uint32_t idesc_4n, uint32_t idesc_2n, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 al;\n\t"
+        ".reg .b64 da, dl, db;\n\t"
+        "setp.ne.b32 p, %9, 0;\n\t"
+        "mov.b64 db, {%5, %6};\n\t"
+        "mov.b64 da, {%2, %4};\n\t"
+        "add.u32 al, %2, %3;\n\t"
+        "mov.b64 dl, {al, %4};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %7, p;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%1], dl, db, %8, 1;\n\t"
+        "}" ::"r"(d0), "r"(d0n), "r"(a_low), "r"(a_lo_delta), "r"(a_high), "r"(b_low), "r"(b_high), "r"(idesc_4n), "r"(idesc_2n),
+        "r"(accumulate)
+        : "memory");
 }
 
 __device__ __forceinline__ void cp_async16_s(uint32_t smem_dst, const void* gsrc, int src_bytes) {
@@ -853,6 +920,8 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
         const uint32_t t2 = (uint32_t)p.tile2_off;                 // second tile of an iteration, in image positions
         uint32_t tap_img1 = 0;                                     // bit tap: the tap reads image 1
         for (int tap = 0; tap < p.ntaps; ++tap) tap_img1 |= (uint32_t)p.tap_img[tap] << tap;
+        const int ntaps = p.ntaps;
+        const bool mt2 = p.mt == 2;
         if (PAIR && half == 1) {
             // The partner of the leader issues no MMAs: it forwards "my image landed" and "my accumulator is drained" to the
             // leader's barriers, in the order the leader waits for them.
@@ -891,6 +960,9 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
                     adj1 = (uint32_t)(tg.xoff + p.tm_delta[1] + (p.tm_img_bytes >> 4) - p.slots);
                 }
             }
+            uint32_t toff[T3_MAXTAPS];   // image offset of every tap for this tile
+#pragma unroll
+            for (int tap = 0; tap < T3_MAXTAPS; ++tap) toff[tap] = tapd[tap] + (((tap_img1 >> tap) & 1u) ? adj1 : adj0);
             const long long tm0 = clock64();
             if (it >= 2) {
                 mbar_wait(&acc_empty[accb], ((it >> 1) - 1) & 1);
@@ -911,28 +983,29 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
                 tm_full += clock64() - tm1;
                 if (leader) {
                     const uint32_t alow = da_low0 + (uint32_t)buf * abuf16;
+                    if (PAIR) {
 #pragma unroll
-                    for (int tap = 0; tap < T3_MAXTAPS; ++tap) {
-                        if (tap < p.ntaps) {
-                            const uint32_t acc = (ph == 0 && tap == 0) ? 0u : 1u;
-                            if (!(p.dbg & 4)) {
-                                uint32_t al = alow + tapd[tap] + (((tap_img1 >> tap) & 1u) ? adj1 : adj0);
-                                if (p.dbg & 16) al &= ~7u;
-                                if (PAIR) {
-                                    tc_mma_f16_w2(d0, al, da_hiw, wlow, db_hiw, IDESC_P4N, acc);                             // a_hi x [b_hi | b_lo] of both halves
-                                    if (!(p.dbg & 64)) tc_mma_f16_w2(d0 + N, al + a_lo_delta, da_hiw, wlow, db_hiw, IDESC_P2N, 1u);   // a_lo x b_hi of both halves
-                                } else {
-                                // the two tiles' accumulators alternate, so back-to-back MMAs never chain on one accumulator
-                                tc_mma_f16_w(d0, al, da_hiw, wlow, db_hiw, IDESC_2N, acc);                                   // a_hi x [b_hi | b_lo]
-                                if (p.mt == 2) tc_mma_f16_w(d0 + 2 * N, al + t2, da_hiw, wlow, db_hiw, IDESC_2N, acc);
-                                if (!(p.dbg & 64)) {
-                                    tc_mma_f16_w(d0, al + a_lo_delta, da_hiw, wlow, db_hiw, IDESC_N, 1u);                    // a_lo x b_hi
-                                    if (p.mt == 2) tc_mma_f16_w(d0 + 2 * N, al + t2 + a_lo_delta, da_hiw, wlow, db_hiw, IDESC_N, 1u);
-                                }
-                                }
+                        for (int tap = 0; tap < T3_MAXTAPS; ++tap)
+                            if (tap < ntaps) {
+                                tc_mma_tap_pair(d0, d0 + N, alow + toff[tap], a_lo_delta, da_hiw, wlow, db_hiw, IDESC_P4N, IDESC_P2N,
+                                                (tap == 0) ? (uint32_t)ph : 1u);
+                                wlow += N * 4;   // next (phase, tap) stage: N * 64 bytes
                             }
-                            wlow += N * 4;   // next (phase, tap) stage: N * 64 bytes
-                        }
+                    } else if (mt2) {
+#pragma unroll
+                        for (int tap = 0; tap < T3_MAXTAPS; ++tap)
+                            if (tap < ntaps) {
+                                tc_mma_tap2(d0, d0 + 2 * N, alow + toff[tap], t2, a_lo_delta, da_hiw, wlow, db_hiw, IDESC_2N, IDESC_N,
+                                            (tap == 0) ? (uint32_t)ph : 1u);
+                                wlow += N * 4;
+                            }
+                    } else {
+#pragma unroll
+                        for (int tap = 0; tap < T3_MAXTAPS; ++tap)
+                            if (tap < ntaps) {
+                                tc_mma_tap1(d0, alow + toff[tap], a_lo_delta, da_hiw, wlow, db_hiw, IDESC_2N, IDESC_N, (tap == 0) ? (uint32_t)ph : 1u);
+                                wlow += N * 4;
+                            }
                     }
                     if (PAIR) tc_commit_pair(&a_empty[buf]);
                     else if (p.cluster) tc_commit_mc(&a_empty[buf], (uint16_t)3);
