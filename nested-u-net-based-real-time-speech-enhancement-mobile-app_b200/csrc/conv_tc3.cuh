@@ -471,6 +471,10 @@ __device__ __forceinline__ void split8p(const float2* v, uint4& hi, uint4& lo) {
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// cycle counter for the per-role profile (Tc3Params::timing); not read at all in normal runs -- the reads sat in the loops whose
+// instruction count matters
+__device__ __forceinline__ long long t3_clock(bool timed) { return timed ? clock64() : 0ll; }
+
 // N: conv channels of this CTA (32 / 64); PC: channels per OUTPUT pixel (N, or 32 for the 64-column sub-pixel
 // shuffle that makes two pixels); LN: LayerNorm + PReLU over each PC-channel group (false: bias only).
 // PAIR: the cta_group::2 variant (must be launched as 2-CTA clusters; Tc3Params::pair set)
@@ -496,6 +500,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
     // weight load -- none of which depends on this kernel's output) on SMs that this grid has already left.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool timed = p.timing != nullptr;
     constexpr int MMA_WARP = T3_EPI_WARPS + T3_LD_WARPS;
     constexpr uint32_t ACC_COLS = 2 * T3_MT * 2 * N;   // 2 buffers x 2 tiles x (N + N) columns
     constexpr uint32_t TMEM_COLS = ACC_COLS <= 32 ? 32 : (ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512)));
@@ -573,15 +578,15 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
         const long long out_rs = (long long)p.F_out * (PC * 4);   // bytes per output frame row
         const long long plane = (long long)p.F_out * 16;          // bytes per output plane
         long long t_wait = 0, t_ld = 0;                           // per-role cycle counters (Tc3Params::timing)
-        const long long t_begin = clock64();
+        const long long t_begin = t3_clock(timed);
         for (int it = 0; it < my_tiles; ++it) {
             const int mt = (p.mt == 2) ? eg : 0;
             if (p.mt == 1 && !PAIR && (it & 1) != eg) continue;
             const int ab = it & 1;
-            const long long tq0 = clock64();
+            const long long tq0 = t3_clock(timed);
             mbar_wait_relaxed(&acc_full[ab], (it >> 1) & 1);
             tc_fence_after();
-            const long long tq1 = clock64();
+            const long long tq1 = t3_clock(timed);
             t_wait += tq1 - tq0;
             // pair accumulator: [hh | hl + lh] of half 0, then [hh + lh | hl] of half 1 (the a_lo x b_hi product lands on columns N .. 3N)
             const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(PAIR ? (ab * 2 + eg) * 2 * N : (ab * p.mt + mt) * 2 * N);
@@ -614,7 +619,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
             // the accumulator is in registers: hand the TMEM buffer back to the MMA warp right away
             tc_fence_before();
             mbar_arrive(&acc_empty[ab]);
-            t_ld += clock64() - tq1;
+            t_ld += t3_clock(timed) - tq1;
             {
                 const float2 sc = make_float2(p.wscale_inv, p.wscale_inv);
 #pragma unroll
@@ -676,7 +681,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
         if (p.timing && blockIdx.x == 0 && threadIdx.x == 0) {
             p.timing[4] = (unsigned long long)t_wait;
             p.timing[5] = (unsigned long long)t_ld;
-            p.timing[6] = (unsigned long long)(clock64() - t_begin);
+            p.timing[6] = (unsigned long long)(t3_clock(timed) - t_begin);
         }
     } else if (warp < MMA_WARP) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T3_REGS_LD));
@@ -698,7 +703,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
         const int NB = p.nabuf;
         const float rcpP = 1.0f / (float)p.P, rcpTp = 1.0f / (float)Tp;
         long long tl_table = 0, tl_wait = 0, tl_fence = 0, tl_issue = 0;   // per-role cycle counters (Tc3Params::timing)
-        const long long tl_begin = clock64();
+        const long long tl_begin = t3_clock(timed);
         // Our sources are the previous kernels' outputs: wait for them (programmatic dependent launch) -- but only right before
         // the first copy, so that the slot table of the first tile is built while the previous kernel drains.
         bool dep_waited = false;
@@ -712,7 +717,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
         int g = 0;
         for (int it = 0; it < my_tiles; ++it) {
             const int q0 = tile_q(it, half) - p.lead;
-            const long long tl0 = clock64();
+            const long long tl0 = t3_clock(timed);
             if (p.tma == 2) {
                 const T3TileGeo tg = t3_tile_geo(q0, p.P, Tp, p.padrow, p.slots, max(p.tm_delta[0], p.tm_delta[1]), p.tm_dmin, p.prev_rows);
                 // pair mode: one A descriptor serves both CTAs, so both must use the same image layout
@@ -722,9 +727,9 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
                     dep_wait();
                     // one box per image into this warp's plane; 32 arrivals per warp keep the barrier count of the fallback
                     for (int ph = 0; ph < p.nphase; ++ph, ++g) {
-                        const long long tl1 = clock64();
+                        const long long tl1 = t3_clock(timed);
                         if (g >= NB) mbar_wait_relaxed(&a_empty[buf], round ^ 1);
-                        const long long tl2 = clock64();
+                        const long long tl2 = t3_clock(timed);
                         tl_wait += tl2 - tl1;
                         if (lane == 0) {
                             const int c0 = ph * T3_KCH;
@@ -746,7 +751,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
                             mbar_arrive_n(&a_full[buf], 32);
                         }
                         __syncwarp();
-                        tl_issue += clock64() - tl2;
+                        tl_issue += t3_clock(timed) - tl2;
                         if (++buf == NB) {
                             buf = 0;
                             round ^= 1;
@@ -814,12 +819,12 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
                     seg_n = xb - xa;
                 }
             }
-            tl_table += clock64() - tl0;
+            tl_table += t3_clock(timed) - tl0;
             dep_wait();
             for (int ph = 0; ph < p.nphase; ++ph, ++g) {
-                const long long tl1 = clock64();
+                const long long tl1 = t3_clock(timed);
                 if (g >= NB) mbar_wait_relaxed(&a_empty[buf], round ^ 1);
-                tl_wait += clock64() - tl1;
+                tl_wait += t3_clock(timed) - tl1;
                 const int c0 = ph * T3_KCH;
                 const bool first = c0 < p.C0;
                 const uint8_t* src = first ? p.src0 : p.src1;
@@ -831,7 +836,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
                 const int* tb = slot_tbl + e0;
                 if (p.tma == 1) {
                     // zero the pad slots of this plane (generic proxy), then hand the row segments to the copy engine
-                    const long long tf0 = clock64();
+                    const long long tf0 = t3_clock(timed);
                     if (padmask) {
                         for (uint32_t m = padmask; m; m &= m - 1) {
                             const int k = __ffs(m) - 1;
@@ -839,7 +844,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
                         }
                         fence_proxy_async();
                     }
-                    const long long tf1 = clock64();
+                    const long long tf1 = t3_clock(timed);
                     tl_fence += tf1 - tf0;
                     if (seg_n > 0 && !(p.dbg & 1)) {
                         mbar_expect_tx(&a_full[buf], (uint32_t)seg_n * 16);
@@ -849,7 +854,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
                         else if (part == half)      // CTA 0 fetches the hi planes, CTA 1 the lo planes, for both CTAs
                             bulk_g2s_mc(dstp, pb + (long long)seg_src * 16, (uint32_t)seg_n * 16, &a_full[buf], (uint16_t)3);
                     }
-                    tl_issue += clock64() - tf1;
+                    tl_issue += t3_clock(timed) - tf1;
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&a_full[buf]);
                 } else {
@@ -876,7 +881,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
         if (p.timing && blockIdx.x == 0 && lt == 0) {
             p.timing[7] = (unsigned long long)tl_wait;
             p.timing[8] = (unsigned long long)tl_table;
-            p.timing[9] = (unsigned long long)(clock64() - tl_begin);
+            p.timing[9] = (unsigned long long)(t3_clock(timed) - tl_begin);
             p.timing[10] = (unsigned long long)tl_fence;
             p.timing[11] = (unsigned long long)tl_issue;
         }
@@ -916,7 +921,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
             tapd[tap] = (tap < p.ntaps) ? (uint32_t)(p.tap_img[tap] * p.slots + p.tap_off[tap]) : 0u;
         int buf = 0, round = 0;
         long long tm_full = 0, tm_acc = 0;                         // per-role cycle counters (Tc3Params::timing)
-        const long long tm_begin = clock64();
+        const long long tm_begin = t3_clock(timed);
         const uint32_t t2 = (uint32_t)p.tile2_off;                 // second tile of an iteration, in image positions
         uint32_t tap_img1 = 0;                                     // bit tap: the tap reads image 1
         for (int tap = 0; tap < p.ntaps; ++tap) tap_img1 |= (uint32_t)p.tap_img[tap] << tap;
@@ -963,24 +968,24 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
             uint32_t toff[T3_MAXTAPS];   // image offset of every tap for this tile
 #pragma unroll
             for (int tap = 0; tap < T3_MAXTAPS; ++tap) toff[tap] = tapd[tap] + (((tap_img1 >> tap) & 1u) ? adj1 : adj0);
-            const long long tm0 = clock64();
+            const long long tm0 = t3_clock(timed);
             if (it >= 2) {
                 mbar_wait(&acc_empty[accb], ((it >> 1) - 1) & 1);
                 if (PAIR) mbar_wait(&peer_acc_empty[accb], ((it >> 1) - 1) & 1);
             }
             tc_fence_after();
-            tm_acc += clock64() - tm0;
+            tm_acc += t3_clock(timed) - tm0;
             uint32_t wlow = db_low0;
             const uint32_t d0 = tmem_base + (uint32_t)(PAIR ? accb * 4 * N : accb * p.mt * 2 * N);
             for (int ph = 0; ph < p.nphase; ++ph) {
-                const long long tm1 = clock64();
+                const long long tm1 = t3_clock(timed);
                 mbar_wait(&a_full[buf], round);
                 if (PAIR) mbar_wait(&peer_full[buf], round);   // (a cluster-scope acquire here costs ~1000 cycles per wait: measured)
                 // cp.async / st.shared wrote through the generic proxy, the MMA reads through the async proxy; tensor-box tiles
                 // were written by the copy engine itself and need no proxy fence
                 if (!boxed && p.fence_mode != 2) fence_proxy_async();
                 tc_fence_after();
-                tm_full += clock64() - tm1;
+                tm_full += t3_clock(timed) - tm1;
                 if (leader) {
                     const uint32_t alow = da_low0 + (uint32_t)buf * abuf16;
                     if (PAIR) {
@@ -1024,7 +1029,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
             __syncwarp();
         }
         if (p.timing && blockIdx.x == 0 && lane == 0) {
-            p.timing[0] = (unsigned long long)(clock64() - tm_begin);
+            p.timing[0] = (unsigned long long)(t3_clock(timed) - tm_begin);
             p.timing[1] = (unsigned long long)tm_full;
             p.timing[2] = (unsigned long long)tm_acc;
             p.timing[3] = (unsigned long long)my_tiles;
