@@ -125,6 +125,7 @@ struct Tc3Params {
                            // ever computed and a tile image starts at a fixed offset of its first frame row (fewest box rows)
     int tile2_off;         // flat distance between the two tiles of an iteration (mt == 2): 128, or P for one row tile per row
     int prev_rows;         // 1: prev0 / prev1 hold the row in front of every clip (streaming step, or a later time chunk)
+    int ld_rr;             // tensor-box loaders: 1 = the warps take the ring buffers in turn, four lanes issue the four planes (see the loader)
     int tm_dmin;           // min(tm_delta): the image may start tm_dmin positions late without losing its first position
     int cluster;           // 1: launched as 2-CTA clusters (the two halves of a 128-channel unit): bulk copies are multicast
     int tma;               // 1: row segments move with 1-D bulk copies; 2: whole tile images move as tensor-map boxes (see tm*)
@@ -725,33 +726,42 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
                                                           max(p.tm_delta[0], p.tm_delta[1]), p.tm_dmin, p.prev_rows).box : 1;
                 if (tg.box && peer_box) {
                     dep_wait();
-                    // one box per image into this warp's plane; 32 arrivals per warp keep the barrier count of the fallback
+                    // One box per (plane, image).  Default: loader warp w issues plane w of every phase (lane 0); 32 arrivals per
+                    // plane keep the barrier count of the fallback.  Issuing a box costs the lane ~500 cycles (expect_tx, the tensor
+                    // copy, the arrival), which bounds units with many short phases (up_sampling o inconv: 8 phases of 2 taps): for
+                    // those (Tc3Params::ld_rr) the warps take the BUFFERS in turn and lanes 0-3 issue the four planes at once.  (A
+                    // buffer always belongs to the same warp, so its waits on that buffer's barrier stay in order -- a warp that
+                    // skipped a use could mistake an older completed phase of the same parity for the one it needs.)
+                    const bool rr = p.ld_rr != 0;
                     for (int ph = 0; ph < p.nphase; ++ph, ++g) {
-                        const long long tl1 = t3_clock(timed);
-                        if (g >= NB) mbar_wait_relaxed(&a_empty[buf], round ^ 1);
-                        const long long tl2 = t3_clock(timed);
-                        tl_wait += tl2 - tl1;
-                        if (lane == 0) {
-                            const int c0 = ph * T3_KCH;
-                            const bool first = c0 < p.C0;
-                            const int cc = first ? c0 : c0 - p.C0;
-                            const int plane = part * cpp0 + (cc >> 3) + chunk;
-                            const CUtensorMap* map = &p.tm_map[first ? 0 : 1];
-                            uint8_t* dstp = abuf0 + (size_t)buf * abuf_bytes + (size_t)lw * p.plane_bytes;
-                            if (!(p.dbg & 1)) {
-                                mbar_expect_tx(&a_full[buf], (uint32_t)(p.nimg * p.tm_box_bytes));
-                                for (int img = 0; img < p.nimg; ++img) {
-                                    const int pl = p.src_eo ? 2 * plane + p.tm_par[img] : plane;
-                                    if (p.tm_rank == 4)
-                                        tensor_g2s_4d(dstp + (size_t)img * p.tm_img_bytes, map, p.tm_c[img], pl, tg.t, tg.b, &a_full[buf]);
-                                    else
-                                        tensor_g2s_5d(dstp + (size_t)img * p.tm_img_bytes, map, 0, p.tm_c[img], pl, tg.t, tg.b, &a_full[buf]);
+                        if (!rr || (buf & (T3_LD_WARPS - 1)) == lw) {
+                            const long long tl1 = t3_clock(timed);
+                            if (g >= NB) mbar_wait_relaxed(&a_empty[buf], round ^ 1);
+                            const long long tl2 = t3_clock(timed);
+                            tl_wait += tl2 - tl1;
+                            if (rr ? (lane < 4) : (lane == 0)) {
+                                const int pw = rr ? lane : lw;              // plane of the buffer this lane fills
+                                const int c0 = ph * T3_KCH;
+                                const bool first = c0 < p.C0;
+                                const int cc = first ? c0 : c0 - p.C0;
+                                const int plane = (pw >> 1) * cpp0 + (cc >> 3) + (pw & 1);
+                                const CUtensorMap* map = &p.tm_map[first ? 0 : 1];
+                                uint8_t* dstp = abuf0 + (size_t)buf * abuf_bytes + (size_t)pw * p.plane_bytes;
+                                if (!(p.dbg & 1)) {
+                                    mbar_expect_tx(&a_full[buf], (uint32_t)(p.nimg * p.tm_box_bytes));
+                                    for (int img = 0; img < p.nimg; ++img) {
+                                        const int pl = p.src_eo ? 2 * plane + p.tm_par[img] : plane;
+                                        if (p.tm_rank == 4)
+                                            tensor_g2s_4d(dstp + (size_t)img * p.tm_img_bytes, map, p.tm_c[img], pl, tg.t, tg.b, &a_full[buf]);
+                                        else
+                                            tensor_g2s_5d(dstp + (size_t)img * p.tm_img_bytes, map, 0, p.tm_c[img], pl, tg.t, tg.b, &a_full[buf]);
+                                    }
                                 }
+                                mbar_arrive_n(&a_full[buf], 32);
                             }
-                            mbar_arrive_n(&a_full[buf], 32);
+                            __syncwarp();
+                            tl_issue += t3_clock(timed) - tl2;
                         }
-                        __syncwarp();
-                        tl_issue += t3_clock(timed) - tl2;
                         if (++buf == NB) {
                             buf = 0;
                             round ^= 1;

@@ -486,6 +486,7 @@ struct Engine {
     int tc3_row_tiles = 1;   // NUNET_TC3_ROW_TILES=0: flat 128-position tiles for every unit
     int tc3_pair = 1;        // NUNET_TC3_PAIR=0: 128-channel units run as two independent CTAs per tile instead of cta_group::2 pairs
     int tc3_pair_minf = 4;   // NUNET_TC3_PAIR_MINF (experiments)
+    bool tc3_ld_rr = true;   // NUNET_TC3_LD_RR=0 (experiments): one loader warp per plane in every unit
     int tc3_box_minf = 4;    // NUNET_TC3_BOX_MINF (experiments): smallest F_conv of a unit that uses tensor-map boxes
     int tc3_tma_minf = 32;   // NUNET_TC3_TMA_MINF (experiments): smallest F_in of a stride-1 unit that uses bulk copies
     int tc3_cluster = 0;     // NUNET_TC3_CLUSTER=1: the two CTAs of a 128-channel unit form a cluster and multicast their bulk copies
@@ -1176,6 +1177,8 @@ struct Engine {
         }
         p.row_tpr = row_tpr;
         p.tile2_off = tile2_off;
+        // units with many short phases (up_sampling o inconv: 8 phases of 2 taps) are bound by the box issue of one lane per plane
+        p.ld_rr = (tc3_ld_rr && box && p.ntaps <= 2 && p.nphase >= 8) ? 1 : 0;
         p.tm_dmin = 0;
         // 128-position tiles of the launch: consecutive runs of the flat axis, or row_tpr per frame row
         const long long units = row_tpr ? (long long)B * (T + p.padrow) * row_tpr : (total + 127) / 128;
@@ -2450,6 +2453,7 @@ int nunet_create(const nunet_config* cfg, const void* blob, size_t blob_bytes, n
         if (const char* c = knob("NUNET_FZ_DBG")) E.fz_dbg = atoi(c);
         if (const char* c = knob("NUNET_STREAM_SPLIT")) E.stream_split = std::max(1, std::min(4, atoi(c)));
         if (const char* c = knob("NUNET_TC3_PAIR_MINF")) E.tc3_pair_minf = atoi(c);
+        if (const char* c = knob("NUNET_TC3_LD_RR")) E.tc3_ld_rr = atoi(c) != 0;
         if (const char* c = knob("NUNET_TC3_BOX_STRIDED")) E.tc3_box_strided = atoi(c);
         if (const char* c = knob("NUNET_TC3_TMA_MINF")) E.tc3_tma_minf = std::max(8, atoi(c));
         if (const char* c = knob("NUNET_TC3_MT")) E.tc3_force_mt = atoi(c);
