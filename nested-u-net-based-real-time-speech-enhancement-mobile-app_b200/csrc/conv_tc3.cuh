@@ -46,7 +46,8 @@
 //                         cp.async.bulk.tensor box per tile image -- whole frame rows, pads and the causal time pad
 //                         zero-filled by the copy engine (Tc3Params::tm_*); tiles that straddle two clips, streaming
 //                         (history row from the other parity's buffer) and NUNET_TC3_TMA=0 use 16-byte cp.async from a
-//                         per-tile slot table; NUNET_TC3_TMA=1 uses 1-D bulk copies per frame-row segment
+//                         per-tile slot table; NUNET_TC3_TMA=1 uses 1-D bulk copies per frame-row segment.  Units with many
+//                         short phases let the warps take the ring buffers in turn, four lanes issuing the four planes (ld_rr)
 //   warp  12    MMA       one elected thread: tcgen05.mma kind::f16, M=128 (256 for pairs), K=16; accumulators
 //                         double-buffered in TMEM, buffers freed by tcgen05.commit
 // Tiles are consecutive runs of 128 flat positions, or, for units with a multiple of 128 output bins, 128-bin pieces
