@@ -126,6 +126,7 @@ struct Tc3Params {
                            // ever computed and a tile image starts at a fixed offset of its first frame row (fewest box rows)
     int tile2_off;         // flat distance between the two tiles of an iteration (mt == 2): 128, or P for one row tile per row
     int prev_rows;         // 1: prev0 / prev1 hold the row in front of every clip (streaming step, or a later time chunk)
+    unsigned long long mg_P, mg_Tp, mg_pair_m, mg_row_tpr;   // floor(2^64 / d) + 1 for d = P, T + padrow, pair_m, row_tpr (0: d = 1 or unused)
     int ld_rr;             // tensor-box loaders: 1 = the warps take the ring buffers in turn, four lanes issue the four planes (see the loader)
     int tm_dmin;           // min(tm_delta): the image may start tm_dmin positions late without losing its first position
     int cluster;           // 1: launched as 2-CTA clusters (the two halves of a 128-channel unit): bulk copies are multicast
@@ -204,6 +205,18 @@ __device__ __forceinline__ void tensor_g2s_5d(void* smem_dst, const CUtensorMap*
                  : "memory");
 }
 __device__ __forceinline__ int floor_div(int n, int d) { return (n >= 0) ? n / d : -((-n + d - 1) / d); }
+// Division by a launch constant through its reciprocal M = floor(2^64 / d) + 1 (Tc3Params::mg_*, 0 for d = 1): exact for every
+// 0 <= n < 2^32 and four multiply-adds instead of the ~40 instructions of an integer division -- the tile geometry below runs
+// once per tile in the loaders and the MMA warp (whose per-tile bookkeeping leaves the tensor pipe idle) and once per row in
+// the epilogue.
+__device__ __forceinline__ int fast_div(int n, uint64_t M) {
+    if (M == 0) return n;
+    const uint32_t mlo = (uint32_t)M, mhi = (uint32_t)(M >> 32);
+    const uint64_t t = (uint64_t)(uint32_t)n * mlo;
+    const uint64_t u = (uint64_t)(uint32_t)n * mhi + (t >> 32);
+    return (int)(u >> 32);
+}
+__device__ __forceinline__ int floor_div_m(int n, int d, uint64_t M) { return (n >= 0) ? fast_div(n, M) : -fast_div(-n + d - 1, M); }
 // tma == 2: does the tile whose image starts at flat position qa fit one clip (-> tensor-map boxes), and where does the
 // image start inside its first frame row?  Evaluated identically by the loaders and the MMA warp.
 struct T3TileGeo {
@@ -211,12 +224,13 @@ struct T3TileGeo {
     int xoff;      // qa - rho_a * P
     int b, t;      // clip and frame (may be -1: the causal pad row) of frame row rho_a
 };
-__device__ __forceinline__ T3TileGeo t3_tile_geo(int qa, int P, int Tp, int padrow, int slots, int dmax, int dmin, int prev_rows) {
+__device__ __forceinline__ T3TileGeo t3_tile_geo(int qa, int P, int Tp, int padrow, int slots, int dmax, int dmin, int prev_rows, uint64_t mgP,
+                                                  uint64_t mgTp) {
     T3TileGeo g;
-    const int rho_a = floor_div(qa + dmin, P);   // image index of flat position f is f - rho_a * P + delta >= 0
+    const int rho_a = floor_div_m(qa + dmin, P, mgP);   // image index of flat position f is f - rho_a * P + delta >= 0
     g.xoff = qa - rho_a * P;                      // >= -dmin
-    const int need = (g.xoff + dmax + slots - 1) / P + 1;       // frame rows the MMAs can touch
-    g.b = floor_div(rho_a, Tp);
+    const int need = fast_div(g.xoff + dmax + slots - 1, mgP) + 1;       // frame rows the MMAs can touch
+    g.b = floor_div_m(rho_a, Tp, mgTp);
     const int tp = rho_a - g.b * Tp;
     g.t = tp - padrow;
     // with carried history rows (time-chunked offline calls) the pad row in front of a clip is real data held in another
@@ -553,13 +567,13 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
         const int u = cta + it * ncta;
         int unit;                                  // index of the 128-position tile
         if (PAIR) {
-            const int blk = u / p.pair_m, j = u - blk * p.pair_m;
+            const int blk = fast_div(u, p.mg_pair_m), j = u - blk * p.pair_m;
             unit = blk * 2 * p.pair_m + j + r * p.pair_m;
         } else {
             unit = u * p.mt;
         }
         if (p.row_tpr == 0) return unit * 128;
-        const int rw = unit / p.row_tpr;
+        const int rw = fast_div(unit, p.mg_row_tpr);
         return rw * p.P + p.xlo + (unit - rw * p.row_tpr) * 128;
     };
 
@@ -637,9 +651,9 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
             }
             // where this row goes (computed only now: nothing of it has to stay live across the arithmetic above)
             const int q = tile_q(it, half) + mt * p.tile2_off + row;
-            const int rho = q / p.P;
+            const int rho = fast_div(q, p.mg_P);
             const int x = q - rho * p.P;
-            const int b = rho / Tp;
+            const int b = fast_div(rho, p.mg_Tp);
             const int t = (rho - b * Tp) - p.padrow;
             const bool valid = (q < p.total_flat) && (t >= 0) && (x >= p.xlo) && (x < p.xlo + p.F_conv);
             // output bins of this conv pixel: obin0 + g (g < NPX); storage position inside a plane of the frame row
@@ -721,10 +735,10 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
             const int q0 = tile_q(it, half) - p.lead;
             const long long tl0 = t3_clock(timed);
             if (p.tma == 2) {
-                const T3TileGeo tg = t3_tile_geo(q0, p.P, Tp, p.padrow, p.slots, max(p.tm_delta[0], p.tm_delta[1]), p.tm_dmin, p.prev_rows);
+                const T3TileGeo tg = t3_tile_geo(q0, p.P, Tp, p.padrow, p.slots, max(p.tm_delta[0], p.tm_delta[1]), p.tm_dmin, p.prev_rows, p.mg_P, p.mg_Tp);
                 // pair mode: one A descriptor serves both CTAs, so both must use the same image layout
                 const int peer_box = PAIR ? t3_tile_geo(tile_q(it, half ^ 1) - p.lead, p.P, Tp, p.padrow, p.slots,
-                                                          max(p.tm_delta[0], p.tm_delta[1]), p.tm_dmin, p.prev_rows).box : 1;
+                                                          max(p.tm_delta[0], p.tm_delta[1]), p.tm_dmin, p.prev_rows, p.mg_P, p.mg_Tp).box : 1;
                 if (tg.box && peer_box) {
                     dep_wait();
                     // One box per (plane, image).  Default: loader warp w issues plane w of every phase (lane 0); 32 arrivals per
@@ -947,8 +961,8 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
                     if (lane == 0) mbar_arrive_peer(&peer_acc_empty[it & 1], 0);
                 }
                 const int dm = max(p.tm_delta[0], p.tm_delta[1]);
-                const bool boxed = t3_tile_geo(tile_q(it, 0) - p.lead, p.P, Tp, p.padrow, p.slots, dm, p.tm_dmin, p.prev_rows).box &&
-                                   t3_tile_geo(tile_q(it, 1) - p.lead, p.P, Tp, p.padrow, p.slots, dm, p.tm_dmin, p.prev_rows).box;
+                const bool boxed = t3_tile_geo(tile_q(it, 0) - p.lead, p.P, Tp, p.padrow, p.slots, dm, p.tm_dmin, p.prev_rows, p.mg_P, p.mg_Tp).box &&
+                                   t3_tile_geo(tile_q(it, 1) - p.lead, p.P, Tp, p.padrow, p.slots, dm, p.tm_dmin, p.prev_rows, p.mg_P, p.mg_Tp).box;
                 for (int ph = 0; ph < p.nphase; ++ph) {
                     mbar_wait(&a_full[buf], round);
                     if (!boxed) fence_proxy_async();   // only the cp.async fallback writes through the generic proxy
@@ -967,9 +981,9 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
             uint32_t adj0 = 0, adj1 = 0;
             bool boxed = false;
             if (p.tma == 2) {
-                const T3TileGeo tg = t3_tile_geo(tile_q(it, 0) - p.lead, p.P, Tp, p.padrow, p.slots, max(p.tm_delta[0], p.tm_delta[1]), p.tm_dmin, p.prev_rows);
+                const T3TileGeo tg = t3_tile_geo(tile_q(it, 0) - p.lead, p.P, Tp, p.padrow, p.slots, max(p.tm_delta[0], p.tm_delta[1]), p.tm_dmin, p.prev_rows, p.mg_P, p.mg_Tp);
                 const int peer_box = PAIR ? t3_tile_geo(tile_q(it, 1) - p.lead, p.P, Tp, p.padrow, p.slots,
-                                                          max(p.tm_delta[0], p.tm_delta[1]), p.tm_dmin, p.prev_rows).box : 1;
+                                                          max(p.tm_delta[0], p.tm_delta[1]), p.tm_dmin, p.prev_rows, p.mg_P, p.mg_Tp).box : 1;
                 if (tg.box && peer_box) {
                     boxed = true;
                     adj0 = (uint32_t)(tg.xoff + p.tm_delta[0]);

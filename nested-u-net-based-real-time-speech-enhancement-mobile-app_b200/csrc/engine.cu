@@ -1177,6 +1177,12 @@ struct Engine {
         }
         p.row_tpr = row_tpr;
         p.tile2_off = tile2_off;
+        {   // reciprocals of the geometry's divisors (conv_tc3.cuh: fast_div)
+            auto magic = [](int d) -> unsigned long long { return d <= 1 ? 0ull : (unsigned long long)(~0ull / (unsigned long long)d) + 1ull; };
+            p.mg_P = magic(p.P);
+            p.mg_Tp = magic(T + p.padrow);
+            p.mg_row_tpr = magic(row_tpr);
+        }
         // units with many short phases (up_sampling o inconv: 8 phases of 2 taps) are bound by the box issue of one lane per plane
         p.ld_rr = (tc3_ld_rr && box && p.ntaps <= 2 && p.nphase >= 8) ? 1 : 0;
         p.tm_dmin = 0;
@@ -1188,6 +1194,7 @@ struct Engine {
             while (b) { const int r = g % b; g = b; b = r; }
             p.pair = 1;
             p.pair_m = row_tpr ? row_tpr : p.P / g;                      // tiles between the two CTAs of a pair: a whole number of frame rows
+            p.mg_pair_m = p.pair_m <= 1 ? 0ull : (~0ull / (unsigned long long)p.pair_m) + 1ull;
             p.ntiles = (int)((units + 2 * p.pair_m - 1) / (2 * p.pair_m)) * p.pair_m;   // cluster work units
         }
         const int grid = std::max(1, std::min(p.ntiles, num_sms / p.nhalf)) * p.nhalf;
