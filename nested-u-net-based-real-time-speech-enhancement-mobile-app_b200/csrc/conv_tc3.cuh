@@ -740,6 +740,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
                 const int peer_box = PAIR ? t3_tile_geo(tile_q(it, half ^ 1) - p.lead, p.P, Tp, p.padrow, p.slots,
                                                           max(p.tm_delta[0], p.tm_delta[1]), p.tm_dmin, p.prev_rows, p.mg_P, p.mg_Tp).box : 1;
                 if (tg.box && peer_box) {
+                    tl_table += t3_clock(timed) - tl0;      // (box tiles: the tile geometry)
                     dep_wait();
                     // One box per (plane, image).  Default: loader warp w issues plane w of every phase (lane 0); 32 arrivals per
                     // plane keep the barrier count of the fallback.  Issuing a box costs the lane ~500 cycles (expect_tx, the tensor
