@@ -403,8 +403,12 @@ __global__ void __launch_bounds__(256) gate_residual_sh_kernel(const uint8_t* __
                                                               const float* __restrict__ gate /*[frames][64]*/,
                                                               uint8_t* __restrict__ out, long long n8, int F, int in_eo, int out_eo) {
     const long long stride = (long long)gridDim.x * blockDim.x;
+    // F is a power of two in every block of the topology: a shift instead of a 64-bit division per item (the kernel runs at the
+    // HBM rate either way, but the division was two thirds of its instructions -- and the step is power-capped)
+    const bool pow2F = (F & (F - 1)) == 0;
+    const int lgF = 31 - __clz(F);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
-        const long long fc = i / F;                 // frame * 8 + chunk
+        const long long fc = pow2F ? (i >> lgF) : i / F;      // frame * 8 + chunk
         const int po = (int)(i - fc * F);           // output storage position
         const int f = out_eo ? ((po < (F >> 1)) ? 2 * po : 2 * (po - (F >> 1)) + 1) : po;   // its bin
         const int pi = sh16_pos(f, F, in_eo);
