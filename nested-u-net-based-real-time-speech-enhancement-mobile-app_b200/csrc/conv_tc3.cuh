@@ -790,9 +790,9 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
             {
                 // (row, x) of slot 0 by two real divisions per tile; every entry then needs only small-number
                 // divisions (float reciprocal + fix-up): slot < 2^11, rows per tile < 2^11
-                const int rho0 = (q0 >= 0) ? q0 / p.P : -((-q0 + p.P - 1) / p.P);
+                const int rho0 = floor_div_m(q0, p.P, p.mg_P);
                 const int x0 = q0 - rho0 * p.P;
-                const int b0 = (rho0 >= 0) ? rho0 / Tp : 0;
+                const int b0 = (rho0 >= 0) ? fast_div(rho0, p.mg_Tp) : 0;
                 const int t0 = rho0 - b0 * Tp;                     // row inside clip b0 (negative before the first clip)
                 for (int e = lt; e < nit * ESTEP; e += T3_LD_THREADS) {
                     const int img = (e >= p.slots) ? 1 : 0;
@@ -828,14 +828,14 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
                 const int img = (p.nimg == 2) ? (lane >> 4) : 0;
                 const int r = (p.nimg == 2) ? (lane & 15) : lane;
                 const int mul = p.img_mul[img], add = p.img_add[img];
-                const int rho0 = (q0 >= 0) ? q0 / p.P : -((-q0 + p.P - 1) / p.P);
+                const int rho0 = floor_div_m(q0, p.P, p.mg_P);
                 const int rho = rho0 + r;
                 const int qs = rho * p.P;                           // flat position of x = 0 of this row
                 const int x_first = (mul == 1) ? -add : ((add < 0) ? (1 - add) / 2 : 0);       // first x with a real source bin
                 const int x_end = (mul == 1) ? p.F_in - add : (p.F_in - add + 1) / 2;          // first x past the last bin
                 int xa = max(q0 - qs, x_first);
                 int xb = min(min(q0 + p.slots - qs, x_end), p.P);
-                const int b = (rho >= 0) ? rho / Tp : 0;
+                const int b = (rho >= 0) ? fast_div(rho, p.mg_Tp) : 0;
                 const int t = rho - b * Tp - p.padrow;
                 if (rho >= 0 && (long long)qs < (long long)p.total_flat && t >= 0 && xb > xa) {
                     const int fi = mul * xa + add;
