@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256) ctfa_ta_sh_kernel(const uint8_t* __restri
         }
         if (lane == 0) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) mean_s[fr][c8 * 8 + e] = s[e] / (float)F;
+            for (int e = 0; e < 8; ++e) mean_s[fr][c8 * 8 + e] = ((F & (F - 1)) == 0) ? s[e] * (1.0f / (float)F) : s[e] / (float)F;
         }
     }
     __syncthreads();
@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(256) ctfa_stream_sh_kernel(const uint8_t* __re
     }
     if (lane == 0) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v_s[c8 * 8 + e] = sum[e] / (float)F;
+        for (int e = 0; e < 8; ++e) v_s[c8 * 8 + e] = ((F & (F - 1)) == 0) ? sum[e] * (1.0f / (float)F) : sum[e] / (float)F;
     }
     __syncthreads();
     if (tid < 64) {
